@@ -1,0 +1,90 @@
+"""ctypes binding of ``libloft_b200.so`` (the C ABI declared in ``include/loft_b200.h``).
+
+There is deliberately no fallback: if the shared library is missing, or a call is made without a
+CUDA device, the product path raises.  Build with ``python -c "import __graft_entry__ as g;
+g.build()"`` or ``make -C bonai_b200/csrc``.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libloft_b200.so')
+
+_lib = None
+
+
+class LoftError(RuntimeError):
+    pass
+
+
+class Epilogue(ctypes.Structure):
+    """Mirror of ``loft_epilogue_t``."""
+    _fields_ = [
+        ('raw_out', ctypes.c_void_p),
+        ('scale', ctypes.c_void_p),
+        ('shift', ctypes.c_void_p),
+        ('residual', ctypes.c_void_p),
+        ('mask', ctypes.c_void_p),
+        ('ldr', ctypes.c_longlong),
+        ('res_upsample2x', ctypes.c_int),
+        ('relu', ctypes.c_int),
+        ('deconv_shuffle', ctypes.c_int),
+    ]
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raise loudly if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LoftError(
+                f'{LIB_PATH} is not built; run `make -C {_HERE}/csrc` (needs nvcc, sm_100a). '
+                'There is no CPU fallback for the LOFT hot path.')
+        _lib = ctypes.CDLL(LIB_PATH)
+        _lib.loft_last_error.restype = ctypes.c_char_p
+    return _lib
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return ctypes.c_void_p(0)
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ll(v):
+    return ctypes.c_longlong(int(v))
+
+
+def f32(v):
+    return ctypes.c_float(float(v))
+
+
+def call(name, *args):
+    """Call ``loft_<name>`` and raise LoftError on a non-zero return code."""
+    fn = getattr(lib(), 'loft_' + name)
+    rc = fn(*args)
+    if rc != 0:
+        msg = lib().loft_last_error()
+        raise LoftError(f'loft_{name} failed ({rc}): {msg.decode() if msg else ""}')
+
+
+def make_epilogue(raw_out=None, scale=None, shift=None, residual=None, mask=None, ldr=0,
+                  res_upsample2x=False, relu=False, deconv_shuffle=False):
+    e = Epilogue()
+    e.raw_out = raw_out.data_ptr() if raw_out is not None else None
+    e.scale = scale.data_ptr() if scale is not None else None
+    e.shift = shift.data_ptr() if shift is not None else None
+    e.residual = residual.data_ptr() if residual is not None else None
+    e.mask = mask.data_ptr() if mask is not None else None
+    e.ldr = int(ldr)
+    e.res_upsample2x = int(bool(res_upsample2x))
+    e.relu = int(bool(relu))
+    e.deconv_shuffle = int(bool(deconv_shuffle))
+    return e

@@ -1,0 +1,782 @@
+// tcgen05 / TMA implicit-GEMM core for every dense contraction on the LOFT path
+// (conv fprop / dgrad / wgrad, Linear, deconv) -- TF32 operands (fp32 in HBM), fp32 accumulate
+// in TMEM.  One persistent warp-specialised kernel, six operand-fetch modes.
+//
+// Orientation: the UMMA "M" side (128 TMEM lanes) is the OUTPUT-CHANNEL axis and the UMMA "N"
+// side (TMEM columns, <=256) is the PIXEL axis, i.e. we compute D[c, p] = sum_k A[c,k] B[p,k].
+// That way an epilogue thread owns one channel: bias / BN scale+shift are one register each and
+// a warp's store for a given pixel is 128 contiguous bytes of the NHWC tensor.
+//
+// Replaces (reference call sites): cuDNN conv fwd/bwd behind torch.nn.Conv2d
+// (mmdet/models/backbones/resnet.py:163-203, necks/fpn.py:116-132, dense_heads/rpn_head.py:26-30,
+// roi_heads/mask_heads/fcn_mask_head.py:64-104, attribute_heads/offset_head_expand_feature.py:72-77)
+// and cuBLAS behind nn.Linear (bbox_heads/convfc_bbox_head.py:118-123,
+// offset_head_expand_feature.py:97-104).
+#include "common.cuh"
+#include "loft_b200.h"
+
+namespace {
+
+constexpr int kStages = 4;
+constexpr int kBlockC = 128;                  // UMMA M: channels per tile
+constexpr int kMaxN = 256;                    // UMMA N max: pixels per tile
+constexpr int kKB = 32;                       // k elements per stage (128 B of fp32)
+constexpr int kABytes = kBlockC * kKB * 4;    // 16 KB
+constexpr int kBBytes = kMaxN * kKB * 4;      // 32 KB
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kThreads = 192;                 // warp0 TMA, warp1 MMA, warps2-5 epilogue
+constexpr int kTmemCols = 512;                // 2 accumulator stages x 256 columns
+
+enum Mode {
+  FPROP_2D = 0,    // A: W[Cout,K] K-major      B: X[P,K] K-major
+  FPROP_CONV = 1,  // A: W[Cout,9*Cin] K-major  B: X[N,H,W,Cin] 4-D boxes shifted per tap
+  DGRAD_2D = 2,    // A: W[Cout,Cin] MN-major (M=cin,k=cout)  B: dY[P,Cout] K-major
+  DGRAD_CONV = 3,  // A: W[Cout,9*Cin] MN-major per tap       B: dY 4-D boxes shifted by -tap
+  WGRAD_2D = 4,    // A: dY[P,Cout] MN-major (M=cout,k=p)     B: X[P,Cin] MN-major
+  WGRAD_CONV = 5,  // same with 5-D boxes; one tap per work item
+};
+
+struct GemmParams {
+  int mode;
+  int nct;        // channel tiles (M side, 128 each)
+  int npt;        // pixel tiles (FPROP/DGRAD) or N-side cin tiles (WGRAD)
+  int num_tiles;  // total work items
+  int num_kb;     // k-blocks per tile (FPROP/DGRAD); total k-blocks (WGRAD)
+  int kb_per_split;
+  int n_mma;  // UMMA N
+  uint32_t tx_bytes;
+  uint64_t a_desc, b_desc;  // smem descriptor templates (address field zero)
+  uint32_t a_kstep, b_kstep;
+  uint32_t idesc;
+  // geometry (pixel side)
+  int N, H, W;      // image batch / height / width of the pixel grid
+  int tn, th, tw;   // pixel tile (conv modes)
+  int tiles_h, tiles_w;
+  int cchunks;      // Cin/32 (FPROP_CONV) or Cout/32 (DGRAD_CONV): k-chunks per tap
+  int ntaps;        // 9 or 1
+  int P;            // total pixels (2D modes)
+  int Cm;           // number of valid channels on the M side (Cout for fprop, Cin for dgrad)
+  int Cn;           // WGRAD: valid columns on the N side (Cin)
+  // epilogue
+  float* out;
+  float* raw_out;
+  const float* scale;
+  const float* shift;
+  const float* residual;
+  const float* mask;
+  long long ldo, ldr;
+  int res_mode;   // 0 none, 1 same pixel, 2 nearest-upsample x2 (residual has H/2 x W/2 pixels)
+  int relu;
+  int out_map;    // 0 plain rows, 1 deconv 2x2/s2 pixel shuffle (out is [N,2H,2W,Cm/4])
+  long long ldw;  // WGRAD: row pitch of dW
+  int tap_stride; // WGRAD_CONV: column offset per tap in dW (= Cin)
+};
+
+struct DebugOverrides {
+  long long a_desc = -1, b_desc = -1;
+  long long a_kstep = -1, b_kstep = -1;
+  long long idesc = -1;
+};
+DebugOverrides g_dbg;
+
+__device__ __forceinline__ void tile_pixel_origin(const GemmParams& p, int ptile, int& n0, int& h0,
+                                                  int& w0) {
+  int twi = ptile % p.tiles_w;
+  int r = ptile / p.tiles_w;
+  int thi = r % p.tiles_h;
+  int tni = r / p.tiles_h;
+  n0 = tni * p.tn;
+  h0 = thi * p.th;
+  w0 = twi * p.tw;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                      const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* full_bar = bars;                    // [kStages]
+  uint64_t* empty_bar = bars + kStages;         // [kStages]
+  uint64_t* tfull_bar = bars + 2 * kStages;     // [2]
+  uint64_t* tempty_bar = bars + 2 * kStages + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const bool is_wgrad = p.mode >= WGRAD_2D;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        int t = tile;
+        const int ct = t % p.nct;
+        t /= p.nct;
+        int pt = t, tap = 0, split = 0;
+        if (is_wgrad) {
+          pt = t % p.npt;
+          t /= p.npt;
+          tap = t % p.ntaps;
+          split = t / p.ntaps;
+        }
+        int kb_begin = 0, kb_count = p.num_kb;
+        if (is_wgrad) {
+          kb_begin = split * p.kb_per_split;
+          kb_count = min(p.kb_per_split, p.num_kb - kb_begin);
+        }
+        int n0 = 0, h0 = 0, w0 = 0;
+        if (p.mode == FPROP_CONV || p.mode == DGRAD_CONV) tile_pixel_origin(p, pt, n0, h0, w0);
+        const int tdh = tap / 3 - 1, tdw = tap % 3 - 1;  // WGRAD_CONV tap shift
+        for (int kbi = 0; kbi < kb_count; ++kbi, ++it) {
+          const int kb = kb_begin + kbi;
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          uint8_t* sa = smem + s * kStageBytes;
+          uint8_t* sb = sa + kABytes;
+          mbar_expect_tx(&full_bar[s], p.tx_bytes);
+          switch (p.mode) {
+            case FPROP_2D:
+              tma_load_2d(sa, &tmap_a, &full_bar[s], kb * kKB, ct * kBlockC);
+              tma_load_2d(sb, &tmap_b, &full_bar[s], kb * kKB, pt * p.n_mma);
+              break;
+            case FPROP_CONV: {
+              const int tp = kb / p.cchunks, ch = kb % p.cchunks;
+              const int dh = (p.ntaps == 9) ? tp / 3 - 1 : 0, dw = (p.ntaps == 9) ? tp % 3 - 1 : 0;
+              tma_load_2d(sa, &tmap_a, &full_bar[s], kb * kKB, ct * kBlockC);
+              tma_load_4d(sb, &tmap_b, &full_bar[s], ch * kKB, w0 + dw, h0 + dh, n0);
+              break;
+            }
+            case DGRAD_2D:
+              // A view: (32 cin, Cout rows, Cin/32 chunks); k-block = 32 cout rows
+              tma_load_3d(sa, &tmap_a, &full_bar[s], 0, kb * kKB, ct * (kBlockC / 32));
+              tma_load_2d(sb, &tmap_b, &full_bar[s], kb * kKB, pt * p.n_mma);
+              break;
+            case DGRAD_CONV: {
+              const int tp = kb / p.cchunks, ch = kb % p.cchunks;
+              const int dh = (p.ntaps == 9) ? tp / 3 - 1 : 0, dw = (p.ntaps == 9) ? tp % 3 - 1 : 0;
+              // A view of W[Cout][ntaps*Cin]: chunk index = (tap*Cin + cin0)/32
+              tma_load_3d(sa, &tmap_a, &full_bar[s], 0, ch * kKB,
+                          tp * (p.tap_stride / 32) + ct * (kBlockC / 32));
+              tma_load_4d(sb, &tmap_b, &full_bar[s], ch * kKB, w0 - dw, h0 - dh, n0);
+              break;
+            }
+            case WGRAD_2D:
+              tma_load_3d(sa, &tmap_a, &full_bar[s], 0, kb * kKB, ct * (kBlockC / 32));
+              tma_load_3d(sb, &tmap_b, &full_bar[s], 0, kb * kKB, pt * (p.n_mma / 32));
+              break;
+            case WGRAD_CONV: {
+              int kn0, kh0, kw0;
+              tile_pixel_origin(p, kb, kn0, kh0, kw0);
+              tma_load_5d(sa, &tmap_a, &full_bar[s], 0, kw0, kh0, kn0, ct * (kBlockC / 32));
+              tma_load_5d(sb, &tmap_b, &full_bar[s], 0, kw0 + tdw, kh0 + tdh, kn0,
+                          pt * (p.n_mma / 32));
+              break;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      uint32_t it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+        int kb_count = p.num_kb;
+        if (is_wgrad) {
+          const int split = tile / (p.nct * p.npt * p.ntaps);
+          kb_count = min(p.kb_per_split, p.num_kb - split * p.kb_per_split);
+        }
+        const uint32_t as = lt & 1u, aph = (lt >> 1) & 1u;
+        mbar_wait(&tempty_bar[as], aph ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * kMaxN;
+        for (int kbi = 0; kbi < kb_count; ++kbi, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * kStageBytes);
+          const uint32_t sb = sa + kABytes;
+          const uint64_t ad = p.a_desc + (uint64_t)((sa >> 4) & 0x3FFFu);
+          const uint64_t bd = p.b_desc + (uint64_t)((sb >> 4) & 0x3FFFu);
+#pragma unroll
+          for (int ks = 0; ks < kKB / 8; ++ks) {
+            umma_tf32(tmem_d, ad + (uint64_t)(ks * p.a_kstep), bd + (uint64_t)(ks * p.b_kstep),
+                      p.idesc, (kbi | ks) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tfull_bar[as]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+      int t = tile;
+      const int ct = t % p.nct;
+      t /= p.nct;
+      int pt = t, tap = 0;
+      if (is_wgrad) {
+        pt = t % p.npt;
+        t /= p.npt;
+        tap = t % p.ntaps;
+      }
+      const uint32_t as = lt & 1u, aph = (lt >> 1) & 1u;
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+      const int c = ct * kBlockC + q * 32 + lane;
+      const bool c_ok = c < p.Cm;
+      const uint32_t taddr = tmem_base + as * kMaxN + ((uint32_t)(q * 32) << 16);
+
+      if (is_wgrad) {
+        float* drow = p.out + (long long)c * p.ldw + (long long)tap * p.tap_stride +
+                      (long long)pt * p.n_mma;
+        const int ncol = min(p.n_mma, p.Cn - pt * p.n_mma);
+        for (int cc = 0; cc < p.n_mma; cc += 16) {
+          float v[16];
+          tmem_ld16(taddr + cc, v);
+          if (c_ok) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (cc + j < ncol) atomicAdd(drow + cc + j, v[j]);
+          }
+        }
+      } else {
+        const float sc = (p.scale != nullptr && c_ok) ? p.scale[c] : 1.f;
+        const float sh = (p.shift != nullptr && c_ok) ? p.shift[c] : 0.f;
+        int n0 = 0, h0 = 0, w0 = 0;
+        const bool conv = (p.mode == FPROP_CONV || p.mode == DGRAD_CONV);
+        if (conv) tile_pixel_origin(p, pt, n0, h0, w0);
+        const int thw = p.th * p.tw;
+        for (int cc = 0; cc < p.n_mma; cc += 16) {
+          float v[16];
+          tmem_ld16(taddr + cc, v);
+          if (!c_ok) continue;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int col = cc + j;
+            long long pix;     // flat pixel index (n*H + h)*W + w
+            int pn, ph_, pw_;  // decoded coordinates (conv / mapped modes)
+            bool ok;
+            if (conv) {
+              const int jn = col / thw, r = col - jn * thw;
+              const int jh = r / p.tw, jw = r - jh * p.tw;
+              pn = n0 + jn;
+              ph_ = h0 + jh;
+              pw_ = w0 + jw;
+              ok = (jn < p.tn) && (pn < p.N) && (ph_ < p.H) && (pw_ < p.W);
+              pix = ((long long)pn * p.H + ph_) * p.W + pw_;
+            } else {
+              pix = (long long)pt * p.n_mma + col;
+              ok = pix < p.P;
+              pn = ph_ = pw_ = 0;
+              if (ok && (p.res_mode == 2 || p.out_map == 1)) {
+                pw_ = (int)(pix % p.W);
+                long long r = pix / p.W;
+                ph_ = (int)(r % p.H);
+                pn = (int)(r / p.H);
+              }
+            }
+            if (!ok) continue;
+            float acc = v[j];
+            long long orow = pix;
+            int ocol = c;
+            if (p.out_map == 1) {
+              // deconv 2x2 stride 2: channel index c = (i*2 + j2)*Co + co
+              const int co_n = p.Cm >> 2;
+              const int ij = c / co_n;
+              ocol = c - ij * co_n;
+              orow = ((long long)pn * (2 * p.H) + (2 * ph_ + (ij >> 1))) * (2 * p.W) +
+                     (2 * pw_ + (ij & 1));
+            }
+            if (p.raw_out != nullptr) p.raw_out[orow * p.ldo + ocol] = acc;
+            acc = fmaf(acc, sc, sh);
+            if (p.res_mode == 1) {
+              acc += p.residual[orow * p.ldr + ocol];
+            } else if (p.res_mode == 2) {
+              const long long rrow =
+                  ((long long)pn * (p.H >> 1) + (ph_ >> 1)) * (p.W >> 1) + (pw_ >> 1);
+              acc += p.residual[rrow * p.ldr + ocol];
+            }
+            if (p.relu) acc = fmaxf(acc, 0.f);
+            if (p.mask != nullptr) acc = (p.mask[orow * p.ldo + ocol] > 0.f) ? acc : 0.f;
+            p.out[orow * p.ldo + ocol] = acc;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+// dims/box are innermost-first; strides (bytes) are for dims 1..rank-1.
+// mn_major selects the 32B-atom 128B swizzle, the only smem layout tcgen05 accepts for MN-major
+// TF32 operands (UMMA LayoutType SWIZZLE_128B_BASE32B); K-major operands use plain SWIZZLE_128B.
+int make_tmap(CUtensorMap* m, int rank, const void* ptr, const uint64_t* dims,
+              const uint64_t* strides, const uint32_t* box, bool mn_major = false) {
+  PFN_encodeTiled enc = get_encode();
+  if (enc == nullptr) {
+    loft_set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return LOFT_ERR_CUDA;
+  }
+  cuuint64_t gd[5];
+  cuuint64_t gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) gs[i - 1] = strides[i - 1];
+    if (box[i] == 0 || box[i] > 256) {
+      loft_set_error("tensor map box dim %d = %u out of range", i, box[i]);
+      return LOFT_ERR_SHAPE;
+    }
+    if (i > 0 && (strides[i - 1] % 16) != 0) {
+      loft_set_error("tensor map stride %d = %llu not a multiple of 16 B", i,
+                     (unsigned long long)strides[i - 1]);
+      return LOFT_ERR_SHAPE;
+    }
+  }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) {
+    loft_set_error("tensor map base pointer not 16 B aligned");
+    return LOFT_ERR_ARG;
+  }
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(ptr), gd,
+                   gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    loft_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank);
+    return LOFT_ERR_CUDA;
+  }
+  return LOFT_OK;
+}
+
+constexpr uint64_t desc_template(uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+  // SmemDescriptor (sm_100): [0,14) addr>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1,
+  // [61,64) layout type (2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B)
+  return ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
+         (1ull << 46) | ((uint64_t)layout_type << 61);
+}
+
+constexpr uint32_t make_idesc(int n_mma, bool a_mn, bool b_mn) {
+  // InstrDescriptor: c_format F32 (1) @4, a_format TF32 (2) @7, b_format TF32 (2) @10,
+  // a_major @15, b_major @16, N>>3 @17, M>>4 @24
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(kBlockC >> 4) << 24);
+}
+
+void fill_descs(GemmParams& p, bool a_mn, bool b_mn) {
+  // K-major SW128: rows of 128 B, 8-row groups 1024 B apart (SBO); LBO unused.
+  // MN-major TF32 (SW128 with 32 B atoms): smem is [chunk][k rows][32 floats]; the swizzle atom
+  //   is 4 k-rows x 128 B = 512 B (SBO), 32-wide MN chunks are kKB*128 B apart (LBO); one
+  //   K=8 MMA consumes two atoms = 1024 B.
+  p.a_desc = a_mn ? desc_template(kKB * 128, 512, 1) : desc_template(16, 1024, 2);
+  p.b_desc = b_mn ? desc_template(kKB * 128, 512, 1) : desc_template(16, 1024, 2);
+  p.a_kstep = a_mn ? (1024 >> 4) : (32 >> 4);
+  p.b_kstep = b_mn ? (1024 >> 4) : (32 >> 4);
+  p.idesc = make_idesc(p.n_mma, a_mn, b_mn);
+  if (g_dbg.a_desc >= 0) p.a_desc = (uint64_t)g_dbg.a_desc;
+  if (g_dbg.b_desc >= 0) p.b_desc = (uint64_t)g_dbg.b_desc;
+  if (g_dbg.a_kstep >= 0) p.a_kstep = (uint32_t)g_dbg.a_kstep;
+  if (g_dbg.b_kstep >= 0) p.b_kstep = (uint32_t)g_dbg.b_kstep;
+  if (g_dbg.idesc >= 0) p.idesc = (uint32_t)g_dbg.idesc;
+}
+
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(loft_gemm_tf32_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) {
+      loft_set_error("gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return LOFT_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  if (p.num_tiles <= 0) return LOFT_OK;
+  int grid = p.num_tiles < loft_num_sms() ? p.num_tiles : loft_num_sms();
+  loft_gemm_tf32_kernel<<<grid, kThreads, kSmemBytes, stream>>>(ta, tb, p);
+  LOFT_CUDA_LAUNCH_CHECK("loft_gemm_tf32_kernel");
+  return LOFT_OK;
+}
+
+int round16(int x) { return (x + 15) & ~15; }
+
+// Pixel tile for the N side of FPROP_CONV / DGRAD_CONV: tn*th*tw <= 256.
+void pick_pixel_tile(int N, int H, int W, int& tn, int& th, int& tw) {
+  tw = W < 16 ? W : 16;
+  th = H < (256 / tw) ? H : (256 / tw);
+  if (th > 16 && tw == 16) th = 16;
+  tn = 256 / (tw * th);
+  if (tn > N) tn = N;
+  if (tn < 1) tn = 1;
+}
+
+// Pixel patch of exactly kKB (=32) positions for the K side of WGRAD_CONV (OOB -> zero fill).
+void pick_k_patch(int H, int W, int& tn, int& th, int& tw) {
+  tw = W > 8 ? 16 : (W > 4 ? 8 : 4);
+  int hmax = kKB / tw;
+  th = 1;
+  while (th < hmax && th < H) th <<= 1;
+  tn = kKB / (tw * th);
+}
+
+void set_epilogue(GemmParams& p, const loft_epilogue_t* e, float* out, long long ldo) {
+  p.out = out;
+  p.ldo = ldo;
+  p.raw_out = e ? e->raw_out : nullptr;
+  p.scale = e ? e->scale : nullptr;
+  p.shift = e ? e->shift : nullptr;
+  p.residual = e ? e->residual : nullptr;
+  p.mask = e ? e->mask : nullptr;
+  p.ldr = e ? (e->ldr ? e->ldr : ldo) : ldo;
+  p.res_mode = (e && e->residual) ? (e->res_upsample2x ? 2 : 1) : 0;
+  p.relu = e ? e->relu : 0;
+  p.out_map = e ? e->deconv_shuffle : 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+void loft_debug_set_desc(long long a_desc, long long b_desc, long long a_kstep, long long b_kstep,
+                         long long idesc) {
+  g_dbg.a_desc = a_desc;
+  g_dbg.b_desc = b_desc;
+  g_dbg.a_kstep = a_kstep;
+  g_dbg.b_kstep = b_kstep;
+  g_dbg.idesc = idesc;
+}
+
+// y[P,Cout] = epi( x[P,K] . w[Cout,K]^T )
+int loft_gemm_fprop(const float* x, const float* w, float* y, long long P, int K, int Cout,
+                    long long ldx, long long ldw, long long ldy, int H, int W,
+                    const loft_epilogue_t* epi, cudaStream_t stream) {
+  LOFT_CHECK_ARG(x && w && y, "gemm_fprop: null pointer");
+  LOFT_CHECK_SHAPE(P >= 0 && K > 0 && Cout > 0, "gemm_fprop: bad sizes P=%lld K=%d Cout=%d", P, K,
+                   Cout);
+  LOFT_CHECK_SHAPE(ldx % 4 == 0 && ldw % 4 == 0, "gemm_fprop: row pitches must be multiples of 4");
+  if (P == 0) return LOFT_OK;
+  GemmParams p{};
+  p.mode = FPROP_2D;
+  p.n_mma = P >= 256 ? 256 : round16((int)P);
+  p.nct = loft_cdiv(Cout, kBlockC);
+  p.npt = loft_cdiv(P, p.n_mma);
+  p.num_tiles = p.nct * p.npt;
+  p.num_kb = loft_cdiv(K, kKB);
+  p.kb_per_split = p.num_kb;
+  p.ntaps = 1;
+  p.tx_bytes = kABytes + p.n_mma * kKB * 4;
+  p.P = (int)P;
+  p.Cm = Cout;
+  p.N = 1;
+  p.H = H > 0 ? H : 1;
+  p.W = W > 0 ? W : (int)P;
+  fill_descs(p, false, false);
+  set_epilogue(p, epi, y, ldy);
+  CUtensorMap ta, tb;
+  {
+    uint64_t d[2] = {(uint64_t)K, (uint64_t)Cout};
+    uint64_t s[1] = {(uint64_t)ldw * 4};
+    uint32_t b[2] = {kKB, kBlockC};
+    int r = make_tmap(&ta, 2, w, d, s, b);
+    if (r) return r;
+  }
+  {
+    uint64_t d[2] = {(uint64_t)K, (uint64_t)P};
+    uint64_t s[1] = {(uint64_t)ldx * 4};
+    uint32_t b[2] = {kKB, (uint32_t)p.n_mma};
+    int r = make_tmap(&tb, 2, x, d, s, b);
+    if (r) return r;
+  }
+  return launch(ta, tb, p, stream);
+}
+
+// dx[P,Cin] = maskrelu( dy[P,Cout] . w[Cout,Cin] )
+int loft_gemm_dgrad(const float* dy, const float* w, float* dx, long long P, int Cin, int Cout,
+                    long long lddy, long long ldw, long long lddx, const loft_epilogue_t* epi,
+                    cudaStream_t stream) {
+  LOFT_CHECK_ARG(dy && w && dx, "gemm_dgrad: null pointer");
+  LOFT_CHECK_SHAPE(Cin % 32 == 0, "gemm_dgrad: Cin=%d must be a multiple of 32", Cin);
+  LOFT_CHECK_SHAPE(lddy % 4 == 0 && ldw % 4 == 0, "gemm_dgrad: row pitches must be multiples of 4");
+  if (P == 0) return LOFT_OK;
+  GemmParams p{};
+  p.mode = DGRAD_2D;
+  p.n_mma = P >= 256 ? 256 : round16((int)P);
+  p.nct = loft_cdiv(Cin, kBlockC);
+  p.npt = loft_cdiv(P, p.n_mma);
+  p.num_tiles = p.nct * p.npt;
+  p.num_kb = loft_cdiv(Cout, kKB);
+  p.kb_per_split = p.num_kb;
+  p.ntaps = 1;
+  p.tx_bytes = kABytes + p.n_mma * kKB * 4;
+  p.P = (int)P;
+  p.Cm = Cin;
+  p.N = 1;
+  p.H = 1;
+  p.W = (int)P;
+  fill_descs(p, true, false);
+  set_epilogue(p, epi, dx, lddx);
+  CUtensorMap ta, tb;
+  {
+    uint64_t d[3] = {32, (uint64_t)Cout, (uint64_t)(Cin / 32)};
+    uint64_t s[2] = {(uint64_t)ldw * 4, 128};
+    uint32_t b[3] = {32, kKB, kBlockC / 32};
+    int r = make_tmap(&ta, 3, w, d, s, b, true);
+    if (r) return r;
+  }
+  {
+    uint64_t d[2] = {(uint64_t)Cout, (uint64_t)P};
+    uint64_t s[1] = {(uint64_t)lddy * 4};
+    uint32_t b[2] = {kKB, (uint32_t)p.n_mma};
+    int r = make_tmap(&tb, 2, dy, d, s, b);
+    if (r) return r;
+  }
+  return launch(ta, tb, p, stream);
+}
+
+// dw[Cout,Cin] += dy[P,Cout]^T . x[P,Cin]   (atomic accumulate; caller zero-fills once per step)
+int loft_gemm_wgrad(const float* dy, const float* x, float* dw, long long P, int Cin, int Cout,
+                    long long lddy, long long ldx, long long lddw, cudaStream_t stream) {
+  LOFT_CHECK_ARG(dy && x && dw, "gemm_wgrad: null pointer");
+  LOFT_CHECK_SHAPE(Cin % 32 == 0 && Cout % 32 == 0,
+                   "gemm_wgrad: Cin=%d and Cout=%d must be multiples of 32", Cin, Cout);
+  LOFT_CHECK_SHAPE(lddy % 4 == 0 && ldx % 4 == 0, "gemm_wgrad: row pitches must be multiples of 4");
+  if (P == 0) return LOFT_OK;
+  GemmParams p{};
+  p.mode = WGRAD_2D;
+  p.n_mma = Cin >= 256 ? 256 : Cin;  // multiple of 32
+  p.nct = loft_cdiv(Cout, kBlockC);
+  p.npt = loft_cdiv(Cin, p.n_mma);
+  p.ntaps = 1;
+  p.num_kb = loft_cdiv(P, kKB);
+  int base = p.nct * p.npt;
+  int splits = loft_num_sms() / base;
+  if (splits < 1) splits = 1;
+  if (splits > p.num_kb) splits = p.num_kb;
+  p.kb_per_split = loft_cdiv(p.num_kb, splits);
+  splits = loft_cdiv(p.num_kb, p.kb_per_split);
+  p.num_tiles = base * splits;
+  p.tx_bytes = kABytes + p.n_mma * kKB * 4;
+  p.Cm = Cout;
+  p.Cn = Cin;
+  p.ldw = lddw;
+  p.tap_stride = 0;
+  p.out = dw;
+  fill_descs(p, true, true);
+  CUtensorMap ta, tb;
+  {
+    uint64_t d[3] = {32, (uint64_t)P, (uint64_t)(Cout / 32)};
+    uint64_t s[2] = {(uint64_t)lddy * 4, 128};
+    uint32_t b[3] = {32, kKB, kBlockC / 32};
+    int r = make_tmap(&ta, 3, dy, d, s, b, true);
+    if (r) return r;
+  }
+  {
+    uint64_t d[3] = {32, (uint64_t)P, (uint64_t)(Cin / 32)};
+    uint64_t s[2] = {(uint64_t)ldx * 4, 128};
+    uint32_t b[3] = {32, kKB, (uint32_t)(p.n_mma / 32)};
+    int r = make_tmap(&tb, 3, x, d, s, b, true);
+    if (r) return r;
+  }
+  return launch(ta, tb, p, stream);
+}
+
+// 3x3 / pad 1 / stride 1 convolution over NHWC, weights [Cout][3][3][Cin].
+int loft_conv3x3_fprop(const float* x, const float* w, float* y, int N, int H, int W, int Cin,
+                       int Cout, const loft_epilogue_t* epi, cudaStream_t stream) {
+  LOFT_CHECK_ARG(x && w && y, "conv3x3_fprop: null pointer");
+  LOFT_CHECK_SHAPE(Cin % 32 == 0, "conv3x3_fprop: Cin=%d must be a multiple of 32", Cin);
+  if (N == 0) return LOFT_OK;
+  GemmParams p{};
+  p.mode = FPROP_CONV;
+  pick_pixel_tile(N, H, W, p.tn, p.th, p.tw);
+  p.n_mma = round16(p.tn * p.th * p.tw);
+  p.tiles_w = loft_cdiv(W, p.tw);
+  p.tiles_h = loft_cdiv(H, p.th);
+  p.nct = loft_cdiv(Cout, kBlockC);
+  p.npt = p.tiles_w * p.tiles_h * loft_cdiv(N, p.tn);
+  p.num_tiles = p.nct * p.npt;
+  p.cchunks = Cin / 32;
+  p.ntaps = 9;
+  p.num_kb = 9 * p.cchunks;
+  p.kb_per_split = p.num_kb;
+  p.tx_bytes = kABytes + p.tn * p.th * p.tw * kKB * 4;
+  p.N = N;
+  p.H = H;
+  p.W = W;
+  p.Cm = Cout;
+  fill_descs(p, false, false);
+  set_epilogue(p, epi, y, Cout);
+  CUtensorMap ta, tb;
+  {
+    uint64_t d[2] = {(uint64_t)9 * Cin, (uint64_t)Cout};
+    uint64_t s[1] = {(uint64_t)9 * Cin * 4};
+    uint32_t b[2] = {kKB, kBlockC};
+    int r = make_tmap(&ta, 2, w, d, s, b);
+    if (r) return r;
+  }
+  {
+    uint64_t d[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    uint64_t s[3] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4};
+    uint32_t b[4] = {kKB, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.tn};
+    int r = make_tmap(&tb, 4, x, d, s, b);
+    if (r) return r;
+  }
+  return launch(ta, tb, p, stream);
+}
+
+int loft_conv3x3_dgrad(const float* dy, const float* w, float* dx, int N, int H, int W, int Cin,
+                       int Cout, const loft_epilogue_t* epi, cudaStream_t stream) {
+  LOFT_CHECK_ARG(dy && w && dx, "conv3x3_dgrad: null pointer");
+  LOFT_CHECK_SHAPE(Cin % 32 == 0 && Cout % 4 == 0,
+                   "conv3x3_dgrad: Cin=%d must be a multiple of 32, Cout=%d of 4", Cin, Cout);
+  if (N == 0) return LOFT_OK;
+  GemmParams p{};
+  p.mode = DGRAD_CONV;
+  pick_pixel_tile(N, H, W, p.tn, p.th, p.tw);
+  p.n_mma = round16(p.tn * p.th * p.tw);
+  p.tiles_w = loft_cdiv(W, p.tw);
+  p.tiles_h = loft_cdiv(H, p.th);
+  p.nct = loft_cdiv(Cin, kBlockC);
+  p.npt = p.tiles_w * p.tiles_h * loft_cdiv(N, p.tn);
+  p.num_tiles = p.nct * p.npt;
+  p.cchunks = loft_cdiv(Cout, 32);
+  p.ntaps = 9;
+  p.num_kb = 9 * p.cchunks;
+  p.kb_per_split = p.num_kb;
+  p.tx_bytes = kABytes + p.tn * p.th * p.tw * kKB * 4;
+  p.N = N;
+  p.H = H;
+  p.W = W;
+  p.Cm = Cin;
+  p.tap_stride = Cin;
+  fill_descs(p, true, false);
+  set_epilogue(p, epi, dx, Cin);
+  CUtensorMap ta, tb;
+  {
+    uint64_t d[3] = {32, (uint64_t)Cout, (uint64_t)(9 * Cin / 32)};
+    uint64_t s[2] = {(uint64_t)9 * Cin * 4, 128};
+    uint32_t b[3] = {32, kKB, kBlockC / 32};
+    int r = make_tmap(&ta, 3, w, d, s, b, true);
+    if (r) return r;
+  }
+  {
+    uint64_t d[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    uint64_t s[3] = {(uint64_t)Cout * 4, (uint64_t)W * Cout * 4, (uint64_t)H * W * Cout * 4};
+    uint32_t b[4] = {kKB, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.tn};
+    int r = make_tmap(&tb, 4, dy, d, s, b);
+    if (r) return r;
+  }
+  return launch(ta, tb, p, stream);
+}
+
+int loft_conv3x3_wgrad(const float* dy, const float* x, float* dw, int N, int H, int W, int Cin,
+                       int Cout, cudaStream_t stream) {
+  LOFT_CHECK_ARG(dy && x && dw, "conv3x3_wgrad: null pointer");
+  LOFT_CHECK_SHAPE(Cin % 32 == 0 && Cout % 32 == 0,
+                   "conv3x3_wgrad: Cin=%d and Cout=%d must be multiples of 32", Cin, Cout);
+  if (N == 0) return LOFT_OK;
+  GemmParams p{};
+  p.mode = WGRAD_CONV;
+  pick_k_patch(H, W, p.tn, p.th, p.tw);
+  p.tiles_w = loft_cdiv(W, p.tw);
+  p.tiles_h = loft_cdiv(H, p.th);
+  p.n_mma = Cin >= 256 ? 256 : Cin;
+  p.nct = loft_cdiv(Cout, kBlockC);
+  p.npt = loft_cdiv(Cin, p.n_mma);
+  p.ntaps = 9;
+  p.num_kb = p.tiles_w * p.tiles_h * loft_cdiv(N, p.tn);
+  int base = p.nct * p.npt * 9;
+  int splits = loft_cdiv(loft_num_sms(), base);
+  if (splits > p.num_kb) splits = p.num_kb;
+  p.kb_per_split = loft_cdiv(p.num_kb, splits);
+  splits = loft_cdiv(p.num_kb, p.kb_per_split);
+  p.num_tiles = base * splits;
+  p.tx_bytes = kABytes + p.n_mma * kKB * 4;
+  p.N = N;
+  p.H = H;
+  p.W = W;
+  p.Cm = Cout;
+  p.Cn = Cin;
+  p.ldw = (long long)9 * Cin;
+  p.tap_stride = Cin;
+  p.out = dw;
+  fill_descs(p, true, true);
+  CUtensorMap ta, tb;
+  {
+    uint64_t d[5] = {32, (uint64_t)W, (uint64_t)H, (uint64_t)N, (uint64_t)(Cout / 32)};
+    uint64_t s[4] = {(uint64_t)Cout * 4, (uint64_t)W * Cout * 4, (uint64_t)H * W * Cout * 4, 128};
+    uint32_t b[5] = {32, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.tn, kBlockC / 32};
+    int r = make_tmap(&ta, 5, dy, d, s, b, true);
+    if (r) return r;
+  }
+  {
+    uint64_t d[5] = {32, (uint64_t)W, (uint64_t)H, (uint64_t)N, (uint64_t)(Cin / 32)};
+    uint64_t s[4] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4, 128};
+    uint32_t b[5] = {32, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.tn, (uint32_t)(p.n_mma / 32)};
+    int r = make_tmap(&tb, 5, x, d, s, b, true);
+    if (r) return r;
+  }
+  return launch(ta, tb, p, stream);
+}
+
+}  // extern "C"

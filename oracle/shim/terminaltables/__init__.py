@@ -1,0 +1,3 @@
+from _shim_dummy import install_getattr as _ig
+
+_ig(globals(), 'terminaltables')
