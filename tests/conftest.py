@@ -1,0 +1,34 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
+
+
+def pytest_collection_modifyitems(config, items):
+    import torch
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason='no CUDA device')
+    for item in items:
+        if 'gpu' in item.keywords:
+            item.add_marker(skip)
+
+
+@pytest.fixture(scope='session')
+def golden_units():
+    import numpy as np
+    return dict(np.load(os.path.join(ROOT, 'tests', 'golden', 'units.npz')))
+
+
+@pytest.fixture(scope='session')
+def golden_step():
+    import numpy as np
+    return dict(np.load(os.path.join(ROOT, 'tests', 'golden', 'loft_step_256.npz')))
