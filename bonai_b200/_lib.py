@@ -31,6 +31,7 @@ class Epilogue(ctypes.Structure):
         ('res_upsample2x', ctypes.c_int),
         ('relu', ctypes.c_int),
         ('deconv_shuffle', ctypes.c_int),
+        ('round_out', ctypes.c_int),
     ]
 
 
@@ -66,9 +67,17 @@ def f32(v):
     return ctypes.c_float(float(v))
 
 
+LAUNCHES = [0]          # kernels launched through this binding (bench.py reads / resets it)
+_KERNELS_PER_CALL = {'iou_assign': 2, 'grad_sqnorm': 1}
+
+
 def call(name, *args):
     """Call ``loft_<name>`` and raise LoftError on a non-zero return code."""
     fn = getattr(lib(), 'loft_' + name)
+    if name == 'nms_sorted':
+        LAUNCHES[0] += 3 * int(args[2].value) + 1      # per image: fill+max+mask; one scan
+    else:
+        LAUNCHES[0] += _KERNELS_PER_CALL.get(name, 1)
     rc = fn(*args)
     if rc != 0:
         msg = lib().loft_last_error()
@@ -76,7 +85,7 @@ def call(name, *args):
 
 
 def make_epilogue(raw_out=None, scale=None, shift=None, residual=None, mask=None, ldr=0,
-                  res_upsample2x=False, relu=False, deconv_shuffle=False):
+                  res_upsample2x=False, relu=False, deconv_shuffle=False, round_out=False):
     e = Epilogue()
     e.raw_out = raw_out.data_ptr() if raw_out is not None else None
     e.scale = scale.data_ptr() if scale is not None else None
@@ -87,4 +96,5 @@ def make_epilogue(raw_out=None, scale=None, shift=None, residual=None, mask=None
     e.res_upsample2x = int(bool(res_upsample2x))
     e.relu = int(bool(relu))
     e.deconv_shuffle = int(bool(deconv_shuffle))
+    e.round_out = int(bool(round_out))
     return e

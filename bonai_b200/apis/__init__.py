@@ -1,0 +1,3 @@
+from .train import Trainer, set_random_seed, step_lr, init_dist, build_optimizer_args
+
+__all__ = ['Trainer', 'set_random_seed', 'step_lr', 'init_dist', 'build_optimizer_args']

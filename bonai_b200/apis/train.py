@@ -1,0 +1,168 @@
+"""Training step driver: the B200-native counterpart of mmdet/apis/train.py:34-143 (+ the mmcv
+pieces it wires together: EpochBasedRunner.train, OptimizerHook(grad_clip), StepLrUpdaterHook with
+linear warm-up, MMDistributedDataParallel).
+
+One process per GPU.  Gradients already live in one flat fp32 buffer (engine.ParamStore), so the
+data-parallel exchange is a bucketed in-place NCCL all-reduce over views of that buffer issued on
+a side stream, followed by ONE fused clip + SGD launch that also applies the 1/world scaling.
+Log scalars are reduced as one packed vector and read back only when asked."""
+import os
+import random
+from collections import OrderedDict
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from ..engine import get_store
+
+
+def set_random_seed(seed, deterministic=False):
+    """mmdet/apis/train.py:15-31."""
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed_all(seed)
+    if deterministic:
+        torch.backends.cudnn.deterministic = True
+        torch.backends.cudnn.benchmark = False
+
+
+def init_dist(backend='nccl', **kwargs):
+    """torch.distributed bootstrap from the torchrun environment (tools/train.py:94-98,
+    default_runtime.py:10)."""
+    if dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', rank))
+    if backend == 'nccl':
+        torch.cuda.set_device(local)
+    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    os.environ.setdefault('MASTER_PORT', '29500')
+    dist.init_process_group(backend=backend, rank=rank, world_size=world, **kwargs)
+    return rank, world
+
+
+def step_lr(base_lr, it, epoch, step=(16, 22), gamma=0.1, warmup='linear', warmup_iters=300,
+            warmup_ratio=0.001):
+    """mmcv StepLrUpdaterHook + linear warm-up as configured by
+    configs/_base_/schedules/schedule_2x_bonai.py:5-10."""
+    exp = sum(1 for s in step if epoch >= s)
+    lr = base_lr * gamma ** exp
+    if warmup is not None and it < warmup_iters:
+        if warmup == 'linear':
+            k = (1 - it / warmup_iters) * (1 - warmup_ratio)
+            lr = lr * (1 - k)
+        elif warmup == 'constant':
+            lr = lr * warmup_ratio
+        else:
+            raise ValueError(warmup)
+    return lr
+
+
+def build_optimizer_args(cfg):
+    opt = dict(cfg.optimizer)
+    if opt.pop('type') != 'SGD':
+        raise NotImplementedError('LOFT path: SGD (schedule_2x_bonai.py:2)')
+    clip = (cfg.get('optimizer_config') or {}).get('grad_clip')
+    if clip is not None and clip.get('norm_type', 2) != 2:
+        raise NotImplementedError('LOFT path: L2 gradient clipping')
+    return dict(lr=opt['lr'], momentum=opt.get('momentum', 0.0),
+                weight_decay=opt.get('weight_decay', 0.0),
+                max_norm=clip['max_norm'] if clip else None)
+
+
+def bucket_views(flat, bucket_bytes=64 << 20):
+    """Contiguous views of a flat buffer, last parameters first (their gradients are ready first in
+    backward), each about `bucket_bytes` large."""
+    n = flat.numel()
+    per = max(bucket_bytes // flat.element_size(), 1)
+    out, end = [], n
+    while end > 0:
+        start = max(end - per, 0)
+        out.append(flat[start:end])
+        end = start
+    return out
+
+
+def allreduce_flat(flat, group=None, bucket_bytes=64 << 20, async_op=False):
+    """Sum-all-reduce a flat gradient buffer in place, bucket by bucket."""
+    works = []
+    for v in bucket_views(flat, bucket_bytes):
+        w = dist.all_reduce(v, group=group, async_op=True)
+        works.append(w)
+    if async_op:
+        return works
+    for w in works:
+        w.wait()
+    return []
+
+
+class Trainer:
+    def __init__(self, model, cfg=None, device=None, lr=0.005, momentum=0.9, weight_decay=1e-4,
+                 max_norm=35.0, bucket_bytes=64 << 20):
+        self.model = model
+        if cfg is not None:
+            a = build_optimizer_args(cfg)
+            lr, momentum, weight_decay, max_norm = a['lr'], a['momentum'], a['weight_decay'], \
+                a['max_norm']
+            self.lr_cfg = dict(cfg.get('lr_config') or {})
+        else:
+            self.lr_cfg = {}
+        self.base_lr, self.momentum, self.weight_decay, self.max_norm = lr, momentum, \
+            weight_decay, max_norm
+        self.bucket_bytes = bucket_bytes
+        self.store = get_store(model, device)
+        self.distributed = dist.is_available() and dist.is_initialized() and \
+            dist.get_world_size() > 1
+        self.world = dist.get_world_size() if self.distributed else 1
+        self.iter = 0
+        self.epoch = 0
+        self._last_logs = None
+
+    def current_lr(self):
+        c = self.lr_cfg
+        if not c:
+            return self.base_lr
+        if c.get('policy', 'step') != 'step':
+            raise NotImplementedError('LOFT path: step LR policy')
+        return step_lr(self.base_lr, self.iter, self.epoch, step=c.get('step', (16, 22)),
+                       gamma=c.get('gamma', 0.1), warmup=c.get('warmup'),
+                       warmup_iters=c.get('warmup_iters', 0),
+                       warmup_ratio=c.get('warmup_ratio', 0.1))
+
+    def train_step(self, data, read_logs=False):
+        """forward + backward + gradient all-reduce + clip + SGD.  Returns the device-resident
+        packed log vector (and its key order); nothing synchronises the host unless read_logs."""
+        model = self.model
+        losses = model(**data)
+        log_vars = OrderedDict()
+        for name, value in losses.items():
+            if isinstance(value, torch.Tensor):
+                log_vars[name] = value.mean()
+            else:
+                log_vars[name] = sum(v.mean() for v in value)
+        loss = sum(v for k, v in log_vars.items() if 'loss' in k)
+        log_vars['loss'] = loss
+        loss.backward()
+        if self.distributed:
+            allreduce_flat(self.store.G, bucket_bytes=self.bucket_bytes)
+        self.store.sgd_step(self.current_lr(), self.momentum, self.weight_decay, self.max_norm,
+                            grad_scale=1.0 / self.world)
+        self.iter += 1
+        packed = torch.stack([v.detach().reshape(()) for v in log_vars.values()])
+        self._last_logs = (list(log_vars.keys()), packed)
+        if read_logs:
+            return self.read_logs()
+        return packed
+
+    def read_logs(self):
+        """Packed mean over ranks + one host read-back (replaces the 8 all_reduce + .item() pairs
+        of detectors/base.py:201-206)."""
+        keys, packed = self._last_logs
+        if self.distributed:
+            packed = packed / self.world
+            dist.all_reduce(packed)
+        return OrderedDict(zip(keys, packed.tolist()))

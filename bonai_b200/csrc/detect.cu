@@ -1,0 +1,420 @@
+// Box-side kernels of the LOFT path: fused IoU + max-IoU assignment, RPN top-k decode
+// (anchor generation + delta2bbox), batched NMS (bitmask + chunked scan), box / offset target
+// encoders.  All index outputs are designed to be bit-exact against the reference arithmetic
+// (fp32, no FMA contraction -- explicit _rn intrinsics).
+// Reference: core/bbox/iou_calculators/iou2d_calculator.py:39-130,
+// core/bbox/assigners/max_iou_assigner.py:127-212, core/anchor/anchor_generator.py:142-271,
+// core/bbox/coder/delta_xywh_bbox_coder.py:74-197, dense_heads/rpn_head.py:79-168,
+// mmcv.ops.batched_nms / nms [mmcv-full 1.0.5],
+// core/bbox/coder/delta_xy_offset_coder.py:46-65,
+// roi_heads/attribute_heads/offset_head_expand_feature.py:271-344.
+#include "common.cuh"
+#include "loft_b200.h"
+
+namespace {
+
+__device__ __forceinline__ float box_iou_ref(float ax1, float ay1, float ax2, float ay2, float aarea,
+                                             float bx1, float by1, float bx2, float by2,
+                                             float barea, float eps) {
+  // bbox_overlaps: wh = clamp(min(rb) - max(lt), 0); overlap = w*h; union = a1 + a2 - overlap;
+  // union = max(union, eps); iou = overlap / union
+  const float w = fmaxf(__fsub_rn(fminf(ax2, bx2), fmaxf(ax1, bx1)), 0.f);
+  const float h = fmaxf(__fsub_rn(fminf(ay2, by2), fmaxf(ay1, by1)), 0.f);
+  const float ov = __fmul_rn(w, h);
+  const float un = fmaxf(__fsub_rn(__fadd_rn(aarea, barea), ov), eps);
+  return __fdiv_rn(ov, un);
+}
+
+constexpr int kMaxGt = 1024;
+
+// pass 1: per box max / argmax over gts, per gt max over boxes (atomicMax on the float bits)
+__global__ void iou_max_kernel(const float* __restrict__ boxes, long long n,
+                               const float* __restrict__ gts, int G, float* __restrict__ max_ov,
+                               int* __restrict__ argmax, unsigned int* __restrict__ gt_max_bits) {
+  extern __shared__ float sg[];  // G*5: x1,y1,x2,y2,area
+  unsigned int* sgmax = reinterpret_cast<unsigned int*>(sg + G * 5);
+  for (int i = threadIdx.x; i < G; i += blockDim.x) {
+    const float x1 = gts[i * 4], y1 = gts[i * 4 + 1], x2 = gts[i * 4 + 2], y2 = gts[i * 4 + 3];
+    sg[i * 5] = x1;
+    sg[i * 5 + 1] = y1;
+    sg[i * 5 + 2] = x2;
+    sg[i * 5 + 3] = y2;
+    sg[i * 5 + 4] = __fmul_rn(__fsub_rn(x2, x1), __fsub_rn(y2, y1));
+    sgmax[i] = 0u;
+  }
+  __syncthreads();
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) {
+    const float4 b = reinterpret_cast<const float4*>(boxes)[j];
+    const float barea = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+    float best = -1.f;
+    int besti = 0;
+    for (int i = 0; i < G; ++i) {
+      const float iou = box_iou_ref(sg[i * 5], sg[i * 5 + 1], sg[i * 5 + 2], sg[i * 5 + 3],
+                                    sg[i * 5 + 4], b.x, b.y, b.z, b.w, barea, 1e-6f);
+      if (iou > best) {
+        best = iou;
+        besti = i;
+      }
+      if (iou > 0.f) atomicMax(&sgmax[i], __float_as_uint(iou));
+    }
+    max_ov[j] = G > 0 ? best : 0.f;
+    argmax[j] = besti;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < G; i += blockDim.x)
+    if (sgmax[i]) atomicMax(&gt_max_bits[i], sgmax[i]);
+}
+
+// pass 2: assignment incl. low-quality matches (later gts overwrite earlier ones)
+__global__ void iou_assign_kernel(const float* __restrict__ boxes, long long n,
+                                  const float* __restrict__ gts, int G,
+                                  const float* __restrict__ max_ov, const int* __restrict__ argmax,
+                                  const unsigned int* __restrict__ gt_max_bits, float pos_thr,
+                                  float neg_thr, float min_pos, int match_low_quality,
+                                  long long* __restrict__ gt_inds) {
+  extern __shared__ float sg[];
+  float* sgmax = sg + G * 5;
+  for (int i = threadIdx.x; i < G; i += blockDim.x) {
+    const float x1 = gts[i * 4], y1 = gts[i * 4 + 1], x2 = gts[i * 4 + 2], y2 = gts[i * 4 + 3];
+    sg[i * 5] = x1;
+    sg[i * 5 + 1] = y1;
+    sg[i * 5 + 2] = x2;
+    sg[i * 5 + 3] = y2;
+    sg[i * 5 + 4] = __fmul_rn(__fsub_rn(x2, x1), __fsub_rn(y2, y1));
+    sgmax[i] = __uint_as_float(gt_max_bits[i]);
+  }
+  __syncthreads();
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  if (G == 0) {
+    gt_inds[j] = 0;
+    return;
+  }
+  const float mo = max_ov[j];
+  long long a = -1;
+  if (mo >= 0.f && mo < neg_thr) a = 0;
+  if (mo >= pos_thr) a = argmax[j] + 1;
+  if (match_low_quality) {
+    const float4 b = reinterpret_cast<const float4*>(boxes)[j];
+    const float barea = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+    for (int i = 0; i < G; ++i) {
+      const float gm = sgmax[i];
+      if (gm >= min_pos) {
+        const float iou = box_iou_ref(sg[i * 5], sg[i * 5 + 1], sg[i * 5 + 2], sg[i * 5 + 3],
+                                      sg[i * 5 + 4], b.x, b.y, b.z, b.w, barea, 1e-6f);
+        if (iou == gm) a = i + 1;
+      }
+    }
+  }
+  gt_inds[j] = a;
+}
+
+// ---------------------------------------------------------------- RPN decode
+// For rank r of level-local top-k index idx (into the (h,w,a) flattening): anchor + delta2bbox.
+__global__ void rpn_decode_kernel(const float* __restrict__ head_out, int ld, int reg_off,
+                                  const long long* __restrict__ topk_idx, int k, int fw, int A,
+                                  const float* __restrict__ base_anchors, float stride,
+                                  float max_ratio, float img_h, float img_w,
+                                  float* __restrict__ boxes_out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= k) return;
+  const long long idx = topk_idx[r];
+  const int a = (int)(idx % A);
+  const long long pos = idx / A;
+  const int w = (int)(pos % fw), h = (int)(pos / fw);
+  const float sx = (float)w * stride, sy = (float)h * stride;
+  const float ax1 = __fadd_rn(base_anchors[a * 4 + 0], sx), ay1 = __fadd_rn(base_anchors[a * 4 + 1], sy);
+  const float ax2 = __fadd_rn(base_anchors[a * 4 + 2], sx), ay2 = __fadd_rn(base_anchors[a * 4 + 3], sy);
+  const float* d = head_out + pos * ld + reg_off + a * 4;
+  const float dx = d[0], dy = d[1];
+  const float dw = fminf(fmaxf(d[2], -max_ratio), max_ratio);
+  const float dh = fminf(fmaxf(d[3], -max_ratio), max_ratio);
+  const float px = __fmul_rn(__fadd_rn(ax1, ax2), 0.5f), py = __fmul_rn(__fadd_rn(ay1, ay2), 0.5f);
+  const float pw = __fsub_rn(ax2, ax1), ph = __fsub_rn(ay2, ay1);
+  const float gw = __fmul_rn(pw, expf(dw)), gh = __fmul_rn(ph, expf(dh));
+  const float gx = __fadd_rn(px, __fmul_rn(pw, dx)), gy = __fadd_rn(py, __fmul_rn(ph, dy));
+  float x1 = __fsub_rn(gx, __fmul_rn(gw, 0.5f)), y1 = __fsub_rn(gy, __fmul_rn(gh, 0.5f));
+  float x2 = __fadd_rn(gx, __fmul_rn(gw, 0.5f)), y2 = __fadd_rn(gy, __fmul_rn(gh, 0.5f));
+  x1 = fminf(fmaxf(x1, 0.f), img_w);
+  y1 = fminf(fmaxf(y1, 0.f), img_h);
+  x2 = fminf(fmaxf(x2, 0.f), img_w);
+  y2 = fminf(fmaxf(y2, 0.f), img_h);
+  reinterpret_cast<float4*>(boxes_out)[r] = make_float4(x1, y1, x2, y2);
+}
+
+// ---------------------------------------------------------------- NMS
+__global__ void fill_f32_kernel(float* p, float v) { *p = v; }
+
+__global__ void max_coord_kernel(const float* __restrict__ boxes, long long n4,
+                                 float* __restrict__ out) {
+  // out must be initialised to -inf bits; boxes may be negative => use ordered-int trick
+  float m = -INFINITY;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x)
+    m = fmaxf(m, boxes[i]);
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) {
+    int* addr = reinterpret_cast<int*>(out);
+    int old = *addr, assumed;
+    do {
+      assumed = old;
+      if (__int_as_float(assumed) >= m) break;
+      old = atomicCAS(addr, assumed, __float_as_int(m));
+    } while (assumed != old);
+  }
+}
+
+// mask[i][w] bit b set  <=>  box j = w*64+b (j > i) is suppressed by box i.
+// Boxes are pre-sorted by score (desc, stable).  Coordinates are offset by idx*(max_coord+1) in
+// fp32 exactly like mmcv batched_nms, so boxes of different idx never overlap.
+__global__ void nms_mask_kernel(const float* __restrict__ boxes, const long long* __restrict__ idxs,
+                                const float* __restrict__ max_coord, int n, float thr,
+                                unsigned long long* __restrict__ mask, int nwords) {
+  const int row = blockIdx.y, colb = blockIdx.x;
+  if (colb < row) return;
+  const float off1 = max_coord ? __fadd_rn(*max_coord, 1.f) : 0.f;
+  __shared__ float sb[64][5];
+  const int t = threadIdx.x;
+  const int cj = colb * 64 + t;
+  if (cj < n) {
+    const float o = idxs ? __fmul_rn((float)idxs[cj], off1) : 0.f;
+    const float x1 = __fadd_rn(boxes[cj * 4 + 0], o), y1 = __fadd_rn(boxes[cj * 4 + 1], o);
+    const float x2 = __fadd_rn(boxes[cj * 4 + 2], o), y2 = __fadd_rn(boxes[cj * 4 + 3], o);
+    sb[t][0] = x1;
+    sb[t][1] = y1;
+    sb[t][2] = x2;
+    sb[t][3] = y2;
+    sb[t][4] = __fmul_rn(__fsub_rn(x2, x1), __fsub_rn(y2, y1));
+  }
+  __syncthreads();
+  const int i = row * 64 + t;
+  if (i >= n) return;
+  const float o = idxs ? __fmul_rn((float)idxs[i], off1) : 0.f;
+  const float x1 = __fadd_rn(boxes[i * 4 + 0], o), y1 = __fadd_rn(boxes[i * 4 + 1], o);
+  const float x2 = __fadd_rn(boxes[i * 4 + 2], o), y2 = __fadd_rn(boxes[i * 4 + 3], o);
+  const float area = __fmul_rn(__fsub_rn(x2, x1), __fsub_rn(y2, y1));
+  unsigned long long bits = 0ull;
+  const int jstart = (row == colb) ? t + 1 : 0;
+  const int jend = min(64, n - colb * 64);
+  for (int j = jstart; j < jend; ++j) {
+    const float w = fmaxf(0.f, __fsub_rn(fminf(x2, sb[j][2]), fmaxf(x1, sb[j][0])));
+    const float h = fmaxf(0.f, __fsub_rn(fminf(y2, sb[j][3]), fmaxf(y1, sb[j][1])));
+    const float inter = __fmul_rn(w, h);
+    const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area, sb[j][4]), inter));
+    if (iou > thr) bits |= 1ull << j;
+  }
+  mask[(long long)i * nwords + colb] = bits;
+}
+
+// One block per image: greedy scan in 64-box chunks.
+constexpr int kScanThreads = 256;
+constexpr int kMaxWords = 2048;  // n <= 131072
+__global__ void nms_scan_kernel(const unsigned long long* __restrict__ mask, int n, int nwords,
+                                int max_keep, long long* __restrict__ keep,
+                                int* __restrict__ num_keep, long long mask_stride,
+                                long long keep_stride) {
+  __shared__ unsigned long long removed[kMaxWords];
+  __shared__ unsigned long long diag[64];
+  __shared__ unsigned long long s_kept;
+  __shared__ int s_count;
+  const int img = blockIdx.x;
+  mask += (long long)img * mask_stride;
+  keep += (long long)img * keep_stride;
+  const int t = threadIdx.x;
+  for (int w = t; w < nwords; w += kScanThreads) removed[w] = 0ull;
+  if (t == 0) s_count = 0;
+  __syncthreads();
+  for (int c = 0; c < nwords; ++c) {
+    if (s_count >= max_keep) break;
+    if (t < 64) {
+      const int i = c * 64 + t;
+      diag[t] = (i < n) ? mask[(long long)i * nwords + c] : 0ull;
+    }
+    __syncthreads();
+    if (t == 0) {
+      unsigned long long rem = removed[c], kept = 0ull;
+      int cnt = s_count;
+      const int lim = min(64, n - c * 64);
+      for (int b = 0; b < lim; ++b) {
+        if (!((rem >> b) & 1ull)) {
+          if (cnt < max_keep) {
+            keep[cnt] = c * 64 + b;
+            kept |= 1ull << b;
+          }
+          ++cnt;
+          rem |= diag[b];
+        }
+      }
+      s_kept = kept;
+      s_count = cnt < max_keep ? cnt : max_keep;
+    }
+    __syncthreads();
+    const unsigned long long kept = s_kept;
+    if (kept) {
+      for (int w = c + 1 + t; w < nwords; w += kScanThreads) {
+        unsigned long long acc = 0ull, k2 = kept;
+        while (k2) {
+          const int b = __ffsll((long long)k2) - 1;
+          k2 &= k2 - 1;
+          acc |= mask[(long long)(c * 64 + b) * nwords + w];
+        }
+        removed[w] |= acc;
+      }
+    }
+    __syncthreads();
+  }
+  if (t == 0) num_keep[img] = s_count;
+}
+
+// ---------------------------------------------------------------- target encoders
+// bbox2delta with means 0: deltas[i] = ((gx-px)/pw, (gy-py)/ph, log(gw/pw), log(gh/ph)) / stds
+__global__ void bbox_encode_kernel(const float* __restrict__ props, const float* __restrict__ gts,
+                                   long long n, float s0, float s1, float s2, float s3,
+                                   float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = reinterpret_cast<const float4*>(props)[i];
+  const float4 g = reinterpret_cast<const float4*>(gts)[i];
+  const float px = __fmul_rn(__fadd_rn(p.x, p.z), 0.5f), py = __fmul_rn(__fadd_rn(p.y, p.w), 0.5f);
+  const float pw = __fsub_rn(p.z, p.x), ph = __fsub_rn(p.w, p.y);
+  const float gx = __fmul_rn(__fadd_rn(g.x, g.z), 0.5f), gy = __fmul_rn(__fadd_rn(g.y, g.w), 0.5f);
+  const float gw = __fsub_rn(g.z, g.x), gh = __fsub_rn(g.w, g.y);
+  float4 d;
+  d.x = __fdiv_rn(__fdiv_rn(__fsub_rn(gx, px), pw), s0);
+  d.y = __fdiv_rn(__fdiv_rn(__fsub_rn(gy, py), ph), s1);
+  d.z = __fdiv_rn(logf(__fdiv_rn(gw, pw)), s2);
+  d.w = __fdiv_rn(logf(__fdiv_rn(gh, ph)), s3);
+  reinterpret_cast<float4*>(out)[i] = d;
+}
+
+// FOA offset targets, closed form of the reference's polar rotation (verified equal):
+//   branch 0: (x/pw, y/ph)/std   90: (y/ph, -x/pw)/std   180: (-x/pw, -y/ph)/std   270: (-y/ph, x/pw)/std
+// out is [4P, 2] branch-major.
+__global__ void offset_target_kernel(const float* __restrict__ props,
+                                     const float* __restrict__ gt_offsets,
+                                     const long long* __restrict__ gt_inds, long long P, float std_x,
+                                     float std_y, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const float4 p = reinterpret_cast<const float4*>(props)[i];
+  const float pw = __fsub_rn(p.z, p.x), ph = __fsub_rn(p.w, p.y);
+  const long long g = gt_inds[i];
+  const float x = __fdiv_rn(__fdiv_rn(gt_offsets[g * 2], pw), std_x);
+  const float y = __fdiv_rn(__fdiv_rn(gt_offsets[g * 2 + 1], ph), std_y);
+  out[(0 * P + i) * 2 + 0] = x;
+  out[(0 * P + i) * 2 + 1] = y;
+  out[(1 * P + i) * 2 + 0] = y;
+  out[(1 * P + i) * 2 + 1] = -x;
+  out[(2 * P + i) * 2 + 0] = -x;
+  out[(2 * P + i) * 2 + 1] = -y;
+  out[(3 * P + i) * 2 + 0] = -y;
+  out[(3 * P + i) * 2 + 1] = x;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t loft_iou_assign_workspace(long long n, int G) {
+  // max_ov[n] f32, argmax[n] i32, gt_max[G] u32
+  return (size_t)n * 8 + (size_t)(G > 0 ? G : 1) * 4 + 64;
+}
+
+int loft_iou_assign(const float* boxes, long long n, const float* gts, int G, float pos_thr,
+                    float neg_thr, float min_pos, int match_low_quality, long long* gt_inds,
+                    float* max_overlaps, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+  LOFT_CHECK_ARG(gt_inds && max_overlaps && workspace, "iou_assign: null pointer");
+  LOFT_CHECK_SHAPE(G <= kMaxGt, "iou_assign: at most %d gt boxes supported, got %d", kMaxGt, G);
+  LOFT_CHECK_ARG(ws_bytes >= loft_iou_assign_workspace(n, G), "iou_assign: workspace too small");
+  if (n == 0) return LOFT_OK;
+  int* argmax = reinterpret_cast<int*>(workspace);
+  unsigned int* gtmax = reinterpret_cast<unsigned int*>(argmax + n);
+  cudaMemsetAsync(gtmax, 0, (size_t)(G > 0 ? G : 1) * 4, stream);
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+  const size_t smem = (size_t)(G > 0 ? G : 1) * 6 * sizeof(float);
+  iou_max_kernel<<<blocks, threads, smem, stream>>>(boxes, n, gts, G, max_overlaps, argmax, gtmax);
+  LOFT_CUDA_LAUNCH_CHECK("iou_max");
+  iou_assign_kernel<<<blocks, threads, smem, stream>>>(boxes, n, gts, G, max_overlaps, argmax, gtmax,
+                                                      pos_thr, neg_thr, min_pos, match_low_quality,
+                                                      gt_inds);
+  LOFT_CUDA_LAUNCH_CHECK("iou_assign");
+  return LOFT_OK;
+}
+
+int loft_rpn_decode(const float* head_out, int ld, int reg_off, const long long* topk_idx, int k,
+                    int fw, int A, const float* base_anchors, float stride, float max_ratio,
+                    float img_h, float img_w, float* boxes_out, cudaStream_t stream) {
+  LOFT_CHECK_ARG(head_out && topk_idx && base_anchors && boxes_out, "rpn_decode: null pointer");
+  if (k == 0) return LOFT_OK;
+  rpn_decode_kernel<<<loft_cdiv(k, 128), 128, 0, stream>>>(head_out, ld, reg_off, topk_idx, k, fw, A,
+                                                          base_anchors, stride, max_ratio, img_h,
+                                                          img_w, boxes_out);
+  LOFT_CUDA_LAUNCH_CHECK("rpn_decode");
+  return LOFT_OK;
+}
+
+size_t loft_nms_workspace(int n) {
+  const size_t nwords = (size_t)(n + 63) / 64;
+  return (size_t)n * nwords * 8 + 64;
+}
+
+// boxes [B,n,4] sorted by score desc within each image; idxs [B,n] (may be NULL); per-image
+// max_coord computed here.  keep [B,n] positions into the sorted order, num_keep [B].
+int loft_nms_sorted(const float* boxes, const long long* idxs, int B, int n, float iou_thr,
+                    int max_keep, long long* keep, int* num_keep, void* workspace, size_t ws_bytes,
+                    cudaStream_t stream) {
+  LOFT_CHECK_ARG(boxes && keep && num_keep && workspace, "nms_sorted: null pointer");
+  const int nwords = (n + 63) / 64;
+  LOFT_CHECK_SHAPE(nwords <= kMaxWords, "nms_sorted: n=%d too large", n);
+  LOFT_CHECK_ARG(ws_bytes >= (size_t)B * loft_nms_workspace(n), "nms_sorted: workspace too small");
+  if (n == 0 || B == 0) {
+    if (B) cudaMemsetAsync(num_keep, 0, sizeof(int) * B, stream);
+    return LOFT_OK;
+  }
+  const size_t per_img = loft_nms_workspace(n);
+  for (int b = 0; b < B; ++b) {
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace) + (size_t)b * per_img;
+    unsigned long long* mask = reinterpret_cast<unsigned long long*>(ws);
+    float* maxc = reinterpret_cast<float*>(ws + (size_t)n * nwords * 8);
+    const float* bx = boxes + (size_t)b * n * 4;
+    const long long* ix = idxs ? idxs + (size_t)b * n : nullptr;
+    if (ix) {
+      fill_f32_kernel<<<1, 1, 0, stream>>>(maxc, -INFINITY);
+      max_coord_kernel<<<32, 256, 0, stream>>>(bx, (long long)n * 4, maxc);
+      LOFT_CUDA_LAUNCH_CHECK("max_coord");
+    }
+    dim3 grid(nwords, nwords);
+    nms_mask_kernel<<<grid, 64, 0, stream>>>(bx, ix, ix ? maxc : nullptr, n, iou_thr, mask, nwords);
+    LOFT_CUDA_LAUNCH_CHECK("nms_mask");
+  }
+  if (max_keep <= 0 || max_keep > n) max_keep = n;
+  nms_scan_kernel<<<B, kScanThreads, 0, stream>>>(
+      reinterpret_cast<const unsigned long long*>(workspace), n, nwords, max_keep, keep, num_keep,
+      (long long)(per_img / 8), (long long)n);
+  LOFT_CUDA_LAUNCH_CHECK("nms_scan");
+  return LOFT_OK;
+}
+
+int loft_bbox_encode(const float* props, const float* gts, long long n, float s0, float s1, float s2,
+                     float s3, float* out, cudaStream_t stream) {
+  LOFT_CHECK_ARG(props && gts && out, "bbox_encode: null pointer");
+  if (n == 0) return LOFT_OK;
+  bbox_encode_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(props, gts, n, s0, s1, s2, s3,
+                                                                      out);
+  LOFT_CUDA_LAUNCH_CHECK("bbox_encode");
+  return LOFT_OK;
+}
+
+int loft_offset_target(const float* props, const float* gt_offsets, const long long* gt_inds,
+                       long long P, float std_x, float std_y, float* out, cudaStream_t stream) {
+  LOFT_CHECK_ARG(props && gt_offsets && gt_inds && out, "offset_target: null pointer");
+  if (P == 0) return LOFT_OK;
+  offset_target_kernel<<<(unsigned)((P + 127) / 128), 128, 0, stream>>>(props, gt_offsets, gt_inds, P,
+                                                                        std_x, std_y, out);
+  LOFT_CUDA_LAUNCH_CHECK("offset_target");
+  return LOFT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,486 @@
+// HBM-bound helper kernels of the LOFT path: TF32 rounding / weight repacks, BN folding and
+// activation backward (+ per-channel reductions), stem im2col, max-pool, 2x subsampling, FPN
+// top-down backward, FOA rot90, fused grad-norm + clip + SGD.
+// Reference semantics: backbones/resnet.py:260-300,525-571,623-649 (BN eval, ReLU, maxpool),
+// necks/fpn.py:164-216, attribute_heads/offset_head_expand_feature.py:163-196 (rotation),
+// mmcv OptimizerHook + torch.optim.SGD (configs/_base_/schedules/schedule_2x_bonai.py:2-3).
+#include "common.cuh"
+#include "loft_b200.h"
+
+namespace {
+
+constexpr int kT = 256;
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+inline int grid_for(long long n, int per_block = kT, int max_blocks = 148 * 16) {
+  long long b = (n + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  if (b > max_blocks) b = max_blocks;
+  return (int)b;
+}
+
+// ---------------------------------------------------------------- copy / round / repack
+// dst[r*ldd + c] (=|+=) round?(src[r*lds + c])
+__global__ void copy2d_kernel(const float* __restrict__ src, long long lds, float* __restrict__ dst,
+                              long long ldd, long long rows, int cols, int accumulate, int round) {
+  const long long n = rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    const int c = (int)(i - r * cols);
+    float v = src[r * lds + c];
+    if (round) v = tf32_rna(v);
+    float* d = dst + r * ldd + c;
+    *d = accumulate ? (*d + v) : v;
+  }
+}
+
+// Generic 3-axis permute of a [A][B][C] tensor into [A][C][B] (dst) or back, with optional TF32
+// rounding / accumulation.  Covers fc (C,HW)->(HW,C) weight repacks and their gradient un-packs.
+__global__ void permute_acb_kernel(const float* __restrict__ src, float* __restrict__ dst, int A,
+                                   int B, int C, int accumulate, int round) {
+  __shared__ float tile[32][33];
+  const int a = blockIdx.z;
+  const int b0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const float* s = src + (long long)a * B * C;
+  float* d = dst + (long long)a * B * C;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int b = b0 + i, c = c0 + threadIdx.x;
+    if (b < B && c < C) tile[i][threadIdx.x] = s[(long long)b * C + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, b = b0 + threadIdx.x;
+    if (b < B && c < C) {
+      float v = tile[threadIdx.x][i];
+      if (round) v = tf32_rna(v);
+      float* p = d + (long long)c * B + b;
+      *p = accumulate ? (*p + v) : v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- BN fold / activation backward
+__global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ mean, const float* __restrict__ var,
+                               float eps, float* __restrict__ scale, float* __restrict__ shift,
+                               float* __restrict__ rstd, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float r = 1.0f / sqrtf(var[c] + eps);
+  const float s = gamma[c] * r;
+  scale[c] = s;
+  shift[c] = beta[c] - mean[c] * s;
+  if (rstd) rstd[c] = r;
+}
+
+// g = dy * (y>0 if relu);  dz = round(g*scale) ; dres = g ; dbeta += sum g ; dgamma += sum g*xhat
+// Threads run along C (coalesced), each block reduces a slab of rows.
+__global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                               const float* __restrict__ z, const float* __restrict__ scale,
+                               const float* __restrict__ mean, const float* __restrict__ rstd,
+                               float* __restrict__ dz, float* __restrict__ dres,
+                               float* __restrict__ dgamma, float* __restrict__ dbeta, long long P,
+                               int C, int relu, int rows_per_block) {
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > P) r1 = P;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float sc = scale ? scale[c] : 1.f;
+    const float mu = mean ? mean[c] : 0.f;
+    const float rs = rstd ? rstd[c] : 1.f;
+    float sb = 0.f, sg = 0.f;
+    for (long long r = r0; r < r1; ++r) {
+      const long long i = r * C + c;
+      float g = dy[i];
+      if (relu && !(y[i] > 0.f)) g = 0.f;
+      sb += g;
+      if (z) sg += g * (z[i] - mu) * rs;
+      if (dres) dres[i] = g;
+      if (dz) dz[i] = tf32_rna(g * sc);
+    }
+    if (dbeta) atomicAdd(dbeta + c, sb);
+    if (dgamma) atomicAdd(dgamma + c, sg);
+  }
+}
+
+// ---------------------------------------------------------------- im2col / col2im (NHWC)
+// col[(n,ho,wo), (r,s,c)] ; K order matches the [Cout][kh][kw][Cin] weight layout. Kpad >= kh*kw*C.
+__global__ void im2col_kernel(const float* __restrict__ x, float* __restrict__ col, int N, int H,
+                              int W, int C, int kh, int kw, int stride, int pad, int Ho, int Wo,
+                              int Kpad, int nchw) {
+  const long long total = (long long)N * Ho * Wo * Kpad;
+  const int K = kh * kw * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % Kpad);
+    const long long m = i / Kpad;
+    float v = 0.f;
+    if (k < K) {
+      const int c = k % C;
+      const int rs = k / C;
+      const int s = rs % kw, r = rs / kw;
+      const int wo = (int)(m % Wo);
+      const long long t = m / Wo;
+      const int ho = (int)(t % Ho);
+      const int n = (int)(t / Ho);
+      const int h = ho * stride - pad + r, w = wo * stride - pad + s;
+      if (h >= 0 && h < H && w >= 0 && w < W) {
+        v = nchw ? x[(((long long)n * C + c) * H + h) * W + w]
+                 : x[(((long long)n * H + h) * W + w) * C + c];
+      }
+    }
+    col[i] = tf32_rna(v);
+  }
+}
+
+// dx[n,h,w,c] = sum over taps of dcol[(n,ho,wo),(r,s,c)] (gather form, no atomics)
+__global__ void col2im_kernel(const float* __restrict__ dcol, float* __restrict__ dx,
+                              const float* __restrict__ mask, int N, int H, int W, int C, int kh,
+                              int kw, int stride, int pad, int Ho, int Wo, int Kpad) {
+  const long long total = (long long)N * H * W * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long t = i / C;
+    const int w = (int)(t % W);
+    t /= W;
+    const int h = (int)(t % H);
+    const int n = (int)(t / H);
+    float acc = 0.f;
+    for (int r = 0; r < kh; ++r) {
+      const int hh = h + pad - r;
+      if (hh < 0 || hh % stride) continue;
+      const int ho = hh / stride;
+      if (ho >= Ho) continue;
+      for (int s = 0; s < kw; ++s) {
+        const int ww = w + pad - s;
+        if (ww < 0 || ww % stride) continue;
+        const int wo = ww / stride;
+        if (wo >= Wo) continue;
+        acc += dcol[(((long long)n * Ho + ho) * Wo + wo) * Kpad + (r * kw + s) * C + c];
+      }
+    }
+    if (mask && !(mask[i] > 0.f)) acc = 0.f;
+    dx[i] = tf32_rna(acc);
+  }
+}
+
+// ---------------------------------------------------------------- pooling / sampling
+__global__ void maxpool3x3s2_kernel(const float* __restrict__ x, float* __restrict__ y, int N,
+                                    int H, int W, int C, int Ho, int Wo) {
+  const long long total = (long long)N * Ho * Wo * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long t = i / C;
+    const int wo = (int)(t % Wo);
+    t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    float m = -INFINITY;
+    for (int r = 0; r < 3; ++r) {
+      const int h = ho * 2 - 1 + r;
+      if (h < 0 || h >= H) continue;
+      for (int s = 0; s < 3; ++s) {
+        const int w = wo * 2 - 1 + s;
+        if (w < 0 || w >= W) continue;
+        m = fmaxf(m, x[(((long long)n * H + h) * W + w) * C + c]);
+      }
+    }
+    y[i] = m;
+  }
+}
+
+// y[n,h,w,:] = x[n,2h,2w,:]  (stride-2 1x1 conv input; FPN P6 = max_pool2d(P5,1,stride=2))
+__global__ void subsample2_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H,
+                                  int W, int C, int Ho, int Wo) {
+  const long long total = (long long)N * Ho * Wo * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long t = i / C;
+    const int wo = (int)(t % Wo);
+    t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    y[i] = x[(((long long)n * H + 2 * ho) * W + 2 * wo) * C + c];
+  }
+}
+
+// dx[n,h,w,:] = (h,w even) ? dy[n,h/2,w/2,:] : 0   (+ optional ReLU mask of the forward input)
+__global__ void subsample2_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx,
+                                      const float* __restrict__ mask, int N, int H, int W, int C,
+                                      int Ho, int Wo) {
+  const long long total = (long long)N * H * W * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long t = i / C;
+    const int w = (int)(t % W);
+    t /= W;
+    const int h = (int)(t % H);
+    const int n = (int)(t / H);
+    float v = 0.f;
+    if (!(h & 1) && !(w & 1) && (h >> 1) < Ho && (w >> 1) < Wo)
+      v = dy[(((long long)n * Ho + (h >> 1)) * Wo + (w >> 1)) * C + c];
+    if (mask && !(mask[i] > 0.f)) v = 0.f;
+    dx[i] = v;
+  }
+}
+
+// out[n,h,w,:] = base[n,h,w,:] + sum_{i,j<2} fine[n,2h+i,2w+j,:]   (FPN top-down backward)
+__global__ void sum2x2_add_kernel(const float* __restrict__ fine, const float* __restrict__ base,
+                                  float* __restrict__ out, int N, int H, int W, int C) {
+  const long long total = (long long)N * H * W * C;
+  const int Hf = 2 * H, Wf = 2 * W;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long t = i / C;
+    const int w = (int)(t % W);
+    t /= W;
+    const int h = (int)(t % H);
+    const int n = (int)(t / H);
+    const float* f = fine + (((long long)n * Hf + 2 * h) * Wf + 2 * w) * C + c;
+    float v = f[0] + f[C] + f[(long long)Wf * C] + f[(long long)Wf * C + C];
+    if (base) v += base[i];
+    out[i] = tf32_rna(v);
+  }
+}
+
+// torch.rot90(x, k, dims=(H,W)) on [K,S,S,C] NHWC:  k=1: y[i][j] = x[j][S-1-i]
+__global__ void rot90_kernel(const float* __restrict__ x, float* __restrict__ y, long long K, int S,
+                             int C, int k) {
+  const long long total = K * S * S * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long t = i / C;
+    const int j = (int)(t % S);
+    t /= S;
+    const int ii = (int)(t % S);
+    const long long n = t / S;
+    int si, sj;
+    switch (k & 3) {
+      case 0: si = ii; sj = j; break;
+      case 1: si = j; sj = S - 1 - ii; break;
+      case 2: si = S - 1 - ii; sj = S - 1 - j; break;
+      default: si = S - 1 - j; sj = ii; break;
+    }
+    y[i] = x[((n * S + si) * S + sj) * C + c];
+  }
+}
+
+__global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                           float* __restrict__ out, long long n, int round) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float v = a[i] + b[i];
+    out[i] = round ? tf32_rna(v) : v;
+  }
+}
+
+// ---------------------------------------------------------------- optimizer
+__global__ void sqnorm_kernel(const float* __restrict__ g, long long n, double* __restrict__ out) {
+  double acc = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float v = g[i];
+    acc += (double)v * v;
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ double sm[kT / 32];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < kT / 32; ++i) t += sm[i];
+    atomicAdd(out, t);
+  }
+}
+
+// clip_grad_norm_(max_norm) + SGD(momentum, weight_decay); grad_scale pre-multiplies the gradient
+// (1/world_size after the all-reduce).  Also refreshes the TF32-rounded copy the GEMMs read.
+__global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                           float* __restrict__ p_tf32, long long n, float lr, float momentum,
+                           float wd, float max_norm, float grad_scale,
+                           const double* __restrict__ sqnorm) {
+  float coef = grad_scale;
+  if (max_norm > 0.f && sqnorm) {
+    const float total = (float)sqrt(*sqnorm) * grad_scale;
+    const float c = max_norm / (total + 1e-6f);
+    if (c < 1.f) coef *= c;
+  }
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float pv = p[i];
+    const float gv = g[i] * coef + wd * pv;
+    const float mv = m[i] * momentum + gv;
+    m[i] = mv;
+    const float nv = pv - lr * mv;
+    p[i] = nv;
+    if (p_tf32) p_tf32[i] = tf32_rna(nv);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int loft_copy2d(const float* src, long long lds, float* dst, long long ldd, long long rows, int cols,
+                int accumulate, int round_tf32, cudaStream_t stream) {
+  LOFT_CHECK_ARG(src && dst, "copy2d: null pointer");
+  if (rows * cols == 0) return LOFT_OK;
+  copy2d_kernel<<<grid_for(rows * cols), kT, 0, stream>>>(src, lds, dst, ldd, rows, cols,
+                                                           accumulate, round_tf32);
+  LOFT_CUDA_LAUNCH_CHECK("copy2d");
+  return LOFT_OK;
+}
+
+int loft_permute_acb(const float* src, float* dst, int A, int B, int C, int accumulate,
+                     int round_tf32, cudaStream_t stream) {
+  LOFT_CHECK_ARG(src && dst, "permute_acb: null pointer");
+  if ((long long)A * B * C == 0) return LOFT_OK;
+  LOFT_CHECK_SHAPE(A <= 65535 && loft_cdiv(B, 32) <= 65535, "permute_acb: grid too large");
+  dim3 grid(loft_cdiv(C, 32), loft_cdiv(B, 32), A), block(32, 8);
+  permute_acb_kernel<<<grid, block, 0, stream>>>(src, dst, A, B, C, accumulate, round_tf32);
+  LOFT_CUDA_LAUNCH_CHECK("permute_acb");
+  return LOFT_OK;
+}
+
+int loft_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var,
+                 float eps, float* scale, float* shift, float* rstd, int C, cudaStream_t stream) {
+  LOFT_CHECK_ARG(gamma && beta && mean && var && scale && shift, "bn_fold: null pointer");
+  bn_fold_kernel<<<loft_cdiv(C, 128), 128, 0, stream>>>(gamma, beta, mean, var, eps, scale, shift,
+                                                        rstd, C);
+  LOFT_CUDA_LAUNCH_CHECK("bn_fold");
+  return LOFT_OK;
+}
+
+int loft_act_bwd(const float* dy, const float* y, const float* z, const float* scale,
+                 const float* mean, const float* rstd, float* dz, float* dres, float* dgamma,
+                 float* dbeta, long long P, int C, int relu, cudaStream_t stream) {
+  LOFT_CHECK_ARG(dy, "act_bwd: null dy");
+  LOFT_CHECK_ARG(!relu || y, "act_bwd: relu needs y");
+  if (P == 0) return LOFT_OK;
+  int rows = 64;
+  while ((P + rows - 1) / rows > 148 * 8 && rows < 4096) rows *= 2;
+  const int blocks = (int)((P + rows - 1) / rows);
+  const int threads = C >= 256 ? 256 : (C >= 128 ? 128 : (C >= 64 ? 64 : 32));
+  act_bwd_kernel<<<blocks, threads, 0, stream>>>(dy, y, z, scale, mean, rstd, dz, dres, dgamma,
+                                                 dbeta, P, C, relu, rows);
+  LOFT_CUDA_LAUNCH_CHECK("act_bwd");
+  return LOFT_OK;
+}
+
+int loft_im2col(const float* x, float* col, int N, int H, int W, int C, int kh, int kw, int stride,
+                int pad, int Kpad, int nchw_input, cudaStream_t stream) {
+  LOFT_CHECK_ARG(x && col, "im2col: null pointer");
+  const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
+  LOFT_CHECK_SHAPE(Kpad >= kh * kw * C, "im2col: Kpad too small");
+  const long long total = (long long)N * Ho * Wo * Kpad;
+  if (total == 0) return LOFT_OK;
+  im2col_kernel<<<grid_for(total, kT, 148 * 32), kT, 0, stream>>>(x, col, N, H, W, C, kh, kw, stride,
+                                                                 pad, Ho, Wo, Kpad, nchw_input);
+  LOFT_CUDA_LAUNCH_CHECK("im2col");
+  return LOFT_OK;
+}
+
+int loft_col2im(const float* dcol, float* dx, const float* mask, int N, int H, int W, int C, int kh,
+                int kw, int stride, int pad, int Kpad, cudaStream_t stream) {
+  LOFT_CHECK_ARG(dcol && dx, "col2im: null pointer");
+  const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
+  const long long total = (long long)N * H * W * C;
+  if (total == 0) return LOFT_OK;
+  col2im_kernel<<<grid_for(total, kT, 148 * 32), kT, 0, stream>>>(dcol, dx, mask, N, H, W, C, kh, kw,
+                                                                 stride, pad, Ho, Wo, Kpad);
+  LOFT_CUDA_LAUNCH_CHECK("col2im");
+  return LOFT_OK;
+}
+
+int loft_maxpool3x3s2(const float* x, float* y, int N, int H, int W, int C, cudaStream_t stream) {
+  LOFT_CHECK_ARG(x && y, "maxpool: null pointer");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const long long total = (long long)N * Ho * Wo * C;
+  if (total == 0) return LOFT_OK;
+  maxpool3x3s2_kernel<<<grid_for(total, kT, 148 * 32), kT, 0, stream>>>(x, y, N, H, W, C, Ho, Wo);
+  LOFT_CUDA_LAUNCH_CHECK("maxpool3x3s2");
+  return LOFT_OK;
+}
+
+int loft_subsample2(const float* x, float* y, int N, int H, int W, int C, cudaStream_t stream) {
+  LOFT_CHECK_ARG(x && y, "subsample2: null pointer");
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const long long total = (long long)N * Ho * Wo * C;
+  if (total == 0) return LOFT_OK;
+  subsample2_kernel<<<grid_for(total), kT, 0, stream>>>(x, y, N, H, W, C, Ho, Wo);
+  LOFT_CUDA_LAUNCH_CHECK("subsample2");
+  return LOFT_OK;
+}
+
+int loft_subsample2_bwd(const float* dy, float* dx, const float* mask, int N, int H, int W, int C,
+                        cudaStream_t stream) {
+  LOFT_CHECK_ARG(dy && dx, "subsample2_bwd: null pointer");
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const long long total = (long long)N * H * W * C;
+  if (total == 0) return LOFT_OK;
+  subsample2_bwd_kernel<<<grid_for(total, kT, 148 * 32), kT, 0, stream>>>(dy, dx, mask, N, H, W, C,
+                                                                         Ho, Wo);
+  LOFT_CUDA_LAUNCH_CHECK("subsample2_bwd");
+  return LOFT_OK;
+}
+
+int loft_sum2x2_add(const float* fine, const float* base, float* out, int N, int H, int W, int C,
+                    cudaStream_t stream) {
+  LOFT_CHECK_ARG(fine && out, "sum2x2_add: null pointer");
+  const long long total = (long long)N * H * W * C;
+  if (total == 0) return LOFT_OK;
+  sum2x2_add_kernel<<<grid_for(total), kT, 0, stream>>>(fine, base, out, N, H, W, C);
+  LOFT_CUDA_LAUNCH_CHECK("sum2x2_add");
+  return LOFT_OK;
+}
+
+int loft_rot90(const float* x, float* y, long long K, int S, int C, int k, cudaStream_t stream) {
+  LOFT_CHECK_ARG(x && y, "rot90: null pointer");
+  if (K * S * S * C == 0) return LOFT_OK;
+  rot90_kernel<<<grid_for(K * S * S * C), kT, 0, stream>>>(x, y, K, S, C, ((k % 4) + 4) % 4);
+  LOFT_CUDA_LAUNCH_CHECK("rot90");
+  return LOFT_OK;
+}
+
+int loft_add(const float* a, const float* b, float* out, long long n, int round_tf32,
+             cudaStream_t stream) {
+  LOFT_CHECK_ARG(a && b && out, "add: null pointer");
+  if (n == 0) return LOFT_OK;
+  add_kernel<<<grid_for(n), kT, 0, stream>>>(a, b, out, n, round_tf32);
+  LOFT_CUDA_LAUNCH_CHECK("add");
+  return LOFT_OK;
+}
+
+int loft_grad_sqnorm(const float* g, long long n, double* out, cudaStream_t stream) {
+  LOFT_CHECK_ARG(g && out, "grad_sqnorm: null pointer");
+  if (n == 0) return LOFT_OK;
+  sqnorm_kernel<<<grid_for(n, kT, 148 * 8), kT, 0, stream>>>(g, n, out);
+  LOFT_CUDA_LAUNCH_CHECK("grad_sqnorm");
+  return LOFT_OK;
+}
+
+int loft_sgd_clip_step(float* p, const float* g, float* m, float* p_tf32, long long n, float lr,
+                       float momentum, float weight_decay, float max_norm, float grad_scale,
+                       const double* sqnorm, cudaStream_t stream) {
+  LOFT_CHECK_ARG(p && g && m, "sgd_clip_step: null pointer");
+  if (n == 0) return LOFT_OK;
+  sgd_kernel<<<grid_for(n, kT, 148 * 8), kT, 0, stream>>>(p, g, m, p_tf32, n, lr, momentum,
+                                                          weight_decay, max_norm, grad_scale,
+                                                          sqnorm);
+  LOFT_CUDA_LAUNCH_CHECK("sgd_clip_step");
+  return LOFT_OK;
+}
+
+}  // extern "C"

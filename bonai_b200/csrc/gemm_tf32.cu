@@ -69,6 +69,7 @@ struct GemmParams {
   int res_mode;   // 0 none, 1 same pixel, 2 nearest-upsample x2 (residual has H/2 x W/2 pixels)
   int relu;
   int out_map;    // 0 plain rows, 1 deconv 2x2/s2 pixel shuffle (out is [N,2H,2W,Cm/4])
+  int round_out;  // round `out` to TF32 (RNA) so the next MMA's operand truncation is exact
   long long ldw;  // WGRAD: row pitch of dW
   int tap_stride; // WGRAD_CONV: column offset per tap in dW (= Cin)
 };
@@ -327,6 +328,11 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
             }
             if (p.relu) acc = fmaxf(acc, 0.f);
             if (p.mask != nullptr) acc = (p.mask[orow * p.ldo + ocol] > 0.f) ? acc : 0.f;
+            if (p.round_out) {
+              uint32_t rr;
+              asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(rr) : "f"(acc));
+              acc = __uint_as_float(rr);
+            }
             p.out[orow * p.ldo + ocol] = acc;
           }
         }
@@ -491,6 +497,7 @@ void set_epilogue(GemmParams& p, const loft_epilogue_t* e, float* out, long long
   p.res_mode = (e && e->residual) ? (e->res_upsample2x ? 2 : 1) : 0;
   p.relu = e ? e->relu : 0;
   p.out_map = e ? e->deconv_shuffle : 0;
+  p.round_out = e ? e->round_out : 0;
 }
 
 }  // namespace

@@ -1,0 +1,239 @@
+"""Device-resident parameter store of the LOFT training path.
+
+All floating-point parameters of a model are moved into ONE flat fp32 buffer (trainable ones
+first) with twin flat buffers for gradients, SGD momentum and the TF32-rounded copy the tensor
+cores read.  ``nn.Parameter.data`` / ``.grad`` become views, so ``state_dict()`` keeps the
+reference's names and shapes while
+
+* weight-gradient kernels accumulate straight into the flat gradient buffer (no autograd
+  accumulation pass, nothing to flatten before the NCCL all-reduce -- replaces the torch DDP
+  reducer wrapped at mmdet/apis/train.py:71-79),
+* grad-norm clipping + SGD(momentum, weight decay) is two launches over the flat buffers
+  (replaces mmcv OptimizerHook + torch.optim.SGD, configs/_base_/schedules/schedule_2x_bonai.py:2-3),
+* 4-D conv weights live in channels_last order ([Cout][kh][kw][Cin]) which is exactly the K-major
+  operand layout of the implicit-GEMM kernels.
+"""
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+
+
+class WeightRef:
+    """Kernel-facing handles of one weight tensor: TF32 copy + gradient accumulation target."""
+
+    def __init__(self, w, grad):
+        self.w = w          # tensor the GEMM reads (TF32-rounded, kernel layout)
+        self.grad = grad    # tensor wgrad accumulates into (None if frozen)
+
+
+class BNRef:
+    def __init__(self, scale, shift, rstd, mean, dgamma, dbeta):
+        self.scale, self.shift, self.rstd, self.mean = scale, shift, rstd, mean
+        self.dgamma, self.dbeta = dgamma, dbeta
+
+
+class Packed:
+    """A kernel weight that is a re-layout / fusion of one or more parameters (fc weights whose K
+    axis must follow NHWC order, the 2x2 deconv, heads fused or padded to a TMA-legal width).
+    ``build`` refreshes ``w``/``b`` from the master parameters; ``scatter`` adds the temp
+    gradients back into the parameters' gradient views at the end of backward."""
+
+    def __init__(self, w, b, gw, gb, build, scatter):
+        self.w, self.b, self.gw, self.gb = w, b, gw, gb
+        self.build, self.scatter = build, scatter
+
+
+def _is_bn(m):
+    return isinstance(m, nn.modules.batchnorm._BatchNorm)
+
+
+class ParamStore:
+    def __init__(self, model, device):
+        self.device = torch.device(device)
+        self.model = model
+        bns = [m for m in model.modules() if _is_bn(m)]
+        bn_param_ids = set()
+        for m in bns:
+            bn_param_ids.add(id(m.weight))
+            bn_param_ids.add(id(m.bias))
+        tr_bn = [m for m in bns if m.weight.requires_grad]
+        fz_bn = [m for m in bns if not m.weight.requires_grad]
+        others = [p for p in model.parameters() if id(p) not in bn_param_ids]
+        tr_other = [p for p in others if p.requires_grad]
+        fz_other = [p for p in others if not p.requires_grad]
+        order = ([m.weight for m in tr_bn] + [m.bias for m in tr_bn] + tr_other +
+                 [m.weight for m in fz_bn] + [m.bias for m in fz_bn] + fz_other)
+        # 16-byte aligned offsets (TMA base addresses)
+        offs, off = [], 0
+        n_train_params = 2 * len(tr_bn) + len(tr_other)
+        self.n_train = None
+        for i, p in enumerate(order):
+            if i == n_train_params:
+                self.n_train = off
+            offs.append(off)
+            off += (p.numel() + 3) // 4 * 4
+        if self.n_train is None:
+            self.n_train = off
+        self.total = off
+        dev = self.device
+        self.P = torch.zeros(off, device=dev)
+        self.T = torch.zeros(off, device=dev)
+        self.G = torch.zeros(self.n_train, device=dev)
+        self.M = torch.zeros(self.n_train, device=dev)
+        self.sqnorm = torch.zeros(1, dtype=torch.float64, device=dev)
+        self._grad_views = []
+        for p, o in zip(order, offs):
+            n = p.numel()
+            src = p.data
+            if p.dim() == 4 and (p.shape[2] > 1 or p.shape[3] > 1):
+                a, b, c, d = p.shape
+                view = self.P[o:o + n].view(a, c, d, b).permute(0, 3, 1, 2)
+                tview = self.T[o:o + n].view(a, c, d, b).permute(0, 3, 1, 2)
+                gview = self.G[o:o + n].view(a, c, d, b).permute(0, 3, 1, 2) \
+                    if o < self.n_train else None
+            else:
+                view = self.P[o:o + n].view(p.shape)
+                tview = self.T[o:o + n].view(p.shape)
+                gview = self.G[o:o + n].view(p.shape) if o < self.n_train else None
+            view.copy_(src)
+            p.data = view
+            p.grad = gview
+            p._loft = WeightRef(tview, gview)
+            self._grad_views.append((p, gview))
+        # BN statistics in two contiguous runs (trainable BNs, frozen BNs)
+        self._bn_groups = []
+        for group in (tr_bn, fz_bn):
+            C = sum(m.num_features for m in group)
+            if C == 0:
+                self._bn_groups.append(None)
+                continue
+            mean = torch.zeros(C, device=dev)
+            var = torch.ones(C, device=dev)
+            scale = torch.zeros(C, device=dev)
+            shift = torch.zeros(C, device=dev)
+            rstd = torch.zeros(C, device=dev)
+            g0 = group[0].weight._loft
+            c0 = 0
+            # gammas of the group are contiguous in P (then betas): find their flat offsets
+            goff = group[0].weight.data.data_ptr()
+            boff = group[0].bias.data.data_ptr()
+            for m in group:
+                c = m.num_features
+                assert c % 4 == 0, 'BN channel counts must be multiples of 4'
+                mean[c0:c0 + c].copy_(m.running_mean)
+                var[c0:c0 + c].copy_(m.running_var)
+                m.running_mean = mean[c0:c0 + c]
+                m.running_var = var[c0:c0 + c]
+                if m.num_batches_tracked is not None:
+                    m.num_batches_tracked = m.num_batches_tracked.to(dev)
+                m._loft_bn = BNRef(scale[c0:c0 + c], shift[c0:c0 + c], rstd[c0:c0 + c],
+                                   mean[c0:c0 + c], m.weight._loft.grad, m.bias._loft.grad)
+                m._loft_eps = m.eps
+                c0 += c
+            eps = group[0].eps
+            assert all(m.eps == eps for m in group)
+            self._bn_groups.append(dict(C=C, gamma_ptr=goff, beta_ptr=boff, mean=mean, var=var,
+                                        scale=scale, shift=shift, rstd=rstd, eps=eps))
+        # move remaining (non-BN) buffers
+        for m in model.modules():
+            if _is_bn(m):
+                continue
+            for k, b in list(m._buffers.items()):
+                if b is not None:
+                    m._buffers[k] = b.to(dev)
+        self.packed = []
+        for m in model.modules():
+            if hasattr(m, 'loft_prepare'):
+                m.loft_prepare(self)
+        self._seen_version = None
+        self._frozen_ready = False
+        self._callback_queued = False
+        model._loft_store = self
+
+    # ------------------------------------------------------------------ packed weights
+    def add_packed(self, packed):
+        self.packed.append(packed)
+        return packed
+
+    # ------------------------------------------------------------------ per-step protocol
+    def refresh_weights(self, force=False):
+        """TF32-round the master weights into T, fold BN, rebuild packed weights (only when the
+        master copy changed since the last call)."""
+        ver = self.P._version
+        if not force and self._seen_version == ver:
+            return
+        n0 = 0 if not self._frozen_ready else 0
+        end = self.total
+        L.call('copy2d', L.ptr(self.P), L.ll(end), L.ptr(self.T), L.ll(end), L.ll(1),
+               ctypes.c_int(end), ctypes.c_int(0), ctypes.c_int(1), L.stream())
+        self._after_weight_update()
+        self._seen_version = ver
+
+    def _after_weight_update(self):
+        for gi, g in enumerate(self._bn_groups):
+            if g is None or (gi == 1 and self._frozen_ready):
+                continue
+            L.call('bn_fold', ctypes.c_void_p(g['gamma_ptr']), ctypes.c_void_p(g['beta_ptr']),
+                   L.ptr(g['mean']), L.ptr(g['var']), L.f32(g['eps']), L.ptr(g['scale']),
+                   L.ptr(g['shift']), L.ptr(g['rstd']), ctypes.c_int(g['C']), L.stream())
+        self._frozen_ready = True
+        for pk in self.packed:
+            pk.build()
+
+    def begin_step(self):
+        """Zero the gradient buffers (weight-gradient kernels accumulate atomically)."""
+        self.refresh_weights()
+        self.G.zero_()
+        self.sqnorm.zero_()
+        for pk in self.packed:
+            if pk.gw is not None:
+                pk.gw.zero_()
+            if pk.gb is not None:
+                pk.gb.zero_()
+        self._callback_queued = False
+
+    def queue_finalize(self):
+        """Called from inside a backward node: run finalize_grads once autograd is done."""
+        if self._callback_queued:
+            return
+        self._callback_queued = True
+        torch.autograd.Variable._execution_engine.queue_callback(self.finalize_grads)
+
+    def finalize_grads(self):
+        for pk in self.packed:
+            pk.scatter()
+        for p, g in self._grad_views:
+            if g is not None and p.grad is not g:
+                p.grad = g
+
+    # ------------------------------------------------------------------ optimizer
+    def sgd_step(self, lr, momentum=0.9, weight_decay=1e-4, max_norm=35.0, grad_scale=1.0):
+        """clip_grad_norm_(max_norm) + SGD on the flat buffers; refreshes T in the same pass."""
+        n = self.n_train
+        use_clip = max_norm is not None and max_norm > 0
+        if use_clip:
+            L.call('grad_sqnorm', L.ptr(self.G), L.ll(n), L.ptr(self.sqnorm), L.stream())
+        L.call('sgd_clip_step', L.ptr(self.P), L.ptr(self.G), L.ptr(self.M), L.ptr(self.T), L.ll(n),
+               L.f32(lr), L.f32(momentum), L.f32(weight_decay), L.f32(max_norm if use_clip else 0.0),
+               L.f32(grad_scale), L.ptr(self.sqnorm) if use_clip else None, L.stream())
+        self._after_weight_update()
+        self._seen_version = self.P._version
+
+    def grad_norm(self):
+        """Global L2 norm of the last step's gradients (device tensor, no sync)."""
+        return self.sqnorm.sqrt().float()
+
+
+def get_store(model, device=None):
+    st = getattr(model, '_loft_store', None)
+    if st is None:
+        if device is None:
+            device = torch.device('cuda', torch.cuda.current_device())
+        if not torch.cuda.is_available():
+            raise L.LoftError('the LOFT hot path needs a CUDA device (sm_100a); there is no CPU '
+                              'fallback')
+        st = ParamStore(model, device)
+    return st

@@ -1,0 +1,274 @@
+"""RPN head (mmdet/models/dense_heads/rpn_head.py:12-168 on top of anchor_head.py:16-576 and
+base_dense_head.py:9-59, rpn_test_mixin.py).
+
+B200 path: the shared 3x3 conv (+bias+ReLU) is one implicit-GEMM launch per level; rpn_cls (3) and
+rpn_reg (12) are fused into one 1x1 GEMM with a 16-wide output row per location, so the NHWC
+output already has the `(n, h, w, a)` order that the reference obtains with
+`permute(0,2,3,1).reshape(-1)` (anchor_head.py:404-418, rpn_head.py:117-124).  Targets come from
+the fused IoU+assign kernel, the losses from fused BCE/L1 reductions, proposals from the
+top-k decode + bitmask-NMS kernels."""
+import ctypes
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from ..builder import HEADS, build_loss
+from ..init_utils import normal_init
+from ... import _lib as L
+from ...core import (build_anchor_generator, build_assigner, build_bbox_coder, build_sampler,
+                     images_to_levels)
+from ...engine import Packed, WeightRef
+from ...ops import dense as D
+from ...ops import losses as K
+from ...ops.nms import nms_sorted
+
+i32 = ctypes.c_int
+_FUSED_W = 16      # 3 cls + 12 reg + 1 zero pad
+
+
+@HEADS.register_module()
+class RPNHead(nn.Module):
+    forced_proposals = None       # test hook: list[Tensor[k,5]] injected instead of get_bboxes
+
+    def __init__(self, in_channels, num_classes=1, feat_channels=256,
+                 anchor_generator=dict(type='AnchorGenerator', scales=[8, 16, 32],
+                                       ratios=[0.5, 1.0, 2.0], strides=[4, 8, 16, 32, 64]),
+                 bbox_coder=dict(type='DeltaXYWHBBoxCoder', target_means=(.0, .0, .0, .0),
+                                 target_stds=(1.0, 1.0, 1.0, 1.0)),
+                 reg_decoded_bbox=False, background_label=0,
+                 loss_cls=dict(type='CrossEntropyLoss', use_sigmoid=True, loss_weight=1.0),
+                 loss_bbox=dict(type='SmoothL1Loss', beta=1.0 / 9.0, loss_weight=1.0),
+                 train_cfg=None, test_cfg=None):
+        super().__init__()
+        self.in_channels, self.num_classes, self.feat_channels = in_channels, num_classes, \
+            feat_channels
+        self.use_sigmoid_cls = loss_cls.get('use_sigmoid', False)
+        if not self.use_sigmoid_cls or reg_decoded_bbox:
+            raise NotImplementedError('LOFT path: sigmoid RPN classification, encoded box targets')
+        self.sampling = loss_cls['type'] not in ['FocalLoss', 'GHMC', 'QualityFocalLoss']
+        self.cls_out_channels = num_classes
+        self.background_label = 0
+        self.reg_decoded_bbox = reg_decoded_bbox
+        self.bbox_coder = build_bbox_coder(bbox_coder)
+        self.loss_cls = build_loss(loss_cls)
+        self.loss_bbox = build_loss(loss_bbox)
+        self.train_cfg, self.test_cfg = train_cfg, test_cfg
+        if self.train_cfg:
+            self.assigner = build_assigner(self.train_cfg.assigner)
+            sampler_cfg = self.train_cfg.sampler if self.sampling and hasattr(
+                self.train_cfg, 'sampler') else dict(type='PseudoSampler')
+            self.sampler = build_sampler(sampler_cfg, context=self)
+        self.fp16_enabled = False
+        self.anchor_generator = build_anchor_generator(anchor_generator)
+        self.num_anchors = self.anchor_generator.num_base_anchors[0]
+        self.rpn_conv = nn.Conv2d(self.in_channels, self.feat_channels, 3, padding=1)
+        self.rpn_cls = nn.Conv2d(self.feat_channels, self.num_anchors * self.cls_out_channels, 1)
+        self.rpn_reg = nn.Conv2d(self.feat_channels, self.num_anchors * 4, 1)
+        assert self.num_anchors * 5 <= _FUSED_W
+
+    def init_weights(self):
+        normal_init(self.rpn_conv, std=0.01)
+        normal_init(self.rpn_cls, std=0.01)
+        normal_init(self.rpn_reg, std=0.01)
+
+    # ------------------------------------------------------------------ kernel weights
+    def loft_prepare(self, store):
+        dev = store.device
+        c = self.rpn_conv
+        self._conv_spec = D.ConvSpec(c.weight._loft, ksize=3, padding=1, relu=True, bias=c.bias,
+                                     bias_grad=c.bias._loft.grad, store=store)
+        C = self.feat_channels
+        A = self.num_anchors
+        w = torch.zeros((_FUSED_W, C), device=dev)
+        b = torch.zeros((_FUSED_W,), device=dev)
+        gw = torch.zeros((_FUSED_W, C), device=dev)
+        gb = torch.zeros((_FUSED_W,), device=dev)
+        cls, reg = self.rpn_cls, self.rpn_reg
+
+        def cp(src, dst, rows, cols, acc, rnd):
+            L.call('copy2d', L.ptr(src), L.ll(cols), L.ptr(dst), L.ll(cols), L.ll(rows), i32(cols),
+                   i32(acc), i32(rnd), L.stream())
+
+        def build():
+            cp(cls.weight._loft.w, w, A, C, 0, 0)
+            cp(reg.weight._loft.w, w[A:], 4 * A, C, 0, 0)
+            cp(cls.bias, b, 1, A, 0, 0)
+            cp(reg.bias, b[A:], 1, 4 * A, 0, 0)
+
+        def scatter():
+            cp(gw, cls.weight._loft.grad, A, C, 1, 0)
+            cp(gw[A:], reg.weight._loft.grad, 4 * A, C, 1, 0)
+            cp(gb, cls.bias._loft.grad, 1, A, 1, 0)
+            cp(gb[A:], reg.bias._loft.grad, 1, 4 * A, 1, 0)
+
+        store.add_packed(Packed(w, b, gw, gb, build, scatter))
+        self._head_spec = D.ConvSpec(WeightRef(w, gw), ksize=1, bias=b, bias_grad=gb,
+                                     round_out=False, store=store)
+        self._base_anchors_dev = [ba.to(dev).contiguous()
+                                  for ba in self.anchor_generator.base_anchors]
+
+    # ------------------------------------------------------------------ forward
+    def forward_single(self, x):
+        c = self.rpn_conv
+        x = D.conv(x, self._conv_spec, triggers=(c.weight, c.bias))
+        fused = D.conv(x, self._head_spec, triggers=(self.rpn_cls.weight, self.rpn_reg.weight))
+        A = self.num_anchors
+        cls, reg = fused[:, :A], fused[:, A:5 * A]
+        cls._loft_fused = fused
+        reg._loft_fused = fused
+        return cls, reg
+
+    def forward(self, feats):
+        outs = [self.forward_single(f) for f in feats]
+        return [o[0] for o in outs], [o[1] for o in outs]
+
+    def forward_train(self, x, img_metas, gt_bboxes, gt_labels=None, gt_bboxes_ignore=None,
+                      proposal_cfg=None, **kwargs):
+        outs = self(x)
+        if gt_labels is None:
+            loss_inputs = outs + (gt_bboxes, img_metas)
+        else:
+            loss_inputs = outs + (gt_bboxes, gt_labels, img_metas)
+        losses = self.loss(*loss_inputs, gt_bboxes_ignore=gt_bboxes_ignore)
+        if proposal_cfg is None:
+            return losses
+        return losses, self.get_bboxes(*outs, img_metas, cfg=proposal_cfg)
+
+    # ------------------------------------------------------------------ targets + loss
+    def get_anchors(self, featmap_sizes, img_metas, device='cuda'):
+        multi = self.anchor_generator.grid_anchors(featmap_sizes, device)
+        anchor_list = [multi for _ in img_metas]
+        valid_flag_list = [self.anchor_generator.valid_flags(featmap_sizes, m['pad_shape'], device)
+                           for m in img_metas]
+        return anchor_list, valid_flag_list
+
+    def _flat_anchors(self, featmap_sizes, device):
+        key = (tuple(tuple(int(v) for v in s) for s in featmap_sizes), str(device))
+        cache = self.__dict__.setdefault('_flat_cache', {})
+        if key not in cache:
+            cache[key] = torch.cat(self.anchor_generator.grid_anchors(featmap_sizes, device))
+        return cache[key]
+
+    def _get_targets_single(self, flat_anchors, gt_bboxes, img_meta):
+        """anchor_head.py:180-278 with allowed_border=-1 (every anchor inside), sampling=True,
+        gt_labels=None (foreground label 1)."""
+        if self.train_cfg.allowed_border >= 0:
+            raise NotImplementedError('LOFT config uses allowed_border=-1')
+        assign_result = self.assigner.assign(flat_anchors, gt_bboxes, None, None)
+        sr = self.sampler.sample(assign_result, flat_anchors, gt_bboxes)
+        n = flat_anchors.shape[0]
+        labels = flat_anchors.new_zeros(n)
+        label_weights = flat_anchors.new_zeros(n)
+        bbox_targets = torch.zeros_like(flat_anchors)
+        bbox_weights = torch.zeros_like(flat_anchors)
+        pos_inds, neg_inds = sr.pos_inds, sr.neg_inds
+        if len(pos_inds) > 0:
+            bbox_targets[pos_inds, :] = self.bbox_coder.encode(sr.pos_bboxes, sr.pos_gt_bboxes)
+            bbox_weights[pos_inds, :] = 1.0
+            labels[pos_inds] = 1.0
+            label_weights[pos_inds] = 1.0 if self.train_cfg.pos_weight <= 0 \
+                else self.train_cfg.pos_weight
+        if len(neg_inds) > 0:
+            label_weights[neg_inds] = 1.0
+        return labels, label_weights, bbox_targets, bbox_weights, pos_inds, neg_inds
+
+    def loss(self, cls_scores, bbox_preds, gt_bboxes, img_metas, gt_bboxes_ignore=None):
+        """AnchorHead.loss / RPNHead.loss (anchor_head.py:429-497, rpn_head.py:46-77)."""
+        featmap_sizes = [f.size()[-2:] for f in cls_scores]
+        device = cls_scores[0].device
+        flat = self._flat_anchors(featmap_sizes, device)
+        num_lvl = [int(h) * int(w) * self.num_anchors for h, w in featmap_sizes]
+        n_img = len(img_metas)
+        lab, lw, bt, bw = [], [], [], []
+        num_pos = num_neg = 0
+        for i in range(n_img):
+            r = self._get_targets_single(flat, gt_bboxes[i], img_metas[i])
+            lab.append(r[0])
+            lw.append(r[1])
+            bt.append(r[2])
+            bw.append(r[3])
+            num_pos += max(r[4].numel(), 1)
+            num_neg += max(r[5].numel(), 1)
+        num_total_samples = num_pos + num_neg
+        lab, lw, bt, bw = (images_to_levels(t, num_lvl) for t in (lab, lw, bt, bw))
+        A = self.num_anchors
+        loss_cls, loss_bbox = [], []
+        for l, cs in enumerate(cls_scores):
+            fused = getattr(cs, '_loft_fused', None)
+            if fused is None:
+                raise L.LoftError('RPNHead.loss expects the fused head output of RPNHead.forward')
+            out2d = fused.permute(0, 2, 3, 1).reshape(-1, _FUSED_W)
+            loss_cls.append(K.elem_loss(out2d, lab[l].reshape(-1), lw[l].reshape(-1), K.BCE_LOGITS,
+                                        self.loss_cls.loss_weight / num_total_samples,
+                                        col_off=0, ncols=A))
+            mode, beta = (K.L1, 1.0) if type(self.loss_bbox).__name__ == 'L1Loss' else \
+                (K.SMOOTH_L1, self.loss_bbox.beta)
+            loss_bbox.append(K.elem_loss(out2d, bt[l].reshape(-1), bw[l].reshape(-1), mode,
+                                         self.loss_bbox.loss_weight / num_total_samples,
+                                         col_off=A, ncols=4 * A, beta=beta))
+        return dict(loss_rpn_cls=loss_cls, loss_rpn_bbox=loss_bbox)
+
+    # ------------------------------------------------------------------ proposals
+    @torch.no_grad()
+    def get_bboxes(self, cls_scores, bbox_preds, img_metas, cfg=None, rescale=False):
+        """AnchorHead.get_bboxes -> RPNHead._get_bboxes_single (rpn_head.py:79-168), all images in
+        one batched NMS.  Order within equal scores is (level, anchor index) = a stable sort."""
+        if RPNHead.forced_proposals is not None:
+            return [p.to(cls_scores[0].device) for p in RPNHead.forced_proposals]
+        cfg = self.test_cfg if cfg is None else cfg
+        if cfg.get('nms_across_levels', False) or cfg.min_bbox_size > 0:
+            raise NotImplementedError('LOFT config: per-level NMS, min_bbox_size=0')
+        A = self.num_anchors
+        n_img = len(img_metas)
+        dev = cls_scores[0].device
+        max_ratio = float(np.abs(np.log(16 / 1000)))
+        per_img_boxes, per_img_scores, per_img_ids = [], [], []
+        for i in range(n_img):
+            img_h, img_w = img_metas[i]['img_shape'][:2]
+            boxes_l, scores_l, ids_l = [], [], []
+            for l, cs in enumerate(cls_scores):
+                fused = cs._loft_fused
+                fh, fw = fused.shape[2], fused.shape[3]
+                out2d = fused[i].permute(1, 2, 0).reshape(-1, _FUSED_W)       # [h*w, 16] view
+                scores = out2d[:, :A].reshape(-1).sigmoid()
+                n = scores.shape[0]
+                if cfg.nms_pre > 0 and n > cfg.nms_pre:
+                    ranked, rank_inds = scores.sort(descending=True, stable=True)
+                    topk = rank_inds[:cfg.nms_pre].contiguous()
+                    scores = ranked[:cfg.nms_pre]
+                else:
+                    topk = torch.arange(n, device=dev)
+                k = topk.shape[0]
+                boxes = torch.empty((k, 4), device=dev, dtype=torch.float32)
+                stride = self.anchor_generator.strides[l][0]
+                L.call('rpn_decode', L.ptr(out2d), i32(_FUSED_W), i32(A), L.ptr(topk), i32(k),
+                       i32(fw), i32(A), L.ptr(self._base_anchors_dev[l]), L.f32(stride),
+                       L.f32(max_ratio), L.f32(img_h), L.f32(img_w), L.ptr(boxes), L.stream())
+                boxes_l.append(boxes)
+                scores_l.append(scores)
+                ids_l.append(torch.full((k,), l, device=dev, dtype=torch.long))
+            per_img_boxes.append(torch.cat(boxes_l))
+            per_img_scores.append(torch.cat(scores_l))
+            per_img_ids.append(torch.cat(ids_l))
+        same = all(b.shape[0] == per_img_boxes[0].shape[0] for b in per_img_boxes)
+        groups = [list(range(n_img))] if same else [[i] for i in range(n_img)]
+        results = [None] * n_img
+        for grp in groups:
+            sc = torch.stack([per_img_scores[i] for i in grp])
+            order = sc.sort(dim=1, descending=True, stable=True)[1]
+            bx = torch.stack([per_img_boxes[i] for i in grp])
+            ids = torch.stack([per_img_ids[i] for i in grp])
+            bx_s = torch.gather(bx, 1, order[:, :, None].expand(-1, -1, 4)).contiguous()
+            ids_s = torch.gather(ids, 1, order).contiguous()
+            sc_s = torch.gather(sc, 1, order)
+            keep, num = nms_sorted(bx_s, ids_s, float(cfg.nms_thr), int(cfg.nms_post))
+            num_h = num.tolist()
+            for j, i in enumerate(grp):
+                kk = keep[j, :num_h[j]]
+                results[i] = torch.cat([bx_s[j, kk], sc_s[j, kk, None]], dim=1)
+        return results
+
+    def simple_test_rpn(self, x, img_metas):
+        rpn_outs = self(x)
+        return self.get_bboxes(*rpn_outs, img_metas)

@@ -1,0 +1,87 @@
+"""TwoStageDetector (mmdet/models/detectors/two_stage.py:9-214)."""
+import torch
+import torch.nn as nn
+
+from ..builder import DETECTORS, build_backbone, build_head, build_neck
+from ...engine import get_store
+from .base import BaseDetector
+
+
+@DETECTORS.register_module()
+class TwoStageDetector(BaseDetector):
+    def __init__(self, backbone, neck=None, rpn_head=None, roi_head=None, train_cfg=None,
+                 test_cfg=None, pretrained=None):
+        super().__init__()
+        self.backbone = build_backbone(backbone)
+        if neck is not None:
+            self.neck = build_neck(neck)
+        if rpn_head is not None:
+            rpn_train_cfg = train_cfg.rpn if train_cfg is not None else None
+            rpn_head_ = dict(rpn_head)
+            rpn_head_.update(train_cfg=rpn_train_cfg, test_cfg=test_cfg.rpn)
+            self.rpn_head = build_head(rpn_head_)
+        if roi_head is not None:
+            rcnn_train_cfg = train_cfg.rcnn if train_cfg is not None else None
+            roi_head_ = dict(roi_head)
+            roi_head_.update(train_cfg=rcnn_train_cfg)
+            roi_head_.update(test_cfg=test_cfg.rcnn)
+            self.roi_head = build_head(roi_head_)
+        self.train_cfg, self.test_cfg = train_cfg, test_cfg
+        self.init_weights(pretrained=pretrained)
+
+    @property
+    def with_rpn(self):
+        return hasattr(self, 'rpn_head') and self.rpn_head is not None
+
+    @property
+    def with_roi_head(self):
+        return hasattr(self, 'roi_head') and self.roi_head is not None
+
+    def init_weights(self, pretrained=None):
+        self.backbone.init_weights(pretrained=pretrained)
+        if self.with_neck:
+            if isinstance(self.neck, nn.Sequential):
+                for m in self.neck:
+                    m.init_weights()
+            else:
+                self.neck.init_weights()
+        if self.with_rpn:
+            self.rpn_head.init_weights()
+        if self.with_roi_head:
+            self.roi_head.init_weights(pretrained)
+
+    def extract_feat(self, img):
+        x = self.backbone(img)
+        if self.with_neck:
+            x = self.neck(x)
+        return x
+
+    def forward_train(self, img, img_metas, gt_bboxes, gt_labels, gt_bboxes_ignore=None,
+                      gt_masks=None, proposals=None, **kwargs):
+        store = get_store(self, img.device if img.is_cuda else None)
+        store.begin_step()
+        if not img.is_cuda:
+            img = img.to(store.device, non_blocking=True)
+        dev = store.device
+        gt_bboxes = [b.to(dev, non_blocking=True) for b in gt_bboxes]
+        gt_labels = [l.to(dev, non_blocking=True) for l in gt_labels]
+        for k, v in list(kwargs.items()):
+            if isinstance(v, (list, tuple)) and len(v) and isinstance(v[0], torch.Tensor):
+                kwargs[k] = [t.to(dev, non_blocking=True) for t in v]
+        x = self.extract_feat(img)
+        losses = dict()
+        if self.with_rpn:
+            proposal_cfg = self.train_cfg.get('rpn_proposal', self.test_cfg.rpn)
+            rpn_losses, proposal_list = self.rpn_head.forward_train(
+                x, img_metas, gt_bboxes, gt_labels=None, gt_bboxes_ignore=gt_bboxes_ignore,
+                proposal_cfg=proposal_cfg)
+            losses.update(rpn_losses)
+        else:
+            proposal_list = proposals
+        roi_losses = self.roi_head.forward_train(x, img_metas, proposal_list, gt_bboxes, gt_labels,
+                                                 gt_bboxes_ignore, gt_masks, **kwargs)
+        losses.update(roi_losses)
+        return losses
+
+    def simple_test(self, img, img_metas, proposals=None, rescale=False):
+        raise NotImplementedError('inference post-processing is a SURVEY section 8(f) "next" row')

@@ -1,0 +1,77 @@
+"""LoftRoIHead (mmdet/models/roi_heads/loft_roi_head.py:22-227): StandardRoIHead + the
+roof-to-footprint offset branch."""
+import torch
+
+from .builder_alias import HEADS, build_head, build_roi_extractor
+from .standard_roi_head import StandardRoIHead
+from ...core import bbox2roi
+
+
+@HEADS.register_module()
+class LoftRoIHead(StandardRoIHead):
+    def __init__(self, offset_roi_extractor=None, offset_head=None, **kwargs):
+        assert offset_head is not None
+        super().__init__(**kwargs)
+        if offset_head is not None:
+            self.init_offset_head(offset_roi_extractor, offset_head)
+        self.with_vis_feat = False
+
+    def init_offset_head(self, offset_roi_extractor, offset_head):
+        self.offset_roi_extractor = build_roi_extractor(offset_roi_extractor)
+        self.offset_head = build_head(offset_head)
+
+    def init_weights(self, pretrained):
+        super().init_weights(pretrained)
+        self.offset_head.init_weights()
+
+    def forward_train(self, x, img_metas, proposal_list, gt_bboxes, gt_labels,
+                      gt_bboxes_ignore=None, gt_masks=None, gt_offsets=None):
+        sampling_results = self.assign_and_sample(x, img_metas, proposal_list, gt_bboxes, gt_labels,
+                                                  gt_bboxes_ignore)
+        self._last_sampling_results = sampling_results
+        losses = dict()
+        if self.with_bbox:
+            bbox_results = self._bbox_forward_train(x, sampling_results, gt_bboxes, gt_labels,
+                                                    img_metas)
+            losses.update(bbox_results['loss_bbox'])
+        if self.with_mask:
+            mask_results = self._mask_forward_train(x, sampling_results,
+                                                    bbox_results['bbox_feats'], gt_masks,
+                                                    img_metas)
+            if mask_results['loss_mask'] is not None:
+                losses.update(mask_results['loss_mask'])
+        if self.with_offset:
+            offset_results = self._offset_forward_train(x, sampling_results,
+                                                        bbox_results['bbox_feats'], gt_offsets,
+                                                        img_metas)
+            if offset_results['loss_offset'] is not None:
+                losses.update(offset_results['loss_offset'])
+        return losses
+
+    def _mask_forward_train(self, x, sampling_results, bbox_feats, gt_masks, img_metas):
+        """loft_roi_head.py:162-194 (no empty-positives early-out, unlike the parent)."""
+        pos_rois = bbox2roi([res.pos_bboxes for res in sampling_results])
+        mask_results = self._mask_forward(x, pos_rois)
+        mask_targets = self.mask_head.get_targets(sampling_results, gt_masks, self.train_cfg)
+        pos_labels = torch.cat([res.pos_gt_labels for res in sampling_results])
+        loss_mask = self.mask_head.loss(mask_results['mask_pred'], mask_targets, pos_labels)
+        mask_results.update(loss_mask=loss_mask, mask_targets=mask_targets)
+        return mask_results
+
+    def _offset_forward_train(self, x, sampling_results, bbox_feats, gt_offsets, img_metas):
+        pos_rois = bbox2roi([res.pos_bboxes for res in sampling_results])
+        offset_results = self._offset_forward(x, pos_rois)
+        offset_targets = self.offset_head.get_targets(sampling_results, gt_offsets, self.train_cfg)
+        loss_offset = self.offset_head.loss(offset_results['offset_pred'], offset_targets)
+        offset_results.update(loss_offset=loss_offset, offset_targets=offset_targets)
+        return offset_results
+
+    def _offset_forward(self, x, rois=None, pos_inds=None, bbox_feats=None):
+        assert ((rois is not None) ^ (pos_inds is not None and bbox_feats is not None))
+        if rois is not None:
+            offset_feats = self.offset_roi_extractor(x[:self.offset_roi_extractor.num_inputs], rois)
+        else:
+            assert bbox_feats is not None
+            offset_feats = bbox_feats[pos_inds]
+        offset_pred = self.offset_head(offset_feats)
+        return dict(offset_pred=offset_pred, offset_feats=offset_feats)

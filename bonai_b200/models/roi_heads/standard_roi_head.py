@@ -1,0 +1,159 @@
+"""BaseRoIHead / StandardRoIHead (mmdet/models/roi_heads/base_roi_head.py:8-154,
+standard_roi_head.py:10-290): assign + sample per image, bbox branch, mask branch."""
+from abc import ABCMeta
+
+import torch
+import torch.nn as nn
+
+from .builder_alias import HEADS, build_head, build_roi_extractor, build_shared_head
+from ...core import bbox2roi, build_assigner, build_sampler
+
+
+class BaseRoIHead(nn.Module, metaclass=ABCMeta):
+    def __init__(self, bbox_roi_extractor=None, bbox_head=None, mask_roi_extractor=None,
+                 mask_head=None, shared_head=None, train_cfg=None, test_cfg=None):
+        super().__init__()
+        self.train_cfg, self.test_cfg = train_cfg, test_cfg
+        if shared_head is not None:
+            self.shared_head = build_shared_head(shared_head)
+        if bbox_head is not None:
+            self.init_bbox_head(bbox_roi_extractor, bbox_head)
+        if mask_head is not None:
+            self.init_mask_head(mask_roi_extractor, mask_head)
+        self.init_assigner_sampler()
+
+    @property
+    def with_bbox(self):
+        return hasattr(self, 'bbox_head') and self.bbox_head is not None
+
+    @property
+    def with_mask(self):
+        return hasattr(self, 'mask_head') and self.mask_head is not None
+
+    @property
+    def with_offset(self):
+        return hasattr(self, 'offset_head') and self.offset_head is not None
+
+    @property
+    def with_shared_head(self):
+        return hasattr(self, 'shared_head') and self.shared_head is not None
+
+
+@HEADS.register_module()
+class StandardRoIHead(BaseRoIHead):
+    def init_assigner_sampler(self):
+        self.bbox_assigner = None
+        self.bbox_sampler = None
+        if self.train_cfg:
+            self.bbox_assigner = build_assigner(self.train_cfg.assigner)
+            self.bbox_sampler = build_sampler(self.train_cfg.sampler, context=self)
+
+    def init_bbox_head(self, bbox_roi_extractor, bbox_head):
+        self.bbox_roi_extractor = build_roi_extractor(bbox_roi_extractor)
+        self.bbox_head = build_head(bbox_head)
+
+    def init_mask_head(self, mask_roi_extractor, mask_head):
+        if mask_roi_extractor is not None:
+            self.mask_roi_extractor = build_roi_extractor(mask_roi_extractor)
+            self.share_roi_extractor = False
+        else:
+            self.share_roi_extractor = True
+            self.mask_roi_extractor = self.bbox_roi_extractor
+        self.mask_head = build_head(mask_head)
+
+    def init_weights(self, pretrained):
+        if self.with_shared_head:
+            self.shared_head.init_weights(pretrained=pretrained)
+        if self.with_bbox:
+            self.bbox_roi_extractor.init_weights()
+            self.bbox_head.init_weights()
+        if self.with_mask:
+            self.mask_head.init_weights()
+            if not self.share_roi_extractor:
+                self.mask_roi_extractor.init_weights()
+
+    def assign_and_sample(self, x, img_metas, proposal_list, gt_bboxes, gt_labels,
+                          gt_bboxes_ignore=None):
+        num_imgs = len(img_metas)
+        if gt_bboxes_ignore is None:
+            gt_bboxes_ignore = [None for _ in range(num_imgs)]
+        sampling_results = []
+        for i in range(num_imgs):
+            assign_result = self.bbox_assigner.assign(proposal_list[i], gt_bboxes[i],
+                                                      gt_bboxes_ignore[i], gt_labels[i])
+            sampling_results.append(self.bbox_sampler.sample(
+                assign_result, proposal_list[i], gt_bboxes[i], gt_labels[i]))
+        return sampling_results
+
+    def forward_train(self, x, img_metas, proposal_list, gt_bboxes, gt_labels,
+                      gt_bboxes_ignore=None, gt_masks=None):
+        sampling_results = self.assign_and_sample(x, img_metas, proposal_list, gt_bboxes, gt_labels,
+                                                  gt_bboxes_ignore)
+        losses = dict()
+        if self.with_bbox:
+            bbox_results = self._bbox_forward_train(x, sampling_results, gt_bboxes, gt_labels,
+                                                    img_metas)
+            losses.update(bbox_results['loss_bbox'])
+        if self.with_mask:
+            mask_results = self._mask_forward_train(x, sampling_results,
+                                                    bbox_results['bbox_feats'], gt_masks,
+                                                    img_metas)
+            if mask_results['loss_mask'] is not None:
+                losses.update(mask_results['loss_mask'])
+        return losses
+
+    def _bbox_forward(self, x, rois):
+        bbox_feats = self.bbox_roi_extractor(x[:self.bbox_roi_extractor.num_inputs], rois)
+        if self.with_shared_head:
+            bbox_feats = self.shared_head(bbox_feats)
+        cls_score, bbox_pred = self.bbox_head(bbox_feats)
+        return dict(cls_score=cls_score, bbox_pred=bbox_pred, bbox_feats=bbox_feats)
+
+    def _bbox_forward_train(self, x, sampling_results, gt_bboxes, gt_labels, img_metas):
+        rois = bbox2roi([res.bboxes for res in sampling_results])
+        bbox_results = self._bbox_forward(x, rois)
+        bbox_targets = self.bbox_head.get_targets(sampling_results, gt_bboxes, gt_labels,
+                                                  self.train_cfg)
+        loss_bbox = self.bbox_head.loss(bbox_results['cls_score'], bbox_results['bbox_pred'], rois,
+                                        *bbox_targets)
+        bbox_results.update(loss_bbox=loss_bbox)
+        return bbox_results
+
+    def _mask_forward_train(self, x, sampling_results, bbox_feats, gt_masks, img_metas):
+        if not self.share_roi_extractor:
+            pos_rois = bbox2roi([res.pos_bboxes for res in sampling_results])
+            if pos_rois.shape[0] == 0:
+                return dict(loss_mask=None)
+            mask_results = self._mask_forward(x, pos_rois)
+        else:
+            pos_inds = []
+            device = bbox_feats.device
+            for res in sampling_results:
+                pos_inds.append(torch.ones(res.pos_bboxes.shape[0], device=device,
+                                           dtype=torch.bool))
+                pos_inds.append(torch.zeros(res.neg_bboxes.shape[0], device=device,
+                                            dtype=torch.bool))
+            pos_inds = torch.cat(pos_inds)
+            if pos_inds.shape[0] == 0:
+                return dict(loss_mask=None)
+            mask_results = self._mask_forward(x, pos_inds=pos_inds, bbox_feats=bbox_feats)
+        mask_targets = self.mask_head.get_targets(sampling_results, gt_masks, self.train_cfg)
+        pos_labels = torch.cat([res.pos_gt_labels for res in sampling_results])
+        loss_mask = self.mask_head.loss(mask_results['mask_pred'], mask_targets, pos_labels)
+        mask_results.update(loss_mask=loss_mask, mask_targets=mask_targets)
+        return mask_results
+
+    def _mask_forward(self, x, rois=None, pos_inds=None, bbox_feats=None):
+        assert ((rois is not None) ^ (pos_inds is not None and bbox_feats is not None))
+        if rois is not None:
+            mask_feats = self.mask_roi_extractor(x[:self.mask_roi_extractor.num_inputs], rois)
+            if self.with_shared_head:
+                mask_feats = self.shared_head(mask_feats)
+        else:
+            assert bbox_feats is not None
+            mask_feats = bbox_feats[pos_inds]
+        mask_pred = self.mask_head(mask_feats)
+        return dict(mask_pred=mask_pred, mask_feats=mask_feats)
+
+    def simple_test(self, x, proposal_list, img_metas, proposals=None, rescale=False):
+        raise NotImplementedError('inference post-processing is a SURVEY section 8(f) "next" row')

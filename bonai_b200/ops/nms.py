@@ -1,0 +1,57 @@
+"""NMS bindings with the mmcv.ops signatures used by the reference (`nms`, `batched_nms`,
+dense_heads/rpn_head.py:166-167, core/post_processing/bbox_nms.py:63)."""
+import ctypes
+
+import torch
+
+from .. import _lib as L
+
+i32 = ctypes.c_int
+
+
+def nms_sorted(boxes, idxs, iou_threshold, max_keep=-1):
+    """boxes [B,n,4] sorted by score (desc) per image, idxs [B,n] int64 or None.
+    Returns keep [B,n] (positions in the sorted order, first num_keep valid) and num_keep [B]."""
+    B, n, _ = boxes.shape
+    keep = torch.empty((B, n), device=boxes.device, dtype=torch.long)
+    num = torch.zeros((B,), device=boxes.device, dtype=torch.int32)
+    if n == 0 or B == 0:
+        return keep, num
+    ws_bytes = B * L.lib().loft_nms_workspace(i32(n))
+    ws = torch.empty((ws_bytes,), device=boxes.device, dtype=torch.uint8)
+    L.call('nms_sorted', L.ptr(boxes.contiguous()), L.ptr(idxs.contiguous()) if idxs is not None else None,
+           i32(B), i32(n), L.f32(iou_threshold), i32(max_keep), L.ptr(keep), L.ptr(num), L.ptr(ws),
+           ctypes.c_size_t(ws_bytes), L.stream())
+    return keep, num
+
+
+def nms(boxes, scores, iou_threshold, offset=0):
+    """mmcv.ops.nms: returns (dets[k,5], inds[k]) with inds in score-descending order
+    (ties keep input order)."""
+    assert offset == 0
+    if boxes.shape[0] == 0:
+        return boxes.new_zeros((0, 5)), torch.zeros(0, dtype=torch.long, device=boxes.device)
+    order = torch.sort(scores, descending=True, stable=True)[1]
+    keep, num = nms_sorted(boxes[order].float()[None], None, float(iou_threshold))
+    k = int(num[0])
+    inds = order[keep[0, :k]]
+    return torch.cat([boxes[inds], scores[inds, None]], dim=1), inds
+
+
+def batched_nms(boxes, scores, idxs, nms_cfg, class_agnostic=False):
+    """mmcv.ops.batched_nms (v1.0.5): boxes of different `idxs` never suppress each other (fp32
+    coordinate-offset trick, applied inside the kernel)."""
+    cfg = dict(nms_cfg)
+    class_agnostic = cfg.pop('class_agnostic', class_agnostic)
+    typ = cfg.pop('type', 'nms')
+    if typ != 'nms':
+        raise NotImplementedError(f'batched_nms type {typ!r}: only hard NMS is on the CUDA path')
+    thr = float(cfg.pop('iou_threshold'))
+    if boxes.shape[0] == 0:
+        return boxes.new_zeros((0, 5)), torch.zeros(0, dtype=torch.long, device=boxes.device)
+    order = torch.sort(scores, descending=True, stable=True)[1]
+    ids = None if class_agnostic else idxs[order].long()[None]
+    keep, num = nms_sorted(boxes[order].float()[None], ids, thr)
+    k = int(num[0])
+    inds = order[keep[0, :k]]
+    return torch.cat([boxes[inds], scores[inds, None]], dim=-1), inds

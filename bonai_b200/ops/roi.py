@@ -1,0 +1,116 @@
+"""RoIAlign / mask-target bindings (mirror of mmcv.ops.RoIAlign / roi_align at the reference call
+sites roi_extractors/base_roi_extractor.py:49-55, single_level_roi_extractor.py:53-80 and
+core/mask/structures.py:286-287)."""
+import ctypes
+
+import torch
+import torch.nn as nn
+from torch.autograd import Function
+from torch.nn.modules.utils import _pair
+
+from .. import _lib as L
+from .dense import nhwc, new_nhwc
+
+i32 = ctypes.c_int
+
+
+def _pyramid_args(feats_nhwc, scales):
+    n = len(feats_nhwc)
+    ptrs = (ctypes.c_void_p * n)(*[f.data_ptr() for f in feats_nhwc])
+    Hs = (ctypes.c_int * n)(*[f.shape[1] for f in feats_nhwc])
+    Ws = (ctypes.c_int * n)(*[f.shape[2] for f in feats_nhwc])
+    sc = (ctypes.c_float * n)(*[float(s) for s in scales])
+    return ptrs, Hs, Ws, sc
+
+
+class _MultiLevelRoIAlign(Function):
+    """All FPN levels in one launch; the level of each RoI is computed in-kernel."""
+
+    @staticmethod
+    def forward(ctx, rois, out_size, scales, finest_scale, *feats):
+        fn = [nhwc(f) for f in feats]
+        K = rois.shape[0]
+        C = fn[0].shape[-1]
+        rois = rois.contiguous().float()
+        out = new_nhwc(K, C, out_size, out_size, rois.device)
+        ptrs, Hs, Ws, sc = _pyramid_args(fn, scales)
+        L.call('roi_align_fwd', ptrs, Hs, Ws, sc, i32(len(fn)), L.ptr(rois), L.ll(K), i32(out_size),
+               i32(C), L.f32(finest_scale), L.ptr(out.permute(0, 2, 3, 1)), None, L.stream())
+        ctx.save_for_backward(rois)
+        ctx.meta = (out_size, tuple(scales), finest_scale, [tuple(f.shape) for f in fn])
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (rois,) = ctx.saved_tensors
+        out_size, scales, finest, shapes = ctx.meta
+        K = rois.shape[0]
+        dn = nhwc(dout)
+        C = dn.shape[-1]
+        grads = [torch.zeros(s, device=dout.device, dtype=torch.float32) for s in shapes]
+        ptrs, Hs, Ws, sc = _pyramid_args(grads, scales)
+        L.call('roi_align_bwd', ptrs, Hs, Ws, sc, i32(len(grads)), L.ptr(rois), L.ll(K),
+               i32(out_size), i32(C), L.f32(finest), L.ptr(dn), L.stream())
+        return (None, None, None, None) + tuple(g.permute(0, 3, 1, 2) for g in grads)
+
+
+def multilevel_roi_align(feats, rois, out_size, strides, finest_scale=56):
+    C = feats[0].shape[1]
+    if rois.shape[0] == 0:
+        return feats[0].new_zeros((0, C, out_size, out_size))
+    return _MultiLevelRoIAlign.apply(rois, int(out_size), [1.0 / s for s in strides],
+                                     float(finest_scale), *feats)
+
+
+def roi_align(input, rois, output_size, spatial_scale=1.0, sampling_ratio=0, pool_mode='avg',
+              aligned=True):
+    """Functional single-level form with the mmcv signature (structures.py:286-287)."""
+    if pool_mode != 'avg' or sampling_ratio != 0 or not aligned:
+        raise NotImplementedError('LOFT path: RoIAlign is avg / sampling_ratio=0 / aligned=True '
+                                  '(bonai_loft_foa_r50_fpn_basic.py:39,56,71)')
+    oh, ow = _pair(output_size)
+    assert oh == ow
+    # a single level: finest_scale large enough that every RoI maps to level 0
+    return _MultiLevelRoIAlign.apply(rois, int(oh), [float(spatial_scale)], 1e30, input)
+
+
+class RoIAlign(nn.Module):
+    """Same constructor / attributes as mmcv.ops.RoIAlign (output_size tuple, aligned,
+    use_torchvision are consulted by the reference, single_level_roi_extractor.py:56,
+    tests/test_config.py:276-291)."""
+
+    def __init__(self, output_size, spatial_scale=1.0, sampling_ratio=0, pool_mode='avg',
+                 aligned=True, use_torchvision=False):
+        super().__init__()
+        self.output_size = _pair(output_size)
+        self.spatial_scale = float(spatial_scale)
+        self.sampling_ratio = int(sampling_ratio)
+        self.pool_mode = pool_mode
+        self.aligned = aligned
+        self.use_torchvision = use_torchvision
+
+    def forward(self, input, rois):
+        return roi_align(input, rois, self.output_size, self.spatial_scale, self.sampling_ratio,
+                         self.pool_mode, self.aligned)
+
+    def __repr__(self):
+        return (f'{self.__class__.__name__}(output_size={self.output_size}, '
+                f'spatial_scale={self.spatial_scale}, sampling_ratio={self.sampling_ratio}, '
+                f'pool_mode={self.pool_mode}, aligned={self.aligned}, '
+                f'use_torchvision={self.use_torchvision})')
+
+
+def mask_target_sample(masks_u8, boxes, gt_inds, size):
+    """RoIAlign(size x size, scale 1, aligned) of each proposal over its assigned uint8 GT bitmap,
+    thresholded at 0.5 (mask_target.py:31-62 + structures.py:261-291) -- reads the uint8 masks
+    in place, no fp32 copy of the bitmaps."""
+    P = boxes.shape[0]
+    out = torch.empty((P, size, size), device=boxes.device, dtype=torch.float32)
+    if P == 0:
+        return out
+    G, H, W = masks_u8.shape
+    assert masks_u8.dtype == torch.uint8 and masks_u8.is_contiguous()
+    L.call('mask_target', L.ptr(masks_u8), L.ptr(boxes.contiguous().float()),
+           L.ptr(gt_inds.contiguous().long()), L.ll(P), i32(size), i32(H), i32(W), L.ptr(out),
+           L.stream())
+    return out

@@ -43,6 +43,7 @@ typedef struct loft_epilogue_t {
   int res_upsample2x;
   int relu;
   int deconv_shuffle;
+  int round_out; /* round out[] to TF32 (round-to-nearest) for the consuming tensor-core op */
 } loft_epilogue_t;
 
 /* ---- dense contractions on tcgen05 (TF32 operands, fp32 accumulate in TMEM) -------------------
@@ -66,6 +67,96 @@ int loft_conv3x3_wgrad(const float* dy, const float* x, float* dw, int N, int H,
 /* bring-up only: override UMMA descriptor fields (-1 = keep default) */
 void loft_debug_set_desc(long long a_desc, long long b_desc, long long a_kstep, long long b_kstep,
                          long long idesc);
+
+/* ---- HBM-bound layout / activation / optimizer kernels (elementwise.cu) ------------------------
+ * BN-eval fold + backward: resnet.py:260-300,640-649; im2col for the 7x7/2 stem and the three
+ * stride-2 3x3 convs: resnet.py:525-571,151-203; maxpool resnet.py:571,631; FPN extra level and
+ * top-down backward: fpn.py:185-199; FOA rotation: offset_head_expand_feature.py:163-196
+ * (affine_grid+grid_sample == rot90); optimizer: mmcv OptimizerHook(grad_clip) +
+ * torch.optim.SGD as configured by configs/_base_/schedules/schedule_2x_bonai.py:2-3. */
+int loft_copy2d(const float* src, long long lds, float* dst, long long ldd, long long rows, int cols,
+                int accumulate, int round_tf32, cudaStream_t stream);
+int loft_permute_acb(const float* src, float* dst, int A, int B, int C, int accumulate,
+                     int round_tf32, cudaStream_t stream);
+int loft_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var,
+                 float eps, float* scale, float* shift, float* rstd, int C, cudaStream_t stream);
+int loft_act_bwd(const float* dy, const float* y, const float* z, const float* scale,
+                 const float* mean, const float* rstd, float* dz, float* dres, float* dgamma,
+                 float* dbeta, long long P, int C, int relu, cudaStream_t stream);
+int loft_im2col(const float* x, float* col, int N, int H, int W, int C, int kh, int kw, int stride,
+                int pad, int Kpad, int nchw_input, cudaStream_t stream);
+int loft_col2im(const float* dcol, float* dx, const float* mask, int N, int H, int W, int C, int kh,
+                int kw, int stride, int pad, int Kpad, cudaStream_t stream);
+int loft_maxpool3x3s2(const float* x, float* y, int N, int H, int W, int C, cudaStream_t stream);
+int loft_subsample2(const float* x, float* y, int N, int H, int W, int C, cudaStream_t stream);
+int loft_subsample2_bwd(const float* dy, float* dx, const float* mask, int N, int H, int W, int C,
+                        cudaStream_t stream);
+int loft_sum2x2_add(const float* fine, const float* base, float* out, int N, int H, int W, int C,
+                    cudaStream_t stream);
+int loft_rot90(const float* x, float* y, long long K, int S, int C, int k, cudaStream_t stream);
+int loft_add(const float* a, const float* b, float* out, long long n, int round_tf32,
+             cudaStream_t stream);
+int loft_grad_sqnorm(const float* g, long long n, double* out, cudaStream_t stream);
+int loft_sgd_clip_step(float* p, const float* g, float* m, float* p_tf32, long long n, float lr,
+                       float momentum, float weight_decay, float max_norm, float grad_scale,
+                       const double* sqnorm, cudaStream_t stream);
+
+/* ---- RoIAlign over the FPN pyramid + mask-target sampling (roi_align.cu) -----------------------
+ * replace mmcv.ops.RoIAlign / roi_align at single_level_roi_extractor.py:32-80 and
+ * core/mask/structures.py:261-291 (+ mask_target.py:31-62).  rois [K,5] = (batch, x1,y1,x2,y2);
+ * out is [K,S,S,C] (NHWC). */
+int loft_roi_align_fwd(const float* const* feats, const int* Hs, const int* Ws, const float* scales,
+                       int num_levels, const float* rois, long long K, int S, int C,
+                       float finest_scale, float* out, int* levels_out, cudaStream_t stream);
+int loft_roi_align_bwd(float* const* grads, const int* Hs, const int* Ws, const float* scales,
+                       int num_levels, const float* rois, long long K, int S, int C,
+                       float finest_scale, const float* dout, cudaStream_t stream);
+int loft_mask_target(const uint8_t* masks, const float* boxes, const long long* gt_inds, long long P,
+                     int S, int H, int W, float* out, cudaStream_t stream);
+
+/* ---- assignment / proposals / NMS / target encoders (detect.cu) ---------------------------------
+ * max_iou_assigner.py:127-212 + iou2d_calculator.py:39-130; rpn_head.py:79-168 +
+ * anchor_generator.py:142-271 + delta_xywh_bbox_coder.py:119-197; mmcv.ops.batched_nms;
+ * delta_xywh_bbox_coder.py:74-116; offset_head_expand_feature.py:271-344 +
+ * delta_xy_offset_coder.py:46-65. */
+size_t loft_iou_assign_workspace(long long n, int G);
+int loft_iou_assign(const float* boxes, long long n, const float* gts, int G, float pos_thr,
+                    float neg_thr, float min_pos, int match_low_quality, long long* gt_inds,
+                    float* max_overlaps, void* workspace, size_t ws_bytes, cudaStream_t stream);
+int loft_rpn_decode(const float* head_out, int ld, int reg_off, const long long* topk_idx, int k,
+                    int fw, int A, const float* base_anchors, float stride, float max_ratio,
+                    float img_h, float img_w, float* boxes_out, cudaStream_t stream);
+size_t loft_nms_workspace(int n);
+int loft_nms_sorted(const float* boxes, const long long* idxs, int B, int n, float iou_thr,
+                    int max_keep, long long* keep, int* num_keep, void* workspace, size_t ws_bytes,
+                    cudaStream_t stream);
+int loft_bbox_encode(const float* props, const float* gts, long long n, float s0, float s1, float s2,
+                     float s3, float* out, cudaStream_t stream);
+int loft_offset_target(const float* props, const float* gt_offsets, const long long* gt_inds,
+                       long long P, float std_x, float std_y, float* out, cudaStream_t stream);
+
+/* ---- losses (loss.cu) ----------------------------------------------------------------------------
+ * mode 0 = BCE-with-logits (cross_entropy_loss.py:58-125), 1 = L1, 2 = SmoothL1
+ * (smooth_l1_loss.py:8-42); sums are accumulated into device scalars (weight_reduce_loss,
+ * losses/utils.py:26-52); gscale is the device-resident upstream gradient (NULL = 1). */
+int loft_elem_loss_fwd(int mode, const float* pred, long long ld, int col_off, int ncols,
+                       long long rows, const float* target, const float* weight, float beta,
+                       float scale, float* out_sum, cudaStream_t stream);
+int loft_elem_loss_bwd(int mode, const float* pred, long long ld, int col_off, int ncols,
+                       long long rows, const float* target, const float* weight, float beta,
+                       float scale, const float* gscale, float* dpred, cudaStream_t stream);
+int loft_softmax_ce_fwd(const float* logits, long long ld, int C, long long n,
+                        const long long* labels, const float* weight, float scale, float* out2,
+                        cudaStream_t stream);
+int loft_softmax_ce_bwd(const float* logits, long long ld, int C, long long n,
+                        const long long* labels, const float* weight, float scale,
+                        const float* gscale, float* dlogits, cudaStream_t stream);
+int loft_sigmoid_focal_loss_fwd(const float* x, const long long* target, const float* weight,
+                                long long n, int C, float gamma, float alpha, float* loss,
+                                cudaStream_t stream);
+int loft_sigmoid_focal_loss_bwd(const float* x, const long long* target, const float* weight,
+                                long long n, int C, float gamma, float alpha, const float* dloss,
+                                float* dx, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

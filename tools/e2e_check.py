@@ -1,0 +1,85 @@
+"""Whole-step parity on the GPU: product (CUDA kernels) vs the CPU oracle, teacher-forced
+(identical weights, oracle's proposals and sampler draws injected).  Prints a JSON report."""
+import json
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import loft_cpu as O  # noqa: E402
+from bonai_b200 import Config  # noqa: E402
+from bonai_b200.models import build_detector  # noqa: E402
+from bonai_b200.core import BitmapMasks  # noqa: E402
+from bonai_b200.core.bbox import RandomSampler  # noqa: E402
+from bonai_b200.models.dense_heads import RPNHead  # noqa: E402
+
+CFG = os.path.join(ROOT, 'configs', 'loft', 'loft_foa_r50_fpn_2x_b200.py')
+
+
+def run(size=256, n_img=1, num_gt=10, seed=0, force_proposals=True, verbose=True):
+    p = O.randomize_bn(O.init_params(seed), seed)
+    img, gb, gl, gm, go = O.make_inputs(seed, n_img, size, num_gt)
+    tk = set(O.trainable_keys(p))
+    po = {k: (v.clone().requires_grad_(True) if k in tk else v) for k, v in p.items()}
+    torch.manual_seed(123)
+    rec, aux = [], {}
+    t0 = time.time()
+    lo = O.forward_train(po, img, gb, gl, gm, go, record=rec, aux=aux, stable_sort=True)
+    loss_o, logs_o = O.parse_losses(lo)
+    loss_o.backward()
+    t_oracle = time.time() - t0
+
+    cfg = Config.fromfile(CFG)
+    model = build_detector(cfg.model, train_cfg=cfg.train_cfg, test_cfg=cfg.test_cfg)
+    model.load_state_dict(p)
+    model.train()
+    dev = torch.device('cuda:0')
+    RandomSampler.forced_choices = [r.clone() for r in rec]
+    RPNHead.forced_proposals = [q.clone() for q in aux['proposals']] if force_proposals else None
+    metas = [dict(img_shape=(size, size, 3), pad_shape=(size, size, 3), ori_shape=(size, size, 3),
+                  scale_factor=1.0, flip=False) for _ in range(n_img)]
+    losses = model.forward_train(img.to(dev), metas, gb, gl,
+                                 gt_masks=[BitmapMasks(m, size, size) for m in gm], gt_offsets=go)
+    loss, logs = model._parse_losses(losses)
+    loss.backward()
+    torch.cuda.synchronize()
+    RandomSampler.forced_choices = None
+    RPNHead.forced_proposals = None
+    rep = {'losses': {}, 'grads': {}}
+    worst = 0.0
+    for k, v in logs_o.items():
+        a, b = float(logs[k]), float(v)
+        rel = abs(a - b) / max(abs(b), 1e-6)
+        rep['losses'][k] = [a, b, rel]
+        if 'loss' in k:
+            worst = max(worst, rel)
+    rep['worst_loss_rel'] = worst
+    gworst, gname = 0.0, None
+    named = dict(model.named_parameters())
+    for k in tk:
+        go_ = po[k].grad
+        gp = named[k].grad
+        if go_ is None or gp is None:
+            rep['grads'][k] = 'missing'
+            continue
+        d = float((gp.detach().cpu().double() - go_.double()).norm())
+        n = float(go_.double().norm())
+        rel = d / max(n, 1e-12)
+        if n > 1e-8 and rel > gworst:
+            gworst, gname = rel, k
+        if verbose and n > 1e-8 and rel > 2e-2:
+            rep['grads'][k] = [d, n, rel]
+    rep['worst_grad_rel'] = [gworst, gname]
+    rep['oracle_seconds'] = t_oracle
+    return rep
+
+
+if __name__ == '__main__':
+    size = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+    n_img = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    num_gt = int(sys.argv[3]) if len(sys.argv) > 3 else 10
+    rep = run(size, n_img, num_gt)
+    print(json.dumps(rep, indent=1))
