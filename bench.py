@@ -222,6 +222,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='loft_b200', choices=['loft_b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--profile', action='store_true', help='timed steps only (for ncu)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != 'reference' else args.warmup
     if args.impl == 'reference':
@@ -279,6 +280,12 @@ def main():
     ms = float(t.item())
     value = BATCH * world * args.steps / (ms * 1e-3)
 
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({'metric': METRIC, 'value': round(value, 3), 'unit': 'img/s',
+                              'ms_per_step': round(ms / args.steps, 3), 'profile_run': True,
+                              'gpu_launches': launches}))
+        return
     # ---- end to end: pinned host inputs copied every step, loss read back every step
     host_batch = make_batch(seed=rank, pinned=True)
     h2d_bytes = 0

@@ -230,10 +230,10 @@ class ParamStore:
 def get_store(model, device=None):
     st = getattr(model, '_loft_store', None)
     if st is None:
-        if device is None:
-            device = torch.device('cuda', torch.cuda.current_device())
         if not torch.cuda.is_available():
             raise L.LoftError('the LOFT hot path needs a CUDA device (sm_100a); there is no CPU '
                               'fallback')
+        if device is None:
+            device = torch.device('cuda', torch.cuda.current_device())
         st = ParamStore(model, device)
     return st
