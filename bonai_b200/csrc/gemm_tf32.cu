@@ -24,8 +24,10 @@ constexpr int kKB = 32;                       // k elements per stage (128 B of 
 constexpr int kABytes = kBlockC * kKB * 4;    // 16 KB
 constexpr int kBBytes = kMaxN * kKB * 4;      // 32 KB
 constexpr int kStageBytes = kABytes + kBBytes;
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int kThreads = 192;                 // warp0 TMA, warp1 MMA, warps2-5 epilogue
+constexpr int kRowTabBytes = 2 * 2 * kMaxN * 4;  // 2 accumulator stages x (out row, residual row)
+constexpr int kSmemBytes =
+    kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kRowTabBytes;
+constexpr int kThreads = 320;                 // warp0 TMA, warp1 MMA, warps2-9 epilogue
 constexpr int kTmemCols = 512;                // 2 accumulator stages x 256 columns
 
 enum Mode {
@@ -104,6 +106,7 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint64_t* tfull_bar = bars + 2 * kStages;     // [2]
   uint64_t* tempty_bar = bars + 2 * kStages + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  int* row_tab = reinterpret_cast<int*>(smem + kStages * kStageBytes + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -117,7 +120,7 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], 8);
     }
     mbar_fence_init();
   }
@@ -236,8 +239,13 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5)
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ------------------------------------------------------------ epilogue (warps 2..9)
+    // Lane quarter q = warp & 3 (TMEM access rule); the two warps of a quarter split the 16-column
+    // chunks.  Output row indices are computed ONCE per tile (one column per epilogue thread)
+    // into shared memory, so the per-element loop is: LDS row, IMAD.WIDE, (LDG), FFMA, STG.
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int et = (int)threadIdx.x - 64;  // 0..255
     uint32_t lt = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
       int t = tile;
@@ -250,6 +258,45 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
         tap = t % p.ntaps;
       }
       const uint32_t as = lt & 1u, aph = (lt >> 1) & 1u;
+      int* s_row = row_tab + as * (2 * kMaxN);
+      int* s_rrow = s_row + kMaxN;
+      if (!is_wgrad) {
+        const int col = et;
+        int row = -1, rrow = 0;
+        if (col < p.n_mma) {
+          long long pix;
+          int pn = 0, ph_ = 0, pw_ = 0;
+          bool ok;
+          if (p.mode == FPROP_CONV || p.mode == DGRAD_CONV) {
+            int n0, h0, w0;
+            tile_pixel_origin(p, pt, n0, h0, w0);
+            const int thw = p.th * p.tw;
+            const int jn = col / thw, r = col - jn * thw;
+            const int jh = r / p.tw, jw = r - jh * p.tw;
+            pn = n0 + jn;
+            ph_ = h0 + jh;
+            pw_ = w0 + jw;
+            ok = (jn < p.tn) && (pn < p.N) && (ph_ < p.H) && (pw_ < p.W);
+            pix = ((long long)pn * p.H + ph_) * p.W + pw_;
+          } else {
+            pix = (long long)pt * p.n_mma + col;
+            ok = pix < p.P;
+            if (ok && (p.res_mode == 2 || p.out_map == 1)) {
+              pw_ = (int)(pix % p.W);
+              const long long r = pix / p.W;
+              ph_ = (int)(r % p.H);
+              pn = (int)(r / p.H);
+            }
+          }
+          if (ok) {
+            row = (p.out_map == 1) ? (pn * (2 * p.H) + 2 * ph_) * (2 * p.W) + 2 * pw_ : (int)pix;
+            if (p.res_mode == 2) rrow = (pn * (p.H >> 1) + (ph_ >> 1)) * (p.W >> 1) + (pw_ >> 1);
+          }
+        }
+        s_row[col] = row;
+        s_rrow[col] = rrow;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
       const int c = ct * kBlockC + q * 32 + lane;
@@ -260,7 +307,7 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
         float* drow = p.out + (long long)c * p.ldw + (long long)tap * p.tap_stride +
                       (long long)pt * p.n_mma;
         const int ncol = min(p.n_mma, p.Cn - pt * p.n_mma);
-        for (int cc = 0; cc < p.n_mma; cc += 16) {
+        for (int cc = half * 16; cc < p.n_mma; cc += 32) {
           float v[16];
           tmem_ld16(taddr + cc, v);
           if (c_ok) {
@@ -272,68 +319,53 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
       } else {
         const float sc = (p.scale != nullptr && c_ok) ? p.scale[c] : 1.f;
         const float sh = (p.shift != nullptr && c_ok) ? p.shift[c] : 0.f;
-        int n0 = 0, h0 = 0, w0 = 0;
-        const bool conv = (p.mode == FPROP_CONV || p.mode == DGRAD_CONV);
-        if (conv) tile_pixel_origin(p, pt, n0, h0, w0);
-        const int thw = p.th * p.tw;
-        for (int cc = 0; cc < p.n_mma; cc += 16) {
+        int ocol = c, row_add = 0;
+        if (p.out_map == 1) {
+          // deconv 2x2 stride 2: channel index c = (i*2 + j2)*Co + co
+          const int co_n = p.Cm >> 2;
+          const int ij = c / co_n;
+          ocol = c - ij * co_n;
+          row_add = (ij >> 1) * (2 * p.W) + (ij & 1);
+        }
+        const float* __restrict__ res = p.residual;
+        const float* __restrict__ msk = p.mask;
+        for (int cc = half * 16; cc < p.n_mma; cc += 32) {
           float v[16];
           tmem_ld16(taddr + cc, v);
           if (!c_ok) continue;
+          int rows[16];
+          float rv[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) rows[j] = s_row[cc + j];
+          if (p.res_mode == 1) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              rv[j] = rows[j] >= 0 ? res[(long long)(rows[j] + row_add) * p.ldr + ocol] : 0.f;
+          } else if (p.res_mode == 2) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              rv[j] = rows[j] >= 0 ? res[(long long)s_rrow[cc + j] * p.ldr + ocol] : 0.f;
+          } else if (msk != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              rv[j] = rows[j] >= 0 ? msk[(long long)(rows[j] + row_add) * p.ldo + ocol] : 0.f;
+          }
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const int col = cc + j;
-            long long pix;     // flat pixel index (n*H + h)*W + w
-            int pn, ph_, pw_;  // decoded coordinates (conv / mapped modes)
-            bool ok;
-            if (conv) {
-              const int jn = col / thw, r = col - jn * thw;
-              const int jh = r / p.tw, jw = r - jh * p.tw;
-              pn = n0 + jn;
-              ph_ = h0 + jh;
-              pw_ = w0 + jw;
-              ok = (jn < p.tn) && (pn < p.N) && (ph_ < p.H) && (pw_ < p.W);
-              pix = ((long long)pn * p.H + ph_) * p.W + pw_;
-            } else {
-              pix = (long long)pt * p.n_mma + col;
-              ok = pix < p.P;
-              pn = ph_ = pw_ = 0;
-              if (ok && (p.res_mode == 2 || p.out_map == 1)) {
-                pw_ = (int)(pix % p.W);
-                long long r = pix / p.W;
-                ph_ = (int)(r % p.H);
-                pn = (int)(r / p.H);
-              }
-            }
-            if (!ok) continue;
+            if (rows[j] < 0) continue;
+            const long long o = (long long)(rows[j] + row_add) * p.ldo + ocol;
             float acc = v[j];
-            long long orow = pix;
-            int ocol = c;
-            if (p.out_map == 1) {
-              // deconv 2x2 stride 2: channel index c = (i*2 + j2)*Co + co
-              const int co_n = p.Cm >> 2;
-              const int ij = c / co_n;
-              ocol = c - ij * co_n;
-              orow = ((long long)pn * (2 * p.H) + (2 * ph_ + (ij >> 1))) * (2 * p.W) +
-                     (2 * pw_ + (ij & 1));
-            }
-            if (p.raw_out != nullptr) p.raw_out[orow * p.ldo + ocol] = acc;
+            if (p.raw_out != nullptr) p.raw_out[o] = acc;
             acc = fmaf(acc, sc, sh);
-            if (p.res_mode == 1) {
-              acc += p.residual[orow * p.ldr + ocol];
-            } else if (p.res_mode == 2) {
-              const long long rrow =
-                  ((long long)pn * (p.H >> 1) + (ph_ >> 1)) * (p.W >> 1) + (pw_ >> 1);
-              acc += p.residual[rrow * p.ldr + ocol];
-            }
+            if (p.res_mode != 0) acc += rv[j];
             if (p.relu) acc = fmaxf(acc, 0.f);
-            if (p.mask != nullptr) acc = (p.mask[orow * p.ldo + ocol] > 0.f) ? acc : 0.f;
+            if (msk != nullptr) acc = (rv[j] > 0.f) ? acc : 0.f;
             if (p.round_out) {
               uint32_t rr;
               asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(rr) : "f"(acc));
               acc = __uint_as_float(rr);
             }
-            p.out[orow * p.ldo + ocol] = acc;
+            p.out[o] = acc;
           }
         }
       }
