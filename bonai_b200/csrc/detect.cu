@@ -207,60 +207,51 @@ __global__ void nms_mask_kernel(const float* __restrict__ boxes, const long long
   mask[(long long)i * nwords + colb] = bits;
 }
 
-// One block per image: greedy scan in 64-box chunks.
-constexpr int kScanThreads = 256;
+// One block per image: greedy scan in 64-box chunks.  For chunk c the suppression word of the
+// chunk is gathered lazily: OR over every box kept so far of mask[kept][c] (independent loads
+// spread over the block, reduced with warp shuffles), then one thread resolves the 64 boxes of
+// the chunk against the diagonal block.  No per-chunk update of a global "removed" bitmap.
+constexpr int kScanThreads = 512;
 constexpr int kMaxWords = 2048;  // n <= 131072
-__global__ void nms_scan_kernel(const unsigned long long* __restrict__ mask, int n, int nwords,
-                                int max_keep, long long* __restrict__ keep,
-                                int* __restrict__ num_keep, long long mask_stride,
-                                long long keep_stride) {
-  __shared__ unsigned long long removed[kMaxWords];
+__global__ void __launch_bounds__(kScanThreads)
+nms_scan_kernel(const unsigned long long* __restrict__ mask, int n, int nwords, int max_keep,
+                long long* __restrict__ keep, int* __restrict__ num_keep, long long mask_stride,
+                long long keep_stride) {
   __shared__ unsigned long long diag[64];
-  __shared__ unsigned long long s_kept;
+  __shared__ unsigned long long warp_or[kScanThreads / 32];
   __shared__ int s_count;
   const int img = blockIdx.x;
   mask += (long long)img * mask_stride;
   keep += (long long)img * keep_stride;
   const int t = threadIdx.x;
-  for (int w = t; w < nwords; w += kScanThreads) removed[w] = 0ull;
   if (t == 0) s_count = 0;
   __syncthreads();
   for (int c = 0; c < nwords; ++c) {
-    if (s_count >= max_keep) break;
+    const int cnt0 = s_count;
+    if (cnt0 >= max_keep) break;
+    unsigned long long acc = 0ull;
+    for (int k = t; k < cnt0; k += kScanThreads) acc |= mask[keep[k] * (long long)nwords + c];
     if (t < 64) {
       const int i = c * 64 + t;
       diag[t] = (i < n) ? mask[(long long)i * nwords + c] : 0ull;
     }
+    unsigned int lo = (unsigned int)acc, hi = (unsigned int)(acc >> 32);
+    lo = __reduce_or_sync(0xffffffffu, lo);
+    hi = __reduce_or_sync(0xffffffffu, hi);
+    if ((t & 31) == 0) warp_or[t >> 5] = ((unsigned long long)hi << 32) | lo;
     __syncthreads();
     if (t == 0) {
-      unsigned long long rem = removed[c], kept = 0ull;
-      int cnt = s_count;
+      unsigned long long rem = 0ull;
+      for (int w = 0; w < kScanThreads / 32; ++w) rem |= warp_or[w];
+      int cnt = cnt0;
       const int lim = min(64, n - c * 64);
-      for (int b = 0; b < lim; ++b) {
+      for (int b = 0; b < lim && cnt < max_keep; ++b) {
         if (!((rem >> b) & 1ull)) {
-          if (cnt < max_keep) {
-            keep[cnt] = c * 64 + b;
-            kept |= 1ull << b;
-          }
-          ++cnt;
+          keep[cnt++] = c * 64 + b;
           rem |= diag[b];
         }
       }
-      s_kept = kept;
-      s_count = cnt < max_keep ? cnt : max_keep;
-    }
-    __syncthreads();
-    const unsigned long long kept = s_kept;
-    if (kept) {
-      for (int w = c + 1 + t; w < nwords; w += kScanThreads) {
-        unsigned long long acc = 0ull, k2 = kept;
-        while (k2) {
-          const int b = __ffsll((long long)k2) - 1;
-          k2 &= k2 - 1;
-          acc |= mask[(long long)(c * 64 + b) * nwords + w];
-        }
-        removed[w] |= acc;
-      }
+      s_count = cnt;
     }
     __syncthreads();
   }

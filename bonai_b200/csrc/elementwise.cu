@@ -80,32 +80,77 @@ __global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __r
 }
 
 // g = dy * (y>0 if relu);  dz = round(g*scale) ; dres = g ; dbeta += sum g ; dgamma += sum g*xhat
-// Threads run along C (coalesced), each block reduces a slab of rows.
-__global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
-                               const float* __restrict__ z, const float* __restrict__ scale,
-                               const float* __restrict__ mean, const float* __restrict__ rstd,
-                               float* __restrict__ dz, float* __restrict__ dres,
-                               float* __restrict__ dgamma, float* __restrict__ dbeta, long long P,
-                               int C, int relu, int rows_per_block) {
+// float4 along C; a block covers `rpb` rows per iteration over its slab of rows, partial channel
+// sums are combined in shared memory before one atomicAdd per channel per block.
+__global__ void __launch_bounds__(256)
+act_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ y,
+               const float4* __restrict__ z, const float4* __restrict__ scale,
+               const float4* __restrict__ mean, const float4* __restrict__ rstd,
+               float4* __restrict__ dz, float4* __restrict__ dres, float* __restrict__ dgamma,
+               float* __restrict__ dbeta, long long P, int cvec, int relu, long long rows_per_block) {
+  __shared__ float4 sm_b[256], sm_g[256];
+  const int tpr = cvec < 256 ? cvec : 256;  // threads per row
+  const int rpb = 256 / tpr;                // rows per block iteration
+  const int tr = threadIdx.x / tpr, tc = threadIdx.x % tpr;
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   long long r1 = r0 + rows_per_block;
   if (r1 > P) r1 = P;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float sc = scale ? scale[c] : 1.f;
-    const float mu = mean ? mean[c] : 0.f;
-    const float rs = rstd ? rstd[c] : 1.f;
-    float sb = 0.f, sg = 0.f;
-    for (long long r = r0; r < r1; ++r) {
-      const long long i = r * C + c;
-      float g = dy[i];
-      if (relu && !(y[i] > 0.f)) g = 0.f;
-      sb += g;
-      if (z) sg += g * (z[i] - mu) * rs;
-      if (dres) dres[i] = g;
-      if (dz) dz[i] = tf32_rna(g * sc);
+  const bool active = tr < rpb;
+  for (int cg = tc; cg < cvec; cg += tpr) {
+    const float4 sc = scale ? scale[cg] : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float4 mu = mean ? mean[cg] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 rs = rstd ? rstd[cg] : make_float4(1.f, 1.f, 1.f, 1.f);
+    float4 sb = make_float4(0.f, 0.f, 0.f, 0.f), sg = sb;
+    if (active) {
+      for (long long r = r0 + tr; r < r1; r += rpb) {
+        const long long i = r * cvec + cg;
+        float4 g = dy[i];
+        if (relu) {
+          const float4 yy = y[i];
+          g.x = yy.x > 0.f ? g.x : 0.f;
+          g.y = yy.y > 0.f ? g.y : 0.f;
+          g.z = yy.z > 0.f ? g.z : 0.f;
+          g.w = yy.w > 0.f ? g.w : 0.f;
+        }
+        sb.x += g.x; sb.y += g.y; sb.z += g.z; sb.w += g.w;
+        if (z) {
+          const float4 zz = z[i];
+          sg.x += g.x * (zz.x - mu.x) * rs.x;
+          sg.y += g.y * (zz.y - mu.y) * rs.y;
+          sg.z += g.z * (zz.z - mu.z) * rs.z;
+          sg.w += g.w * (zz.w - mu.w) * rs.w;
+        }
+        if (dres) dres[i] = g;
+        if (dz)
+          dz[i] = make_float4(tf32_rna(g.x * sc.x), tf32_rna(g.y * sc.y), tf32_rna(g.z * sc.z),
+                              tf32_rna(g.w * sc.w));
+      }
     }
-    if (dbeta) atomicAdd(dbeta + c, sb);
-    if (dgamma) atomicAdd(dgamma + c, sg);
+    if (dbeta || dgamma) {
+      sm_b[threadIdx.x] = sb;
+      sm_g[threadIdx.x] = sg;
+      __syncthreads();
+      if (tr == 0) {
+        for (int k = 1; k < rpb; ++k) {
+          const float4 b2 = sm_b[k * tpr + tc], g2 = sm_g[k * tpr + tc];
+          sb.x += b2.x; sb.y += b2.y; sb.z += b2.z; sb.w += b2.w;
+          sg.x += g2.x; sg.y += g2.y; sg.z += g2.z; sg.w += g2.w;
+        }
+        if (dbeta) {
+          atomicAdd(dbeta + 4 * cg + 0, sb.x);
+          atomicAdd(dbeta + 4 * cg + 1, sb.y);
+          atomicAdd(dbeta + 4 * cg + 2, sb.z);
+          atomicAdd(dbeta + 4 * cg + 3, sb.w);
+        }
+        if (dgamma) {
+          atomicAdd(dgamma + 4 * cg + 0, sg.x);
+          atomicAdd(dgamma + 4 * cg + 1, sg.y);
+          atomicAdd(dgamma + 4 * cg + 2, sg.z);
+          atomicAdd(dgamma + 4 * cg + 3, sg.w);
+        }
+      }
+      __syncthreads();
+    }
   }
 }
 
@@ -368,13 +413,23 @@ int loft_act_bwd(const float* dy, const float* y, const float* z, const float* s
                  float* dbeta, long long P, int C, int relu, cudaStream_t stream) {
   LOFT_CHECK_ARG(dy, "act_bwd: null dy");
   LOFT_CHECK_ARG(!relu || y, "act_bwd: relu needs y");
+  LOFT_CHECK_SHAPE(C % 4 == 0, "act_bwd: C=%d must be a multiple of 4", C);
   if (P == 0) return LOFT_OK;
-  int rows = 64;
-  while ((P + rows - 1) / rows > 148 * 8 && rows < 4096) rows *= 2;
-  const int blocks = (int)((P + rows - 1) / rows);
-  const int threads = C >= 256 ? 256 : (C >= 128 ? 128 : (C >= 64 ? 64 : 32));
-  act_bwd_kernel<<<blocks, threads, 0, stream>>>(dy, y, z, scale, mean, rstd, dz, dres, dgamma,
-                                                 dbeta, P, C, relu, rows);
+  const int cvec = C / 4;
+  const int tpr = cvec < 256 ? cvec : 256;
+  const int rpb = 256 / tpr;
+  long long blocks = (P + rpb * 8 - 1) / (rpb * 8);  // >= 8 rows per thread-row
+  const long long maxb = 148 * 6;
+  if (blocks > maxb) blocks = maxb;
+  if (blocks < 1) blocks = 1;
+  const long long rows = (P + blocks - 1) / blocks;
+  blocks = (P + rows - 1) / rows;
+  act_bwd_kernel<<<(unsigned)blocks, 256, 0, stream>>>(
+      reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(y),
+      reinterpret_cast<const float4*>(z), reinterpret_cast<const float4*>(scale),
+      reinterpret_cast<const float4*>(mean), reinterpret_cast<const float4*>(rstd),
+      reinterpret_cast<float4*>(dz), reinterpret_cast<float4*>(dres), dgamma, dbeta, P, cvec, relu,
+      rows);
   LOFT_CUDA_LAUNCH_CHECK("act_bwd");
   return LOFT_OK;
 }

@@ -498,14 +498,53 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cu
 
 int round16(int x) { return (x + 15) & ~15; }
 
-// Pixel tile for the N side of FPROP_CONV / DGRAD_CONV: tn*th*tw <= 256.
-void pick_pixel_tile(int N, int H, int W, int& tn, int& th, int& tw) {
+// Relative cost of covering `tiles` tiles of n columns on the machine: full waves x (n + fixed
+// per-tile overhead).  Used to pick the UMMA N (pixels per tile) for small problems so that the
+// grid fills the 148 SMs instead of leaving most of them idle.
+long long wave_cost(long long tiles, int n) {
+  const long long waves = (tiles + loft_num_sms() - 1) / loft_num_sms();
+  return waves * (n + 48);
+}
+
+int pick_n_2d(long long P, int nct) {
+  if (P < 256) return round16((int)P);
+  int best = 256;
+  long long bc = wave_cost((long long)nct * loft_cdiv(P, 256), 256);
+  for (int n : {128, 64}) {
+    const long long c = wave_cost((long long)nct * loft_cdiv(P, n), n);
+    if (c < bc) {
+      bc = c;
+      best = n;
+    }
+  }
+  return best;
+}
+
+// Pixel tile for the N side of FPROP_CONV / DGRAD_CONV: tn*th*tw <= target.
+void pixel_tile_for(int target, int N, int H, int W, int& tn, int& th, int& tw) {
   tw = W < 16 ? W : 16;
-  th = H < (256 / tw) ? H : (256 / tw);
-  if (th > 16 && tw == 16) th = 16;
-  tn = 256 / (tw * th);
+  th = H < (target / tw) ? H : (target / tw);
+  if (th < 1) th = 1;
+  tn = target / (tw * th);
   if (tn > N) tn = N;
   if (tn < 1) tn = 1;
+}
+
+void pick_pixel_tile(int N, int H, int W, int nct, int& tn, int& th, int& tw) {
+  long long bc = -1;
+  for (int target : {256, 128, 64}) {
+    int a, b, c;
+    pixel_tile_for(target, N, H, W, a, b, c);
+    const long long tiles =
+        (long long)nct * loft_cdiv(W, c) * loft_cdiv(H, b) * loft_cdiv(N, a);
+    const long long cost = wave_cost(tiles, round16(a * b * c));
+    if (bc < 0 || cost < bc) {
+      bc = cost;
+      tn = a;
+      th = b;
+      tw = c;
+    }
+  }
 }
 
 // Pixel patch of exactly kKB (=32) positions for the K side of WGRAD_CONV (OOB -> zero fill).
@@ -556,8 +595,8 @@ int loft_gemm_fprop(const float* x, const float* w, float* y, long long P, int K
   if (P == 0) return LOFT_OK;
   GemmParams p{};
   p.mode = FPROP_2D;
-  p.n_mma = P >= 256 ? 256 : round16((int)P);
   p.nct = loft_cdiv(Cout, kBlockC);
+  p.n_mma = pick_n_2d(P, p.nct);
   p.npt = loft_cdiv(P, p.n_mma);
   p.num_tiles = p.nct * p.npt;
   p.num_kb = loft_cdiv(K, kKB);
@@ -599,8 +638,8 @@ int loft_gemm_dgrad(const float* dy, const float* w, float* dx, long long P, int
   if (P == 0) return LOFT_OK;
   GemmParams p{};
   p.mode = DGRAD_2D;
-  p.n_mma = P >= 256 ? 256 : round16((int)P);
   p.nct = loft_cdiv(Cin, kBlockC);
+  p.n_mma = pick_n_2d(P, p.nct);
   p.npt = loft_cdiv(P, p.n_mma);
   p.num_tiles = p.nct * p.npt;
   p.num_kb = loft_cdiv(Cout, kKB);
@@ -687,11 +726,11 @@ int loft_conv3x3_fprop(const float* x, const float* w, float* y, int N, int H, i
   if (N == 0) return LOFT_OK;
   GemmParams p{};
   p.mode = FPROP_CONV;
-  pick_pixel_tile(N, H, W, p.tn, p.th, p.tw);
+  p.nct = loft_cdiv(Cout, kBlockC);
+  pick_pixel_tile(N, H, W, p.nct, p.tn, p.th, p.tw);
   p.n_mma = round16(p.tn * p.th * p.tw);
   p.tiles_w = loft_cdiv(W, p.tw);
   p.tiles_h = loft_cdiv(H, p.th);
-  p.nct = loft_cdiv(Cout, kBlockC);
   p.npt = p.tiles_w * p.tiles_h * loft_cdiv(N, p.tn);
   p.num_tiles = p.nct * p.npt;
   p.cchunks = Cin / 32;
@@ -731,11 +770,11 @@ int loft_conv3x3_dgrad(const float* dy, const float* w, float* dx, int N, int H,
   if (N == 0) return LOFT_OK;
   GemmParams p{};
   p.mode = DGRAD_CONV;
-  pick_pixel_tile(N, H, W, p.tn, p.th, p.tw);
+  p.nct = loft_cdiv(Cin, kBlockC);
+  pick_pixel_tile(N, H, W, p.nct, p.tn, p.th, p.tw);
   p.n_mma = round16(p.tn * p.th * p.tw);
   p.tiles_w = loft_cdiv(W, p.tw);
   p.tiles_h = loft_cdiv(H, p.th);
-  p.nct = loft_cdiv(Cin, kBlockC);
   p.npt = p.tiles_w * p.tiles_h * loft_cdiv(N, p.tn);
   p.num_tiles = p.nct * p.npt;
   p.cchunks = loft_cdiv(Cout, 32);
@@ -785,7 +824,8 @@ int loft_conv3x3_wgrad(const float* dy, const float* x, float* dw, int N, int H,
   p.ntaps = 9;
   p.num_kb = p.tiles_w * p.tiles_h * loft_cdiv(N, p.tn);
   int base = p.nct * p.npt * 9;
-  int splits = loft_cdiv(loft_num_sms(), base);
+  int splits = loft_num_sms() / base;  // floor: one full wave, never a ragged second one
+  if (splits < 1) splits = 1;
   if (splits > p.num_kb) splits = p.num_kb;
   p.kb_per_split = loft_cdiv(p.num_kb, splits);
   splits = loft_cdiv(p.num_kb, p.kb_per_split);
