@@ -151,7 +151,9 @@ def roofline_probe(model, device, pk):
     achieved = flops / (ms * 1e-3) / 1e12
     return dict(bound='tensor', kernel='loft_gemm_tf32_kernel (FPROP_CONV 131072x2304x256)',
                 achieved=round(achieved, 1), peak=pk['tensor'], unit='TFLOP/s',
-                frac=round(achieved / pk['tensor'], 4), traffic=None,
+                frac=round(achieved / pk['tensor'], 4),
+                traffic=228.55e6,   # dram read+write bytes/launch, profiles/r01_ncu_gemm_fprop_p2.txt
+                algorithmic_bytes=2 * N * H * W * C * 4 + 9 * C * C * 4,
                 peak_source=f"{pk['source']} bf16 dense burst; TF32 operands run at half that rate",
                 frac_of_tf32_half_peak=round(achieved / (pk['tensor'] / 2), 4),
                 ms_per_launch=round(ms, 4))

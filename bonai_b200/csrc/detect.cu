@@ -258,6 +258,117 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, int n, int nwords, 
   if (t == 0) num_keep[img] = s_count;
 }
 
+// ---------------------------------------------------------------- soft-NMS (linear), test time
+// mmcv.ops.soft_nms(method='linear') [mmcv-full 1.0.5, CPU-only there]: repeatedly select the
+// highest-scoring live box, decay every other live box j by (1 - iou) if iou > thr, drop boxes whose
+// score falls below min_score.  One block; scores live in shared memory.
+constexpr int kSoftThreads = 1024;
+constexpr int kSoftMax = 8192;
+__global__ void __launch_bounds__(kSoftThreads)
+soft_nms_kernel(const float* __restrict__ boxes, const float* __restrict__ scores_in,
+                const long long* __restrict__ idxs, int n, float thr, float min_score, int max_keep,
+                float* __restrict__ dets, long long* __restrict__ keep, int* __restrict__ num_keep) {
+  __shared__ float sc[kSoftMax];
+  __shared__ float red_v[kSoftThreads / 32];
+  __shared__ int red_i[kSoftThreads / 32];
+  __shared__ float s_max;
+  __shared__ int s_arg;
+  const int t = threadIdx.x;
+  // class-aware offset like batched_nms: boxes + idx * (max_coord + 1)
+  float off1 = 0.f;
+  if (idxs != nullptr) {
+    float m = -INFINITY;
+    for (int i = t; i < n * 4; i += kSoftThreads) m = fmaxf(m, boxes[i]);
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((t & 31) == 0) red_v[t >> 5] = m;
+    __syncthreads();
+    if (t == 0) {
+      float mm = -INFINITY;
+      for (int w = 0; w < kSoftThreads / 32; ++w) mm = fmaxf(mm, red_v[w]);
+      s_max = mm;
+    }
+    __syncthreads();
+    off1 = __fadd_rn(s_max, 1.f);
+    __syncthreads();
+  }
+  for (int i = t; i < n; i += kSoftThreads) sc[i] = scores_in[i];   // dead boxes get -inf
+  __syncthreads();
+  int count = 0;
+  while (count < max_keep) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = t; i < n; i += kSoftThreads) {
+      const float v = sc[i];
+      if (v > bv || (v == bv && i < bi && v > -INFINITY)) {
+        bv = v;
+        bi = i;
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) {
+        bv = ov;
+        bi = oi;
+      }
+    }
+    if ((t & 31) == 0) {
+      red_v[t >> 5] = bv;
+      red_i[t >> 5] = bi;
+    }
+    __syncthreads();
+    if (t == 0) {
+      float v = red_v[0];
+      int a = red_i[0];
+      for (int w = 1; w < kSoftThreads / 32; ++w)
+        if (red_v[w] > v || (red_v[w] == v && red_i[w] < a)) {
+          v = red_v[w];
+          a = red_i[w];
+        }
+      s_max = v;
+      s_arg = a;
+    }
+    __syncthreads();
+    const float mv = s_max;
+    const int ma = s_arg;
+    if (!(mv > -INFINITY)) break;  // nothing alive
+    const float o_m = idxs ? __fmul_rn((float)idxs[ma], off1) : 0.f;
+    const float mx1 = __fadd_rn(boxes[ma * 4 + 0], o_m), my1 = __fadd_rn(boxes[ma * 4 + 1], o_m);
+    const float mx2 = __fadd_rn(boxes[ma * 4 + 2], o_m), my2 = __fadd_rn(boxes[ma * 4 + 3], o_m);
+    const float marea = __fmul_rn(__fsub_rn(mx2, mx1), __fsub_rn(my2, my1));
+    if (t == 0) {
+      dets[count * 5 + 0] = boxes[ma * 4 + 0];
+      dets[count * 5 + 1] = boxes[ma * 4 + 1];
+      dets[count * 5 + 2] = boxes[ma * 4 + 2];
+      dets[count * 5 + 3] = boxes[ma * 4 + 3];
+      dets[count * 5 + 4] = mv;
+      keep[count] = ma;
+    }
+    for (int i = t; i < n; i += kSoftThreads) {
+      if (i == ma) {
+        sc[i] = -INFINITY;
+        continue;
+      }
+      const float v = sc[i];
+      if (!(v > -INFINITY)) continue;
+      const float o_i = idxs ? __fmul_rn((float)idxs[i], off1) : 0.f;
+      const float x1 = __fadd_rn(boxes[i * 4 + 0], o_i), y1 = __fadd_rn(boxes[i * 4 + 1], o_i);
+      const float x2 = __fadd_rn(boxes[i * 4 + 2], o_i), y2 = __fadd_rn(boxes[i * 4 + 3], o_i);
+      const float w = fmaxf(__fsub_rn(fminf(mx2, x2), fmaxf(mx1, x1)), 0.f);
+      const float h = fmaxf(__fsub_rn(fminf(my2, y2), fmaxf(my1, y1)), 0.f);
+      const float inter = __fmul_rn(w, h);
+      const float area = __fmul_rn(__fsub_rn(x2, x1), __fsub_rn(y2, y1));
+      const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(marea, area), inter));
+      const float wgt = ovr > thr ? __fsub_rn(1.f, ovr) : 1.f;
+      const float nv = __fmul_rn(v, wgt);
+      sc[i] = nv < min_score ? -INFINITY : nv;
+    }
+    ++count;
+    __syncthreads();
+  }
+  if (t == 0) *num_keep = count;
+}
+
 // ---------------------------------------------------------------- target encoders
 // bbox2delta with means 0: deltas[i] = ((gx-px)/pw, (gy-py)/ph, log(gw/pw), log(gh/ph)) / stds
 __global__ void bbox_encode_kernel(const float* __restrict__ props, const float* __restrict__ gts,
@@ -385,6 +496,23 @@ int loft_nms_sorted(const float* boxes, const long long* idxs, int B, int n, flo
       reinterpret_cast<const unsigned long long*>(workspace), n, nwords, max_keep, keep, num_keep,
       (long long)(per_img / 8), (long long)n);
   LOFT_CUDA_LAUNCH_CHECK("nms_scan");
+  return LOFT_OK;
+}
+
+// Linear soft-NMS of one image.  dets [n,5], keep [n] (selection order), num_keep [1].
+int loft_soft_nms_linear(const float* boxes, const float* scores, const long long* idxs, int n,
+                         float iou_thr, float min_score, int max_keep, float* dets, long long* keep,
+                         int* num_keep, cudaStream_t stream) {
+  LOFT_CHECK_ARG(boxes && scores && dets && keep && num_keep, "soft_nms_linear: null pointer");
+  LOFT_CHECK_SHAPE(n <= kSoftMax, "soft_nms_linear: at most %d boxes, got %d", kSoftMax, n);
+  if (max_keep <= 0 || max_keep > n) max_keep = n;
+  if (n == 0) {
+    cudaMemsetAsync(num_keep, 0, sizeof(int), stream);
+    return LOFT_OK;
+  }
+  soft_nms_kernel<<<1, kSoftThreads, 0, stream>>>(boxes, scores, idxs, n, iou_thr, min_score,
+                                                   max_keep, dets, keep, num_keep);
+  LOFT_CUDA_LAUNCH_CHECK("soft_nms_linear");
   return LOFT_OK;
 }
 

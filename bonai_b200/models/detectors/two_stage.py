@@ -83,5 +83,17 @@ class TwoStageDetector(BaseDetector):
         losses.update(roi_losses)
         return losses
 
+    @torch.no_grad()
     def simple_test(self, img, img_metas, proposals=None, rescale=False):
-        raise NotImplementedError('inference post-processing is a SURVEY section 8(f) "next" row')
+        """TwoStageDetector.simple_test (two_stage.py:187-199)."""
+        assert self.with_bbox, 'Bbox head must be implemented.'
+        store = get_store(self, img.device if img.is_cuda else None)
+        store.refresh_weights()
+        if not img.is_cuda:
+            img = img.to(store.device, non_blocking=True)
+        x = self.extract_feat(img)
+        if proposals is None:
+            proposal_list = self.rpn_head.simple_test_rpn(x, img_metas)
+        else:
+            proposal_list = proposals
+        return self.roi_head.simple_test(x, proposal_list, img_metas, rescale=rescale)

@@ -75,3 +75,33 @@ class LoftRoIHead(StandardRoIHead):
             offset_feats = bbox_feats[pos_inds]
         offset_pred = self.offset_head(offset_feats)
         return dict(offset_pred=offset_pred, offset_feats=offset_feats)
+
+    # ------------------------------------------------------------------ inference
+    def simple_test_offset(self, x, img_metas, det_bboxes, det_labels, rescale=False):
+        """OffsetTestMixin.simple_test_offset (test_mixins.py:211-241)."""
+        scale_factor = img_metas[0]['scale_factor']
+        if det_bboxes.shape[0] == 0:
+            return [[] for _ in range(2)]
+        if rescale and not isinstance(scale_factor, float):
+            scale_factor = torch.from_numpy(scale_factor).to(det_bboxes.device)
+        _bboxes = det_bboxes[:, :4] * scale_factor if rescale else det_bboxes
+        offset_rois = bbox2roi([_bboxes])
+        offset_feats = self.offset_roi_extractor(x[:self.offset_roi_extractor.num_inputs],
+                                                 offset_rois)
+        offset_pred = self.offset_head(offset_feats)
+        return self.offset_head.get_offsets(offset_pred.contiguous(), _bboxes, scale_factor, rescale)
+
+    def simple_test(self, x, proposal_list, img_metas, proposals=None, rescale=False):
+        """LoftRoIHead.simple_test (loft_roi_head.py:196-227): (bbox, segm, offset) results."""
+        from ...core import bbox2result
+        assert self.with_bbox, 'Bbox head must be implemented.'
+        det_bboxes, det_labels = self.simple_test_bboxes(x, img_metas, proposal_list, self.test_cfg,
+                                                         rescale=rescale)
+        bbox_results = bbox2result(det_bboxes, det_labels, self.bbox_head.num_classes)
+        segm_results = None
+        if self.with_mask:
+            segm_results = self.simple_test_mask(x, img_metas, det_bboxes, det_labels,
+                                                 rescale=rescale)
+        offset_results = self.simple_test_offset(x, img_metas, det_bboxes, det_labels,
+                                                 rescale=rescale)
+        return bbox_results, segm_results, offset_results

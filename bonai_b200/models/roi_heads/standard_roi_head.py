@@ -155,5 +155,39 @@ class StandardRoIHead(BaseRoIHead):
         mask_pred = self.mask_head(mask_feats)
         return dict(mask_pred=mask_pred, mask_feats=mask_feats)
 
+    # ------------------------------------------------------------------ inference (test_mixins.py)
+    def simple_test_bboxes(self, x, img_metas, proposals, rcnn_test_cfg, rescale=False):
+        """BBoxTestMixin.simple_test_bboxes (test_mixins.py:53-72)."""
+        rois = bbox2roi(proposals)
+        bbox_results = self._bbox_forward(x, rois)
+        img_shape = img_metas[0]['img_shape']
+        scale_factor = img_metas[0]['scale_factor']
+        return self.bbox_head.get_bboxes(rois, bbox_results['cls_score'].contiguous(),
+                                         bbox_results['bbox_pred'].contiguous(), img_shape,
+                                         scale_factor, rescale=rescale, cfg=rcnn_test_cfg)
+
+    def simple_test_mask(self, x, img_metas, det_bboxes, det_labels, rescale=False):
+        """MaskTestMixin.simple_test_mask (test_mixins.py:152-177)."""
+        ori_shape = img_metas[0]['ori_shape']
+        scale_factor = img_metas[0]['scale_factor']
+        if det_bboxes.shape[0] == 0:
+            return [[] for _ in range(self.mask_head.num_classes)]
+        if rescale and not isinstance(scale_factor, float):
+            scale_factor = torch.from_numpy(scale_factor).to(det_bboxes.device)
+        _bboxes = det_bboxes[:, :4] * scale_factor if rescale else det_bboxes
+        mask_rois = bbox2roi([_bboxes])
+        mask_results = self._mask_forward(x, mask_rois)
+        return self.mask_head.get_seg_masks(mask_results['mask_pred'].contiguous(), _bboxes,
+                                            det_labels, self.test_cfg, ori_shape, scale_factor,
+                                            rescale)
+
     def simple_test(self, x, proposal_list, img_metas, proposals=None, rescale=False):
-        raise NotImplementedError('inference post-processing is a SURVEY section 8(f) "next" row')
+        """StandardRoIHead.simple_test (standard_roi_head.py:218-237)."""
+        from ...core import bbox2result
+        det_bboxes, det_labels = self.simple_test_bboxes(x, img_metas, proposal_list, self.test_cfg,
+                                                         rescale=rescale)
+        bbox_results = bbox2result(det_bboxes, det_labels, self.bbox_head.num_classes)
+        if not self.with_mask:
+            return bbox_results
+        return bbox_results, self.simple_test_mask(x, img_metas, det_bboxes, det_labels,
+                                                   rescale=rescale)

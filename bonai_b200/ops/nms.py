@@ -38,14 +38,38 @@ def nms(boxes, scores, iou_threshold, offset=0):
     return torch.cat([boxes[inds], scores[inds, None]], dim=1), inds
 
 
+def soft_nms(boxes, scores, iou_threshold=0.3, sigma=0.5, min_score=1e-3, method='linear',
+             offset=0, idxs=None, max_keep=-1):
+    """mmcv.ops.soft_nms (linear): returns (dets[k,5] with decayed scores, inds[k]) in selection
+    order.  `idxs` (optional) applies batched_nms' per-class coordinate offset inside the kernel."""
+    if method != 'linear' or offset != 0:
+        raise NotImplementedError('LOFT test_cfg uses linear soft-NMS with offset 0')
+    n = boxes.shape[0]
+    dev = boxes.device
+    dets = torch.empty((n, 5), device=dev, dtype=torch.float32)
+    keep = torch.empty((n,), device=dev, dtype=torch.long)
+    num = torch.zeros((1,), device=dev, dtype=torch.int32)
+    if n == 0:
+        return dets, keep
+    L.call('soft_nms_linear', L.ptr(boxes.contiguous().float()), L.ptr(scores.contiguous().float()),
+           L.ptr(idxs.contiguous().long()) if idxs is not None else None, i32(n),
+           L.f32(iou_threshold), L.f32(min_score), i32(max_keep), L.ptr(dets), L.ptr(keep),
+           L.ptr(num), L.stream())
+    k = int(num[0])
+    return dets[:k], keep[:k]
+
+
 def batched_nms(boxes, scores, idxs, nms_cfg, class_agnostic=False):
     """mmcv.ops.batched_nms (v1.0.5): boxes of different `idxs` never suppress each other (fp32
     coordinate-offset trick, applied inside the kernel)."""
     cfg = dict(nms_cfg)
     class_agnostic = cfg.pop('class_agnostic', class_agnostic)
     typ = cfg.pop('type', 'nms')
+    if typ == 'soft_nms':
+        dets, keep = soft_nms(boxes, scores, idxs=None if class_agnostic else idxs, **cfg)
+        return torch.cat([boxes[keep], dets[:, 4:5]], dim=-1), keep
     if typ != 'nms':
-        raise NotImplementedError(f'batched_nms type {typ!r}: only hard NMS is on the CUDA path')
+        raise NotImplementedError(f'batched_nms type {typ!r}')
     thr = float(cfg.pop('iou_threshold'))
     if boxes.shape[0] == 0:
         return boxes.new_zeros((0, 5)), torch.zeros(0, dtype=torch.long, device=boxes.device)

@@ -130,6 +130,11 @@ size_t loft_nms_workspace(int n);
 int loft_nms_sorted(const float* boxes, const long long* idxs, int B, int n, float iou_thr,
                     int max_keep, long long* keep, int* num_keep, void* workspace, size_t ws_bytes,
                     cudaStream_t stream);
+/* test-time linear soft-NMS (mmcv.ops.soft_nms via core/post_processing/bbox_nms.py:63 with
+ * bonai_loft_foa_r50_fpn_basic.py:138); CPU-only in mmcv 1.0.5, one-block kernel here */
+int loft_soft_nms_linear(const float* boxes, const float* scores, const long long* idxs, int n,
+                         float iou_thr, float min_score, int max_keep, float* dets, long long* keep,
+                         int* num_keep, cudaStream_t stream);
 int loft_bbox_encode(const float* props, const float* gts, long long n, float s0, float s1, float s2,
                      float s3, float* out, cudaStream_t stream);
 int loft_offset_target(const float* props, const float* gt_offsets, const long long* gt_inds,

@@ -807,3 +807,82 @@ def init_params(seed=0):
     p[oh + '.fc_offset.weight'] = torch.randn((2, 1024), generator=g) * 0.01
     p[oh + '.fc_offset.bias'] = torch.zeros(2)
     return p
+
+
+# ----------------------------------------------------------------------------- inference
+TEST_CFG = dict(score_thr=0.05, nms_iou=0.5, max_per_img=2000, mask_thr_binary=0.5)   # :128-140
+
+
+def multiclass_nms_soft(bboxes, scores, score_thr, iou_thr, max_num):
+    """multiclass_nms with nms=dict(type='soft_nms'), 1 foreground class
+    (core/post_processing/bbox_nms.py:5-69)."""
+    sc = scores[:, :-1]
+    valid = sc > score_thr
+    b = bboxes.view(scores.size(0), -1, 4)[valid]
+    s = sc[valid]
+    labels = valid.nonzero(as_tuple=False)[:, 1]
+    if b.numel() == 0:
+        return bboxes.new_zeros((0, 5)), labels.new_zeros((0,))
+    max_coordinate = b.max()
+    offs = labels.to(b) * (max_coordinate + 1)
+    dets, keep = ops_cpu.soft_nms_linear(b + offs[:, None], s, iou_thr, 1e-3)
+    dets = torch.cat([b[keep], dets[:, -1:]], -1)
+    if max_num > 0:
+        dets, keep = dets[:max_num], keep[:max_num]
+    return dets, labels[keep]
+
+
+def paste_masks(mask_pred, det_bboxes, img_h, img_w, thr=0.5):
+    """FCNMaskHead.get_seg_masks + _do_paste_mask on CPU (fcn_mask_head.py:151-308), rescale=False,
+    scale_factor=1: returns a bool tensor [k, H, W]."""
+    n = mask_pred.shape[0]
+    out = torch.zeros(n, img_h, img_w, dtype=torch.bool)
+    m = mask_pred.sigmoid()
+    for i in range(n):                                   # CPU path: one chunk per detection
+        boxes = det_bboxes[i:i + 1, :4]
+        x0_int, y0_int = torch.clamp(boxes.min(dim=0).values.floor()[:2] - 1, min=0).to(torch.int32)
+        x1_int = torch.clamp(boxes[:, 2].max().ceil() + 1, max=img_w).to(torch.int32)
+        y1_int = torch.clamp(boxes[:, 3].max().ceil() + 1, max=img_h).to(torch.int32)
+        x0, y0, x1, y1 = torch.split(boxes, 1, dim=1)
+        img_y = torch.arange(y0_int, y1_int, dtype=torch.float32) + 0.5
+        img_x = torch.arange(x0_int, x1_int, dtype=torch.float32) + 0.5
+        img_y = (img_y - y0) / (y1 - y0) * 2 - 1
+        img_x = (img_x - x0) / (x1 - x0) * 2 - 1
+        img_x[torch.isinf(img_x)] = 0
+        img_y[torch.isinf(img_y)] = 0
+        gx = img_x[:, None, :].expand(1, img_y.size(1), img_x.size(1))
+        gy = img_y[:, :, None].expand(1, img_y.size(1), img_x.size(1))
+        grid = torch.stack([gx, gy], dim=3)
+        pm = F.grid_sample(m[i:i + 1].float(), grid, align_corners=False)
+        out[i, y0_int:y1_int, x0_int:x1_int] = pm[0, 0] >= thr
+    return out
+
+
+@torch.no_grad()
+def simple_test(p, img, cfg=CFG, tcfg=TEST_CFG, proposals=None, aux=None):
+    """TwoStageDetector.simple_test -> LoftRoIHead.simple_test (two_stage.py:187-199,
+    loft_roi_head.py:196-227, test_mixins.py:53-72,152-177,211-241).  One image, rescale=False.
+    Returns (dets[k,5], masks bool[k,H,W], offsets[k,2])."""
+    assert img.size(0) == 1
+    img_shape = tuple(img.shape[-2:])
+    feats = fpn(resnet50(img, p), p)
+    if proposals is None:
+        cls_scores, bbox_preds = rpn_forward(feats, p)
+        proposals = rpn_get_bboxes(cls_scores, bbox_preds, [img_shape], cfg)
+    rois = bbox2roi([q[:, :4] for q in proposals])
+    cls_score, bbox_pred = bbox_head_forward(roi_extract(feats[:4], rois, 7, cfg), p)
+    scores = F.softmax(cls_score, dim=1)
+    bboxes = delta2bbox(rois[:, 1:], bbox_pred, cfg['rcnn_stds'], max_shape=img_shape)
+    dets, labels = multiclass_nms_soft(bboxes, scores, tcfg['score_thr'], tcfg['nms_iou'],
+                                       tcfg['max_per_img'])
+    if dets.shape[0] == 0:
+        return dets, torch.zeros((0,) + img_shape, dtype=torch.bool), dets.new_zeros((0, 2))
+    det_rois = bbox2roi([dets[:, :4]])
+    mask_pred = mask_head_forward(roi_extract(feats[:4], det_rois, 14, cfg), p)
+    masks = paste_masks(mask_pred[:, 0:1], dets, img_shape[0], img_shape[1], tcfg['mask_thr_binary'])
+    off_pred = offset_head_forward(roi_extract(feats[:4], det_rois, 7, cfg), p, cfg)
+    offsets = delta2offset(dets, offset_fusion_max(off_pred), cfg['offset_stds'],
+                           max_shape=[1024, 1024])       # get_offsets default img_shape (App. C.7)
+    if aux is not None:
+        aux.update(proposals=proposals, mask_pred=mask_pred, offset_pred=off_pred)
+    return dets, masks, offsets

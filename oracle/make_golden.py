@@ -170,7 +170,32 @@ def gold_units():
     print('units:', len(out), 'arrays')
 
 
+def gold_inference():
+    """Reference simple_test (bbox, segm, offset results) on the portable init, one 256^2 tile."""
+    p = O.randomize_bn(O.init_params(0), 0)
+    model, _ = build_reference_model(p)
+    model.eval()
+    img, _, _, _, _ = O.make_inputs(0, 1, 256, 10)
+    metas = [dict(img_shape=(256, 256, 3), ori_shape=(256, 256, 3), pad_shape=(256, 256, 3),
+                  scale_factor=1.0, flip=False, filename='synthetic')]
+    with torch.no_grad():
+        bbox_r, segm_r, off_r = model.simple_test(img, metas, rescale=False)
+    dets = bbox_r[0]
+    areas = np.array([int(m.sum()) for m in segm_r[0]], dtype=np.int64)
+    np.savez_compressed(os.path.join(GOLD, 'loft_infer_256.npz'), dets=dets,
+                        offsets=np.asarray(off_r, dtype=np.float32), mask_areas=areas,
+                        meta=np.array(['init_params(0)+randomize_bn(0); make_inputs(0,1,256,10) img; '
+                                       'reference simple_test(rescale=False); torch ' +
+                                       torch.__version__]))
+    print('loft_infer_256:', dets.shape, np.asarray(off_r).shape, areas[:5])
+
+
 if __name__ == '__main__':
     os.makedirs(GOLD, exist_ok=True)
-    gold_units()
-    gold_loft_step()
+    which = sys.argv[1:] or ['units', 'step', 'infer']
+    if 'units' in which:
+        gold_units()
+    if 'step' in which:
+        gold_loft_step()
+    if 'infer' in which:
+        gold_inference()

@@ -19,7 +19,7 @@ from bonai_b200.models.dense_heads import RPNHead  # noqa: E402
 CFG = os.path.join(ROOT, 'configs', 'loft', 'loft_foa_r50_fpn_2x_b200.py')
 
 
-def run(size=256, n_img=1, num_gt=10, seed=0, force_proposals=True, verbose=True):
+def run(size=256, n_img=1, num_gt=10, seed=0, force_proposals=True, verbose=True, diag=False):
     p = O.randomize_bn(O.init_params(seed), seed)
     img, gb, gl, gm, go = O.make_inputs(seed, n_img, size, num_gt)
     tk = set(O.trainable_keys(p))
@@ -41,6 +41,18 @@ def run(size=256, n_img=1, num_gt=10, seed=0, force_proposals=True, verbose=True
     RPNHead.forced_proposals = [q.clone() for q in aux['proposals']] if force_proposals else None
     metas = [dict(img_shape=(size, size, 3), pad_shape=(size, size, 3), ori_shape=(size, size, 3),
                   scale_factor=1.0, flip=False) for _ in range(n_img)]
+    caps = {}
+    if diag:
+        def cap(name):
+            def hook(mod, inp, out):
+                caps[name] = out
+            return hook
+        model.neck.register_forward_hook(cap('feats'))
+        model.roi_head.bbox_roi_extractor.register_forward_hook(cap('bbox_feats'))
+        model.roi_head.mask_roi_extractor.register_forward_hook(cap('mask_feats'))
+        model.roi_head.mask_head.register_forward_hook(cap('mask_pred'))
+        model.roi_head.offset_head.register_forward_hook(cap('offset_pred'))
+        model.roi_head.bbox_head.register_forward_hook(cap('bbox_out'))
     losses = model.forward_train(img.to(dev), metas, gb, gl,
                                  gt_masks=[BitmapMasks(m, size, size) for m in gm], gt_offsets=go)
     loss, logs = model._parse_losses(losses)
@@ -49,6 +61,30 @@ def run(size=256, n_img=1, num_gt=10, seed=0, force_proposals=True, verbose=True
     RandomSampler.forced_choices = None
     RPNHead.forced_proposals = None
     rep = {'losses': {}, 'grads': {}}
+    if diag:
+        import torch.nn.functional as F
+        def st(name, a, b):
+            a, b = a.detach().cpu().double(), b.detach().double()
+            d = a - b
+            print(f'{name:14s} rel_l2={float(d.norm() / b.norm()):.2e} '
+                  f'signed_mean/abs_mean={float(d.mean() / b.abs().mean()):+.2e}')
+        for i, (a, b) in enumerate(zip(caps['feats'], aux['feats'])):
+            st(f'fpn{i}', a, b)
+        st('bbox_feats', caps['bbox_feats'], aux['bbox_feats'])
+        mo = O.roi_extract(aux['feats'][:4], aux['pos_rois'], 14)
+        st('mask_feats', caps['mask_feats'], mo)
+        st('mask_pred', caps['mask_pred'], aux['mask_pred'])
+        st('offset_pred', caps['offset_pred'], aux['offset_pred'])
+        st('cls_score', caps['bbox_out'][0], aux['cls_score'])
+        mt = aux['mask_targets']
+        lg = F.binary_cross_entropy_with_logits(caps['mask_pred'].detach().cpu()[:, 0], mt)
+        lo_ = F.binary_cross_entropy_with_logits(aux['mask_pred'].detach()[:, 0], mt)
+        print('mask loss from captured preds', float(lg), float(lo_), float((lg - lo_) / lo_))
+        sr = model.roi_head._last_sampling_results
+        from bonai_b200.core import mask_target as MT
+        print('mask targets equal:', bool(torch.equal(
+            model.roi_head.mask_head.get_targets(sr, [BitmapMasks(m, size, size) for m in gm],
+                                                 model.roi_head.train_cfg).cpu(), mt)))
     worst = 0.0
     for k, v in logs_o.items():
         a, b = float(logs[k]), float(v)
@@ -81,5 +117,5 @@ if __name__ == '__main__':
     size = int(sys.argv[1]) if len(sys.argv) > 1 else 256
     n_img = int(sys.argv[2]) if len(sys.argv) > 2 else 1
     num_gt = int(sys.argv[3]) if len(sys.argv) > 3 else 10
-    rep = run(size, n_img, num_gt)
+    rep = run(size, n_img, num_gt, diag=len(sys.argv) > 4)
     print(json.dumps(rep, indent=1))
