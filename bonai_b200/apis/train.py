@@ -133,6 +133,42 @@ class Trainer:
                        warmup_iters=c.get('warmup_iters', 0),
                        warmup_ratio=c.get('warmup_ratio', 0.1))
 
+    def stage(self, host_batch):
+        """Copy a (pinned) host batch to the device on a dedicated copy stream, like a prefetching
+        data loader would: the copies overlap the previous step's backward and the returned batch
+        carries the event the compute streams wait on.  Accepts the reference's input dict
+        (img, gt_bboxes, gt_labels, gt_masks, gt_offsets; lists of tensors or BitmapMasks)."""
+        from ..core import BitmapMasks
+        dev = self.store.device
+        if not hasattr(self, '_copy_stream'):
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        out, nbytes = {}, 0
+
+        def mv(t):
+            nonlocal nbytes
+            if isinstance(t, BitmapMasks):
+                src = t._t if t._t is not None else torch.from_numpy(t._np)
+                nbytes += src.numel() * src.element_size()
+                return BitmapMasks(src.to(dev, non_blocking=True), t.height, t.width)
+            if isinstance(t, torch.Tensor):
+                nbytes += t.numel() * t.element_size()
+                return t.to(dev, non_blocking=True)
+            return t
+
+        with torch.cuda.stream(self._copy_stream):
+            for k, v in host_batch.items():
+                out[k] = [mv(t) for t in v] if isinstance(v, (list, tuple)) and k != 'img_metas' \
+                    else mv(v)
+            out['ready_event'] = self._copy_stream.record_event()
+        main = torch.cuda.current_stream(dev)
+        for k, v in out.items():
+            for t in (v if isinstance(v, list) else [v]):
+                t = t._t if isinstance(t, BitmapMasks) else t
+                if isinstance(t, torch.Tensor):
+                    t.record_stream(main)
+        self.staged_bytes = nbytes
+        return out
+
     def train_step(self, data, read_logs=False):
         """forward + backward + gradient all-reduce + clip + SGD.  Returns the device-resident
         packed log vector (and its key order); nothing synchronises the host unless read_logs."""

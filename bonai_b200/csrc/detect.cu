@@ -116,9 +116,13 @@ __global__ void rpn_decode_kernel(const float* __restrict__ head_out, int ld, in
                                   const long long* __restrict__ topk_idx, int k, int fw, int A,
                                   const float* __restrict__ base_anchors, float stride,
                                   float max_ratio, float img_h, float img_w,
-                                  float* __restrict__ boxes_out) {
+                                  float* __restrict__ boxes_out, long long head_stride,
+                                  long long idx_stride, long long out_stride) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= k) return;
+  head_out += (long long)blockIdx.y * head_stride;   // image blockIdx.y
+  topk_idx += (long long)blockIdx.y * idx_stride;
+  boxes_out += (long long)blockIdx.y * out_stride;
   const long long idx = topk_idx[r];
   const int a = (int)(idx % A);
   const long long pos = idx / A;
@@ -447,12 +451,14 @@ int loft_iou_assign(const float* boxes, long long n, const float* gts, int G, fl
 
 int loft_rpn_decode(const float* head_out, int ld, int reg_off, const long long* topk_idx, int k,
                     int fw, int A, const float* base_anchors, float stride, float max_ratio,
-                    float img_h, float img_w, float* boxes_out, cudaStream_t stream) {
+                    float img_h, float img_w, float* boxes_out, int batch, long long head_stride,
+                    long long idx_stride, long long out_stride, cudaStream_t stream) {
   LOFT_CHECK_ARG(head_out && topk_idx && base_anchors && boxes_out, "rpn_decode: null pointer");
-  if (k == 0) return LOFT_OK;
-  rpn_decode_kernel<<<loft_cdiv(k, 128), 128, 0, stream>>>(head_out, ld, reg_off, topk_idx, k, fw, A,
-                                                          base_anchors, stride, max_ratio, img_h,
-                                                          img_w, boxes_out);
+  if (k == 0 || batch == 0) return LOFT_OK;
+  dim3 grid(loft_cdiv(k, 128), batch);
+  rpn_decode_kernel<<<grid, 128, 0, stream>>>(head_out, ld, reg_off, topk_idx, k, fw, A,
+                                              base_anchors, stride, max_ratio, img_h, img_w,
+                                              boxes_out, head_stride, idx_stride, out_stride);
   LOFT_CUDA_LAUNCH_CHECK("rpn_decode");
   return LOFT_OK;
 }

@@ -173,16 +173,14 @@ class RPNHead(nn.Module):
             label_weights[neg_inds] = 1.0
         return labels, label_weights, bbox_targets, bbox_weights, pos_inds, neg_inds
 
-    def loss(self, cls_scores, bbox_preds, gt_bboxes, img_metas, gt_bboxes_ignore=None):
-        """AnchorHead.loss / RPNHead.loss (anchor_head.py:429-497, rpn_head.py:46-77)."""
-        featmap_sizes = [f.size()[-2:] for f in cls_scores]
-        device = cls_scores[0].device
+    def _build_targets(self, featmap_sizes, gt_bboxes, img_metas, device):
+        """get_targets (anchor_head.py:280-380) for all images, regrouped per level and flattened
+        in the (n, h, w, a) order of the fused head output."""
         flat = self._flat_anchors(featmap_sizes, device)
         num_lvl = [int(h) * int(w) * self.num_anchors for h, w in featmap_sizes]
-        n_img = len(img_metas)
         lab, lw, bt, bw = [], [], [], []
         num_pos = num_neg = 0
-        for i in range(n_img):
+        for i in range(len(img_metas)):
             r = self._get_targets_single(flat, gt_bboxes[i], img_metas[i])
             lab.append(r[0])
             lw.append(r[1])
@@ -190,8 +188,54 @@ class RPNHead(nn.Module):
             bw.append(r[3])
             num_pos += max(r[4].numel(), 1)
             num_neg += max(r[5].numel(), 1)
-        num_total_samples = num_pos + num_neg
         lab, lw, bt, bw = (images_to_levels(t, num_lvl) for t in (lab, lw, bt, bw))
+        per_level = [(lab[l].reshape(-1), lw[l].reshape(-1), bt[l].reshape(-1), bw[l].reshape(-1))
+                     for l in range(len(num_lvl))]
+        return per_level, num_pos + num_neg
+
+    def featmap_sizes_for(self, img_hw):
+        """Pyramid sizes implied by the strides (every stage halves with ceil)."""
+        return [(-(-int(img_hw[0]) // s[1]), -(-int(img_hw[1]) // s[0]))
+                for s in self.anchor_generator.strides]
+
+    def prefetch_targets(self, gt_bboxes, img_metas, img_hw, ready_event=None):
+        """RPN targets depend only on the anchors and the GT boxes, not on the network: compute
+        them on a side stream while the backbone runs (their host syncs then wait for the side
+        stream only, so the launch thread keeps running ahead of the GPU)."""
+        dev = gt_bboxes[0].device
+        if not hasattr(self, '_tstream'):
+            self._tstream = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        # The side stream must not read GT boxes before they exist.  If the caller staged them
+        # with an event, wait for that; if they are the very tensors of the previous step they
+        # are long since resident; otherwise fall back to ordering after the main stream (which
+        # serialises behind the previous step's backward).
+        ident = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in gt_bboxes)
+        if ready_event is not None:
+            self._tstream.wait_event(ready_event)
+        elif ident != getattr(self, '_last_gt_ident', None):
+            self._tstream.wait_stream(main)
+        self._last_gt_ident = ident
+        sizes = self.featmap_sizes_for(img_hw)
+        with torch.cuda.stream(self._tstream):
+            per_level, num_total = self._build_targets(sizes, gt_bboxes, img_metas, dev)
+            ev = self._tstream.record_event()
+        for tup in per_level:
+            for t in tup:
+                t.record_stream(main)
+        self._prefetched = (tuple(sizes), per_level, num_total, ev)
+
+    def loss(self, cls_scores, bbox_preds, gt_bboxes, img_metas, gt_bboxes_ignore=None):
+        """AnchorHead.loss / RPNHead.loss (anchor_head.py:429-497, rpn_head.py:46-77)."""
+        featmap_sizes = [tuple(int(v) for v in f.size()[-2:]) for f in cls_scores]
+        device = cls_scores[0].device
+        pre = self.__dict__.pop('_prefetched', None)
+        if pre is not None and pre[0] == tuple(featmap_sizes):
+            _, per_level, num_total_samples, ev = pre
+            torch.cuda.current_stream(device).wait_event(ev)
+        else:
+            per_level, num_total_samples = self._build_targets(featmap_sizes, gt_bboxes, img_metas,
+                                                               device)
         A = self.num_anchors
         loss_cls, loss_bbox = [], []
         for l, cs in enumerate(cls_scores):
@@ -199,12 +243,13 @@ class RPNHead(nn.Module):
             if fused is None:
                 raise L.LoftError('RPNHead.loss expects the fused head output of RPNHead.forward')
             out2d = fused.permute(0, 2, 3, 1).reshape(-1, _FUSED_W)
-            loss_cls.append(K.elem_loss(out2d, lab[l].reshape(-1), lw[l].reshape(-1), K.BCE_LOGITS,
+            lab, lw, bt, bw = per_level[l]
+            loss_cls.append(K.elem_loss(out2d, lab, lw, K.BCE_LOGITS,
                                         self.loss_cls.loss_weight / num_total_samples,
                                         col_off=0, ncols=A))
             mode, beta = (K.L1, 1.0) if type(self.loss_bbox).__name__ == 'L1Loss' else \
                 (K.SMOOTH_L1, self.loss_bbox.beta)
-            loss_bbox.append(K.elem_loss(out2d, bt[l].reshape(-1), bw[l].reshape(-1), mode,
+            loss_bbox.append(K.elem_loss(out2d, bt, bw, mode,
                                          self.loss_bbox.loss_weight / num_total_samples,
                                          col_off=A, ncols=4 * A, beta=beta))
         return dict(loss_rpn_cls=loss_cls, loss_rpn_bbox=loss_bbox)
@@ -223,50 +268,45 @@ class RPNHead(nn.Module):
         n_img = len(img_metas)
         dev = cls_scores[0].device
         max_ratio = float(np.abs(np.log(16 / 1000)))
-        per_img_boxes, per_img_scores, per_img_ids = [], [], []
+        shapes = [tuple(m['img_shape'][:2]) for m in img_metas]
+        assert all(s == shapes[0] for s in shapes), 'batched tiles must share one img_shape'
+        img_h, img_w = shapes[0]
+        boxes_l, scores_l, ids_l = [], [], []
+        for l, cs in enumerate(cls_scores):
+            fused = cs._loft_fused                                     # [N,16,h,w], NHWC storage
+            fh, fw = fused.shape[2], fused.shape[3]
+            out3d = fused.permute(0, 2, 3, 1).reshape(n_img, fh * fw, _FUSED_W)
+            scores = out3d[:, :, :A].reshape(n_img, -1).sigmoid()      # (h, w, a) order
+            n = scores.shape[1]
+            if cfg.nms_pre > 0 and n > cfg.nms_pre:
+                ranked, rank_inds = scores.sort(dim=1, descending=True, stable=True)
+                topk = rank_inds[:, :cfg.nms_pre].contiguous()
+                scores = ranked[:, :cfg.nms_pre]
+            else:
+                topk = torch.arange(n, device=dev).expand(n_img, n).contiguous()
+            k = topk.shape[1]
+            boxes = torch.empty((n_img, k, 4), device=dev, dtype=torch.float32)
+            stride = self.anchor_generator.strides[l][0]
+            L.call('rpn_decode', L.ptr(out3d), i32(_FUSED_W), i32(A), L.ptr(topk), i32(k), i32(fw),
+                   i32(A), L.ptr(self._base_anchors_dev[l]), L.f32(stride), L.f32(max_ratio),
+                   L.f32(img_h), L.f32(img_w), L.ptr(boxes), i32(n_img),
+                   L.ll(fh * fw * _FUSED_W), L.ll(k), L.ll(k * 4), L.stream())
+            boxes_l.append(boxes)
+            scores_l.append(scores)
+            ids_l.append(torch.full((n_img, k), l, device=dev, dtype=torch.long))
+        bx = torch.cat(boxes_l, dim=1)
+        sc = torch.cat(scores_l, dim=1)
+        ids = torch.cat(ids_l, dim=1)
+        order = sc.sort(dim=1, descending=True, stable=True)[1]
+        bx_s = torch.gather(bx, 1, order[:, :, None].expand(-1, -1, 4)).contiguous()
+        ids_s = torch.gather(ids, 1, order).contiguous()
+        sc_s = torch.gather(sc, 1, order)
+        keep, num = nms_sorted(bx_s, ids_s, float(cfg.nms_thr), int(cfg.nms_post))
+        num_h = num.tolist()
+        results = []
         for i in range(n_img):
-            img_h, img_w = img_metas[i]['img_shape'][:2]
-            boxes_l, scores_l, ids_l = [], [], []
-            for l, cs in enumerate(cls_scores):
-                fused = cs._loft_fused
-                fh, fw = fused.shape[2], fused.shape[3]
-                out2d = fused[i].permute(1, 2, 0).reshape(-1, _FUSED_W)       # [h*w, 16] view
-                scores = out2d[:, :A].reshape(-1).sigmoid()
-                n = scores.shape[0]
-                if cfg.nms_pre > 0 and n > cfg.nms_pre:
-                    ranked, rank_inds = scores.sort(descending=True, stable=True)
-                    topk = rank_inds[:cfg.nms_pre].contiguous()
-                    scores = ranked[:cfg.nms_pre]
-                else:
-                    topk = torch.arange(n, device=dev)
-                k = topk.shape[0]
-                boxes = torch.empty((k, 4), device=dev, dtype=torch.float32)
-                stride = self.anchor_generator.strides[l][0]
-                L.call('rpn_decode', L.ptr(out2d), i32(_FUSED_W), i32(A), L.ptr(topk), i32(k),
-                       i32(fw), i32(A), L.ptr(self._base_anchors_dev[l]), L.f32(stride),
-                       L.f32(max_ratio), L.f32(img_h), L.f32(img_w), L.ptr(boxes), L.stream())
-                boxes_l.append(boxes)
-                scores_l.append(scores)
-                ids_l.append(torch.full((k,), l, device=dev, dtype=torch.long))
-            per_img_boxes.append(torch.cat(boxes_l))
-            per_img_scores.append(torch.cat(scores_l))
-            per_img_ids.append(torch.cat(ids_l))
-        same = all(b.shape[0] == per_img_boxes[0].shape[0] for b in per_img_boxes)
-        groups = [list(range(n_img))] if same else [[i] for i in range(n_img)]
-        results = [None] * n_img
-        for grp in groups:
-            sc = torch.stack([per_img_scores[i] for i in grp])
-            order = sc.sort(dim=1, descending=True, stable=True)[1]
-            bx = torch.stack([per_img_boxes[i] for i in grp])
-            ids = torch.stack([per_img_ids[i] for i in grp])
-            bx_s = torch.gather(bx, 1, order[:, :, None].expand(-1, -1, 4)).contiguous()
-            ids_s = torch.gather(ids, 1, order).contiguous()
-            sc_s = torch.gather(sc, 1, order)
-            keep, num = nms_sorted(bx_s, ids_s, float(cfg.nms_thr), int(cfg.nms_post))
-            num_h = num.tolist()
-            for j, i in enumerate(grp):
-                kk = keep[j, :num_h[j]]
-                results[i] = torch.cat([bx_s[j, kk], sc_s[j, kk, None]], dim=1)
+            kk = keep[i, :num_h[i]]
+            results.append(torch.cat([bx_s[i, kk], sc_s[i, kk, None]], dim=1))
         return results
 
     def simple_test_rpn(self, x, img_metas):

@@ -60,6 +60,9 @@ class TwoStageDetector(BaseDetector):
                       gt_masks=None, proposals=None, **kwargs):
         store = get_store(self, img.device if img.is_cuda else None)
         store.begin_step()
+        ready_event = kwargs.pop('ready_event', None)    # inputs staged on a copy stream
+        if ready_event is not None:
+            torch.cuda.current_stream(store.device).wait_event(ready_event)
         if not img.is_cuda:
             img = img.to(store.device, non_blocking=True)
         dev = store.device
@@ -68,6 +71,8 @@ class TwoStageDetector(BaseDetector):
         for k, v in list(kwargs.items()):
             if isinstance(v, (list, tuple)) and len(v) and isinstance(v[0], torch.Tensor):
                 kwargs[k] = [t.to(dev, non_blocking=True) for t in v]
+        if self.with_rpn and hasattr(self.rpn_head, 'prefetch_targets') and len(gt_bboxes) > 0:
+            self.rpn_head.prefetch_targets(gt_bboxes, img_metas, img.shape[-2:], ready_event)
         x = self.extract_feat(img)
         losses = dict()
         if self.with_rpn:

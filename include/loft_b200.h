@@ -125,7 +125,8 @@ int loft_iou_assign(const float* boxes, long long n, const float* gts, int G, fl
                     float* max_overlaps, void* workspace, size_t ws_bytes, cudaStream_t stream);
 int loft_rpn_decode(const float* head_out, int ld, int reg_off, const long long* topk_idx, int k,
                     int fw, int A, const float* base_anchors, float stride, float max_ratio,
-                    float img_h, float img_w, float* boxes_out, cudaStream_t stream);
+                    float img_h, float img_w, float* boxes_out, int batch, long long head_stride,
+                    long long idx_stride, long long out_stride, cudaStream_t stream);
 size_t loft_nms_workspace(int n);
 int loft_nms_sorted(const float* boxes, const long long* idxs, int B, int n, float iou_thr,
                     int max_keep, long long* keep, int* num_keep, void* workspace, size_t ws_bytes,
