@@ -74,6 +74,12 @@ struct GemmParams {
   int round_out;  // round `out` to TF32 (RNA) so the next MMA's operand truncation is exact
   long long ldw;  // WGRAD: row pitch of dW
   int tap_stride; // WGRAD_CONV: column offset per tap in dW (= Cin)
+  // grouped conv modes (FOA: 4 branches with their own weights in one launch)
+  int groups;               // >= 1
+  int group_n;              // images (RoIs) per group along the N axis of the activations
+  int splits;               // WGRAD: split-K factor per (group, tap, tile)
+  long long vec_gstride;    // scale / shift stride between groups (floats)
+  long long out_gstride;    // WGRAD: dW stride between groups (floats)
 };
 
 struct DebugOverrides {
@@ -140,20 +146,27 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
         int t = tile;
         const int ct = t % p.nct;
         t /= p.nct;
-        int pt = t, tap = 0, split = 0;
+        int pt = t % p.npt, tap = 0, split = 0, grp;
+        t /= p.npt;
         if (is_wgrad) {
-          pt = t % p.npt;
-          t /= p.npt;
           tap = t % p.ntaps;
-          split = t / p.ntaps;
+          t /= p.ntaps;
+          split = t % p.splits;
+          grp = t / p.splits;
+        } else {
+          grp = t;
         }
+        const int gn0 = grp * p.group_n;  // first image of this group
         int kb_begin = 0, kb_count = p.num_kb;
         if (is_wgrad) {
           kb_begin = split * p.kb_per_split;
           kb_count = min(p.kb_per_split, p.num_kb - kb_begin);
         }
         int n0 = 0, h0 = 0, w0 = 0;
-        if (p.mode == FPROP_CONV || p.mode == DGRAD_CONV) tile_pixel_origin(p, pt, n0, h0, w0);
+        if (p.mode == FPROP_CONV || p.mode == DGRAD_CONV) {
+          tile_pixel_origin(p, pt, n0, h0, w0);
+          n0 += gn0;
+        }
         const int tdh = tap / 3 - 1, tdw = tap % 3 - 1;  // WGRAD_CONV tap shift
         for (int kbi = 0; kbi < kb_count; ++kbi, ++it) {
           const int kb = kb_begin + kbi;
@@ -171,7 +184,7 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
             case FPROP_CONV: {
               const int tp = kb / p.cchunks, ch = kb % p.cchunks;
               const int dh = (p.ntaps == 9) ? tp / 3 - 1 : 0, dw = (p.ntaps == 9) ? tp % 3 - 1 : 0;
-              tma_load_2d(sa, &tmap_a, &full_bar[s], kb * kKB, ct * kBlockC);
+              tma_load_3d(sa, &tmap_a, &full_bar[s], kb * kKB, ct * kBlockC, grp);
               tma_load_4d(sb, &tmap_b, &full_bar[s], ch * kKB, w0 + dw, h0 + dh, n0);
               break;
             }
@@ -184,8 +197,8 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
               const int tp = kb / p.cchunks, ch = kb % p.cchunks;
               const int dh = (p.ntaps == 9) ? tp / 3 - 1 : 0, dw = (p.ntaps == 9) ? tp % 3 - 1 : 0;
               // A view of W[Cout][ntaps*Cin]: chunk index = (tap*Cin + cin0)/32
-              tma_load_3d(sa, &tmap_a, &full_bar[s], 0, ch * kKB,
-                          tp * (p.tap_stride / 32) + ct * (kBlockC / 32));
+              tma_load_4d(sa, &tmap_a, &full_bar[s], 0, ch * kKB,
+                          tp * (p.tap_stride / 32) + ct * (kBlockC / 32), grp);
               tma_load_4d(sb, &tmap_b, &full_bar[s], ch * kKB, w0 - dw, h0 - dh, n0);
               break;
             }
@@ -196,6 +209,7 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
             case WGRAD_CONV: {
               int kn0, kh0, kw0;
               tile_pixel_origin(p, kb, kn0, kh0, kw0);
+              kn0 += gn0;
               tma_load_5d(sa, &tmap_a, &full_bar[s], 0, kw0, kh0, kn0, ct * (kBlockC / 32));
               tma_load_5d(sb, &tmap_b, &full_bar[s], 0, kw0 + tdw, kh0 + tdh, kn0,
                           pt * (p.n_mma / 32));
@@ -212,7 +226,7 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
         int kb_count = p.num_kb;
         if (is_wgrad) {
-          const int split = tile / (p.nct * p.npt * p.ntaps);
+          const int split = (tile / (p.nct * p.npt * p.ntaps)) % p.splits;
           kb_count = min(p.kb_per_split, p.num_kb - split * p.kb_per_split);
         }
         const uint32_t as = lt & 1u, aph = (lt >> 1) & 1u;
@@ -251,12 +265,15 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
       int t = tile;
       const int ct = t % p.nct;
       t /= p.nct;
-      int pt = t, tap = 0;
+      int pt = t % p.npt, tap = 0, grp;
+      t /= p.npt;
       if (is_wgrad) {
-        pt = t % p.npt;
-        t /= p.npt;
         tap = t % p.ntaps;
+        grp = t / (p.ntaps * p.splits);
+      } else {
+        grp = t;
       }
+      const int n_lim = p.groups > 1 ? (grp + 1) * p.group_n : p.N;
       const uint32_t as = lt & 1u, aph = (lt >> 1) & 1u;
       int* s_row = row_tab + as * (2 * kMaxN);
       int* s_rrow = s_row + kMaxN;
@@ -270,13 +287,14 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (p.mode == FPROP_CONV || p.mode == DGRAD_CONV) {
             int n0, h0, w0;
             tile_pixel_origin(p, pt, n0, h0, w0);
+            n0 += grp * p.group_n;
             const int thw = p.th * p.tw;
             const int jn = col / thw, r = col - jn * thw;
             const int jh = r / p.tw, jw = r - jh * p.tw;
             pn = n0 + jn;
             ph_ = h0 + jh;
             pw_ = w0 + jw;
-            ok = (jn < p.tn) && (pn < p.N) && (ph_ < p.H) && (pw_ < p.W);
+            ok = (jn < p.tn) && (pn < n_lim) && (ph_ < p.H) && (pw_ < p.W);
             pix = ((long long)pn * p.H + ph_) * p.W + pw_;
           } else {
             pix = (long long)pt * p.n_mma + col;
@@ -304,8 +322,8 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const uint32_t taddr = tmem_base + as * kMaxN + ((uint32_t)(q * 32) << 16);
 
       if (is_wgrad) {
-        float* drow = p.out + (long long)c * p.ldw + (long long)tap * p.tap_stride +
-                      (long long)pt * p.n_mma;
+        float* drow = p.out + (long long)grp * p.out_gstride + (long long)c * p.ldw +
+                      (long long)tap * p.tap_stride + (long long)pt * p.n_mma;
         const int ncol = min(p.n_mma, p.Cn - pt * p.n_mma);
         for (int cc = half * 16; cc < p.n_mma; cc += 32) {
           float v[16];
@@ -317,8 +335,9 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
           }
         }
       } else {
-        const float sc = (p.scale != nullptr && c_ok) ? p.scale[c] : 1.f;
-        const float sh = (p.shift != nullptr && c_ok) ? p.shift[c] : 0.f;
+        const long long vo = (long long)grp * p.vec_gstride;
+        const float sc = (p.scale != nullptr && c_ok) ? p.scale[vo + c] : 1.f;
+        const float sh = (p.shift != nullptr && c_ok) ? p.shift[vo + c] : 0.f;
         int ocol = c, row_add = 0;
         if (p.out_map == 1) {
           // deconv 2x2 stride 2: channel index c = (i*2 + j2)*Co + co
@@ -595,6 +614,8 @@ int loft_gemm_fprop(const float* x, const float* w, float* y, long long P, int K
   if (P == 0) return LOFT_OK;
   GemmParams p{};
   p.mode = FPROP_2D;
+  p.groups = 1;
+  p.splits = 1;
   p.nct = loft_cdiv(Cout, kBlockC);
   p.n_mma = pick_n_2d(P, p.nct);
   p.npt = loft_cdiv(P, p.n_mma);
@@ -638,6 +659,8 @@ int loft_gemm_dgrad(const float* dy, const float* w, float* dx, long long P, int
   if (P == 0) return LOFT_OK;
   GemmParams p{};
   p.mode = DGRAD_2D;
+  p.groups = 1;
+  p.splits = 1;
   p.nct = loft_cdiv(Cin, kBlockC);
   p.n_mma = pick_n_2d(P, p.nct);
   p.npt = loft_cdiv(P, p.n_mma);
@@ -693,6 +716,8 @@ int loft_gemm_wgrad(const float* dy, const float* x, float* dw, long long P, int
   p.kb_per_split = loft_cdiv(p.num_kb, splits);
   splits = loft_cdiv(p.num_kb, p.kb_per_split);
   p.num_tiles = base * splits;
+  p.groups = 1;
+  p.splits = splits;
   p.tx_bytes = kABytes + p.n_mma * kKB * 4;
   p.Cm = Cout;
   p.Cn = Cin;
@@ -719,20 +744,31 @@ int loft_gemm_wgrad(const float* dy, const float* x, float* dw, long long P, int
 }
 
 // 3x3 / pad 1 / stride 1 convolution over NHWC, weights [Cout][3][3][Cin].
-int loft_conv3x3_fprop(const float* x, const float* w, float* y, int N, int H, int W, int Cin,
-                       int Cout, const loft_epilogue_t* epi, cudaStream_t stream) {
+// Grouped form: the N images are G consecutive groups of N/G images; group g uses the weights at
+// w + g*w_gstride (and scale/shift at + g*vec_gstride): the four FOA branches in one launch.
+int loft_conv3x3_fprop_grouped(const float* x, const float* w, float* y, int N, int H, int W,
+                               int Cin, int Cout, int G, long long w_gstride,
+                               long long vec_gstride, const loft_epilogue_t* epi,
+                               cudaStream_t stream) {
   LOFT_CHECK_ARG(x && w && y, "conv3x3_fprop: null pointer");
   LOFT_CHECK_SHAPE(Cin % 32 == 0, "conv3x3_fprop: Cin=%d must be a multiple of 32", Cin);
+  LOFT_CHECK_SHAPE(G >= 1 && N % G == 0 && (G == 1 || w_gstride % 4 == 0),
+                   "conv3x3_fprop: bad grouping N=%d G=%d", N, G);
   if (N == 0) return LOFT_OK;
+  const int Ng = N / G;
   GemmParams p{};
   p.mode = FPROP_CONV;
+  p.groups = G;
+  p.group_n = Ng;
+  p.splits = 1;
+  p.vec_gstride = vec_gstride;
   p.nct = loft_cdiv(Cout, kBlockC);
-  pick_pixel_tile(N, H, W, p.nct, p.tn, p.th, p.tw);
+  pick_pixel_tile(Ng, H, W, p.nct * G, p.tn, p.th, p.tw);
   p.n_mma = round16(p.tn * p.th * p.tw);
   p.tiles_w = loft_cdiv(W, p.tw);
   p.tiles_h = loft_cdiv(H, p.th);
-  p.npt = p.tiles_w * p.tiles_h * loft_cdiv(N, p.tn);
-  p.num_tiles = p.nct * p.npt;
+  p.npt = p.tiles_w * p.tiles_h * loft_cdiv(Ng, p.tn);
+  p.num_tiles = p.nct * p.npt * G;
   p.cchunks = Cin / 32;
   p.ntaps = 9;
   p.num_kb = 9 * p.cchunks;
@@ -746,10 +782,11 @@ int loft_conv3x3_fprop(const float* x, const float* w, float* y, int N, int H, i
   set_epilogue(p, epi, y, Cout);
   CUtensorMap ta, tb;
   {
-    uint64_t d[2] = {(uint64_t)9 * Cin, (uint64_t)Cout};
-    uint64_t s[1] = {(uint64_t)9 * Cin * 4};
-    uint32_t b[2] = {kKB, kBlockC};
-    int r = make_tmap(&ta, 2, w, d, s, b);
+    uint64_t d[3] = {(uint64_t)9 * Cin, (uint64_t)Cout, (uint64_t)G};
+    uint64_t s[2] = {(uint64_t)9 * Cin * 4,
+                     (uint64_t)(G > 1 ? w_gstride : (long long)9 * Cin * Cout) * 4};
+    uint32_t b[3] = {kKB, kBlockC, 1};
+    int r = make_tmap(&ta, 3, w, d, s, b);
     if (r) return r;
   }
   {
@@ -762,21 +799,33 @@ int loft_conv3x3_fprop(const float* x, const float* w, float* y, int N, int H, i
   return launch(ta, tb, p, stream);
 }
 
-int loft_conv3x3_dgrad(const float* dy, const float* w, float* dx, int N, int H, int W, int Cin,
+int loft_conv3x3_fprop(const float* x, const float* w, float* y, int N, int H, int W, int Cin,
                        int Cout, const loft_epilogue_t* epi, cudaStream_t stream) {
+  return loft_conv3x3_fprop_grouped(x, w, y, N, H, W, Cin, Cout, 1, 0, 0, epi, stream);
+}
+
+int loft_conv3x3_dgrad_grouped(const float* dy, const float* w, float* dx, int N, int H, int W,
+                               int Cin, int Cout, int G, long long w_gstride,
+                               const loft_epilogue_t* epi, cudaStream_t stream) {
   LOFT_CHECK_ARG(dy && w && dx, "conv3x3_dgrad: null pointer");
   LOFT_CHECK_SHAPE(Cin % 32 == 0 && Cout % 4 == 0,
                    "conv3x3_dgrad: Cin=%d must be a multiple of 32, Cout=%d of 4", Cin, Cout);
+  LOFT_CHECK_SHAPE(G >= 1 && N % G == 0 && (G == 1 || w_gstride % 4 == 0),
+                   "conv3x3_dgrad: bad grouping N=%d G=%d", N, G);
   if (N == 0) return LOFT_OK;
+  const int Ng = N / G;
   GemmParams p{};
   p.mode = DGRAD_CONV;
+  p.groups = G;
+  p.group_n = Ng;
+  p.splits = 1;
   p.nct = loft_cdiv(Cin, kBlockC);
-  pick_pixel_tile(N, H, W, p.nct, p.tn, p.th, p.tw);
+  pick_pixel_tile(Ng, H, W, p.nct * G, p.tn, p.th, p.tw);
   p.n_mma = round16(p.tn * p.th * p.tw);
   p.tiles_w = loft_cdiv(W, p.tw);
   p.tiles_h = loft_cdiv(H, p.th);
-  p.npt = p.tiles_w * p.tiles_h * loft_cdiv(N, p.tn);
-  p.num_tiles = p.nct * p.npt;
+  p.npt = p.tiles_w * p.tiles_h * loft_cdiv(Ng, p.tn);
+  p.num_tiles = p.nct * p.npt * G;
   p.cchunks = loft_cdiv(Cout, 32);
   p.ntaps = 9;
   p.num_kb = 9 * p.cchunks;
@@ -791,10 +840,11 @@ int loft_conv3x3_dgrad(const float* dy, const float* w, float* dx, int N, int H,
   set_epilogue(p, epi, dx, Cin);
   CUtensorMap ta, tb;
   {
-    uint64_t d[3] = {32, (uint64_t)Cout, (uint64_t)(9 * Cin / 32)};
-    uint64_t s[2] = {(uint64_t)9 * Cin * 4, 128};
-    uint32_t b[3] = {32, kKB, kBlockC / 32};
-    int r = make_tmap(&ta, 3, w, d, s, b, true);
+    uint64_t d[4] = {32, (uint64_t)Cout, (uint64_t)(9 * Cin / 32), (uint64_t)G};
+    uint64_t s[3] = {(uint64_t)9 * Cin * 4, 128,
+                     (uint64_t)(G > 1 ? w_gstride : (long long)9 * Cin * Cout) * 4};
+    uint32_t b[4] = {32, kKB, kBlockC / 32, 1};
+    int r = make_tmap(&ta, 4, w, d, s, b, true);
     if (r) return r;
   }
   {
@@ -807,28 +857,42 @@ int loft_conv3x3_dgrad(const float* dy, const float* w, float* dx, int N, int H,
   return launch(ta, tb, p, stream);
 }
 
-int loft_conv3x3_wgrad(const float* dy, const float* x, float* dw, int N, int H, int W, int Cin,
-                       int Cout, cudaStream_t stream) {
+int loft_conv3x3_dgrad(const float* dy, const float* w, float* dx, int N, int H, int W, int Cin,
+                       int Cout, const loft_epilogue_t* epi, cudaStream_t stream) {
+  return loft_conv3x3_dgrad_grouped(dy, w, dx, N, H, W, Cin, Cout, 1, 0, epi, stream);
+}
+
+int loft_conv3x3_wgrad_grouped(const float* dy, const float* x, float* dw, int N, int H, int W,
+                               int Cin, int Cout, int G, long long dw_gstride,
+                               cudaStream_t stream) {
   LOFT_CHECK_ARG(dy && x && dw, "conv3x3_wgrad: null pointer");
   LOFT_CHECK_SHAPE(Cin % 32 == 0 && Cout % 32 == 0,
                    "conv3x3_wgrad: Cin=%d and Cout=%d must be multiples of 32", Cin, Cout);
+  LOFT_CHECK_SHAPE(G >= 1 && N % G == 0, "conv3x3_wgrad: bad grouping N=%d G=%d", N, G);
   if (N == 0) return LOFT_OK;
+  const int Ng = N / G;
   GemmParams p{};
   p.mode = WGRAD_CONV;
+  p.groups = G;
+  p.group_n = Ng;
+  p.out_gstride = dw_gstride;
   pick_k_patch(H, W, p.tn, p.th, p.tw);
+  LOFT_CHECK_SHAPE(G == 1 || Ng % p.tn == 0,
+                   "conv3x3_wgrad: group size %d not a multiple of the k-patch depth %d", Ng, p.tn);
   p.tiles_w = loft_cdiv(W, p.tw);
   p.tiles_h = loft_cdiv(H, p.th);
   p.n_mma = Cin >= 256 ? 256 : Cin;
   p.nct = loft_cdiv(Cout, kBlockC);
   p.npt = loft_cdiv(Cin, p.n_mma);
   p.ntaps = 9;
-  p.num_kb = p.tiles_w * p.tiles_h * loft_cdiv(N, p.tn);
-  int base = p.nct * p.npt * 9;
+  p.num_kb = p.tiles_w * p.tiles_h * loft_cdiv(Ng, p.tn);  // k-blocks per group
+  int base = p.nct * p.npt * 9 * G;
   int splits = loft_num_sms() / base;  // floor: one full wave, never a ragged second one
   if (splits < 1) splits = 1;
   if (splits > p.num_kb) splits = p.num_kb;
   p.kb_per_split = loft_cdiv(p.num_kb, splits);
   splits = loft_cdiv(p.num_kb, p.kb_per_split);
+  p.splits = splits;
   p.num_tiles = base * splits;
   p.tx_bytes = kABytes + p.n_mma * kKB * 4;
   p.N = N;
@@ -856,6 +920,11 @@ int loft_conv3x3_wgrad(const float* dy, const float* x, float* dw, int N, int H,
     if (r) return r;
   }
   return launch(ta, tb, p, stream);
+}
+
+int loft_conv3x3_wgrad(const float* dy, const float* x, float* dw, int N, int H, int W, int Cin,
+                       int Cout, cudaStream_t stream) {
+  return loft_conv3x3_wgrad_grouped(dy, x, dw, N, H, W, Cin, Cout, 1, 0, stream);
 }
 
 }  // extern "C"

@@ -82,6 +82,21 @@ class OffsetHeadExpandFeature(nn.Module):
         self._conv_specs = [[D.ConvSpec(c.weight._loft, ksize=3, padding=1, relu=True, bias=c.bias,
                                         bias_grad=c.bias._loft.grad, store=store) for c in convs]
                             for convs in self.expand_convs]
+        # the same conv layer of all branches in one grouped launch (weights are equally strided
+        # in the ParamStore's flat buffers)
+        self._group_specs = None
+        nconv = len(self.expand_convs[0])
+        if self.expand_feature_num > 1 and all(len(c) == nconv for c in self.expand_convs) and \
+                self.in_channels == self.conv_out_channels:
+            gs = []
+            for i in range(nconv):
+                convs = [self.expand_convs[b][i] for b in range(self.expand_feature_num)]
+                gs.append(D.GroupedConvSpec([c.weight._loft for c in convs],
+                                            [c.bias for c in convs],
+                                            [c.bias._loft.grad for c in convs], relu=True,
+                                            store=store))
+            if all(g.uniform for g in gs):
+                self._group_specs = gs
         area = self.roi_feat_size[0] * self.roi_feat_size[1]
         self._fc_specs = []
         for i, fc in enumerate(self.fcs):
@@ -100,13 +115,21 @@ class OffsetHeadExpandFeature(nn.Module):
     def forward(self, x):
         if x.size(0) == 0:
             return x.new_empty(x.size(0), 2 * self.expand_feature_num)
-        feats = []
-        for idx in range(self.expand_feature_num):
-            y = self.expand_feature(x, idx)
-            for conv, spec in zip(self.expand_convs[idx], self._conv_specs[idx]):
-                y = D.conv(y, spec, triggers=(conv.weight, conv.bias))
-            feats.append(D.nhwc(y).reshape(y.shape[0], -1))
-        y = torch.cat(feats, 0)                                  # [4P, 7*7*C], branch-major
+        if self._group_specs is not None:
+            # branch-major batch [4P, C, 7, 7]; each layer of the 4 branches is ONE launch
+            y = torch.cat([self.expand_feature(x, idx) for idx in range(self.expand_feature_num)], 0)
+            for i, gspec in enumerate(self._group_specs):
+                trig = tuple(self.expand_convs[b][i].weight for b in range(self.expand_feature_num))
+                y = D.grouped_conv3x3(y, gspec, triggers=trig)
+            y = D.nhwc(y).reshape(y.shape[0], -1)                # [4P, 7*7*C], branch-major
+        else:
+            feats = []
+            for idx in range(self.expand_feature_num):
+                yb = self.expand_feature(x, idx)
+                for conv, spec in zip(self.expand_convs[idx], self._conv_specs[idx]):
+                    yb = D.conv(yb, spec, triggers=(conv.weight, conv.bias))
+                feats.append(D.nhwc(yb).reshape(yb.shape[0], -1))
+            y = torch.cat(feats, 0)                              # [4P, 7*7*C], branch-major
         for fc, spec in zip(self.fcs, self._fc_specs):
             y = D.linear(y, spec, triggers=(fc.weight, fc.bias))
         fused = D.linear(y, self._head, triggers=(self.fc_offset.weight, self.fc_offset.bias))

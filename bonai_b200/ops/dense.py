@@ -348,3 +348,81 @@ def deconv2x2(x, spec, triggers=()):
         N, _, H, W = x.shape
         return x.new_zeros((0, spec.wref.w.shape[0] // 4, 2 * H, 2 * W))
     return _Deconv2x2Fn.apply(x, spec, *triggers)
+
+
+# ----------------------------------------------------------------------------------- grouped 3x3
+class GroupedConvSpec:
+    """G convs (3x3/s1/p1 + bias + ReLU) with separate weights applied to G consecutive groups of
+    images in ONE launch.  The per-group weights / biases / gradients must be equally strided in
+    memory (true for the FOA branches in the ParamStore's flat buffers)."""
+
+    def __init__(self, wrefs, biases, bias_grads, relu=True, store=None):
+        self.G = len(wrefs)
+        self.w0 = wrefs[0].w
+        self.gw0 = wrefs[0].grad
+        self.b0 = biases[0]
+        self.bias_grads = bias_grads
+        self.relu = relu
+        self.store = store
+        self.cout, self.cin = wrefs[0].w.shape[0], wrefs[0].w.shape[1]
+
+        def stride(ts):
+            d = [(ts[i + 1].data_ptr() - ts[i].data_ptr()) for i in range(len(ts) - 1)]
+            ok = len(set(d)) <= 1 and (not d or (d[0] > 0 and d[0] % 16 == 0))
+            return (d[0] // 4 if d else 0), ok
+        self.w_gstride, ok1 = stride([r.w for r in wrefs])
+        self.b_gstride, ok2 = stride(list(biases))
+        ok3 = True
+        self.gw_gstride = 0
+        if self.gw0 is not None:
+            self.gw_gstride, ok3 = stride([r.grad for r in wrefs])
+        self.uniform = ok1 and ok2 and ok3
+
+
+class _GroupedConv3x3Fn(Function):
+    @staticmethod
+    def forward(ctx, x, spec, *triggers):
+        N, Cin, H, W = x.shape
+        xn = nhwc(x)
+        y = new_nhwc(N, spec.cout, H, W, x.device)
+        e = L.make_epilogue(shift=spec.b0, relu=spec.relu, round_out=True)
+        L.call('conv3x3_fprop_grouped', L.ptr(xn), L.ptr(spec.w0), L.ptr(y.permute(0, 2, 3, 1)),
+               i32(N), i32(H), i32(W), i32(Cin), i32(spec.cout), i32(spec.G), L.ll(spec.w_gstride),
+               L.ll(spec.b_gstride), ctypes.byref(e), L.stream())
+        ctx.spec = spec
+        ctx.save_for_backward(xn, y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        spec = ctx.spec
+        xn, y = ctx.saved_tensors
+        _queue_finalize(spec.store)
+        st = L.stream()
+        N, H, W, Cin = xn.shape
+        Cout, G = spec.cout, spec.G
+        dyn = nhwc(dy)
+        yn = nhwc(y)
+        dz = torch.empty_like(dyn)
+        rows_g = (N // G) * H * W
+        for g in range(G):
+            o = g * rows_g * Cout * 4
+            L.call('act_bwd', ctypes.c_void_p(dyn.data_ptr() + o), ctypes.c_void_p(yn.data_ptr() + o),
+                   None, None, None, None, ctypes.c_void_p(dz.data_ptr() + o), None, None,
+                   L.ptr(spec.bias_grads[g]) if spec.bias_grads[g] is not None else None,
+                   L.ll(rows_g), i32(Cout), i32(spec.relu), st)
+        if spec.gw0 is not None:
+            L.call('conv3x3_wgrad_grouped', L.ptr(dz), L.ptr(xn), L.ptr(spec.gw0), i32(N), i32(H),
+                   i32(W), i32(Cin), i32(Cout), i32(G), L.ll(spec.gw_gstride), st)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = new_nhwc(N, Cin, H, W, dy.device)
+            e = L.make_epilogue(round_out=True)
+            L.call('conv3x3_dgrad_grouped', L.ptr(dz), L.ptr(spec.w0), L.ptr(dx.permute(0, 2, 3, 1)),
+                   i32(N), i32(H), i32(W), i32(Cin), i32(Cout), i32(G), L.ll(spec.w_gstride),
+                   ctypes.byref(e), st)
+        return (dx, None) + (None,) * (len(ctx.needs_input_grad) - 2)
+
+
+def grouped_conv3x3(x, spec, triggers=()):
+    return _GroupedConv3x3Fn.apply(x, spec, *triggers)

@@ -64,6 +64,19 @@ int loft_conv3x3_dgrad(const float* dy, const float* w, float* dx, int N, int H,
                        int Cout, const loft_epilogue_t* epi, cudaStream_t stream);
 int loft_conv3x3_wgrad(const float* dy, const float* x, float* dw, int N, int H, int W, int Cin,
                        int Cout, cudaStream_t stream);
+/* grouped forms: the N images are G consecutive groups; group g reads the weights at
+ * w + g*w_gstride floats (scale/shift at + g*vec_gstride) -- the four FOA branches
+ * (offset_head_expand_feature.py:134-161) in one launch per layer */
+int loft_conv3x3_fprop_grouped(const float* x, const float* w, float* y, int N, int H, int W,
+                               int Cin, int Cout, int G, long long w_gstride,
+                               long long vec_gstride, const loft_epilogue_t* epi,
+                               cudaStream_t stream);
+int loft_conv3x3_dgrad_grouped(const float* dy, const float* w, float* dx, int N, int H, int W,
+                               int Cin, int Cout, int G, long long w_gstride,
+                               const loft_epilogue_t* epi, cudaStream_t stream);
+int loft_conv3x3_wgrad_grouped(const float* dy, const float* x, float* dw, int N, int H, int W,
+                               int Cin, int Cout, int G, long long dw_gstride,
+                               cudaStream_t stream);
 /* bring-up only: override UMMA descriptor fields (-1 = keep default) */
 void loft_debug_set_desc(long long a_desc, long long b_desc, long long a_kstep, long long b_kstep,
                          long long idesc);

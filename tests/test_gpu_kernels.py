@@ -417,3 +417,35 @@ def test_sgd_clip_step_vs_oracle():
     assert torch.allclose(p.cpu(), params['w'], rtol=1e-5, atol=1e-6)
     assert torch.allclose(m.cpu(), bufs['w'], rtol=1e-5, atol=1e-6)
     assert torch.equal(t, tf32_round(p))
+
+
+def test_grouped_conv3x3_matches_per_group():
+    """4 FOA-style branches (own weights) in one launch == 4 separate convs, fwd / dgrad / wgrad."""
+    from bonai_b200.engine import WeightRef
+    from bonai_b200.ops import dense as D
+    G, Pg, C = 4, 13, 256
+    wall = tf32_round(rnd(G, C + 1, 3, 3, C, seed=1, scale=0.03))       # +1 row of slack = stride
+    gwall = torch.zeros_like(wall)
+    ball = rnd(G, 260, seed=2)
+    gball = torch.zeros_like(ball)
+    wrefs = [WeightRef(wall[g, :C].permute(0, 3, 1, 2), gwall[g, :C].permute(0, 3, 1, 2))
+             for g in range(G)]
+    biases = [ball[g, :C] for g in range(G)]
+    bgrads = [gball[g, :C] for g in range(G)]
+    spec = D.GroupedConvSpec(wrefs, biases, bgrads, relu=True, store=_Store())
+    assert spec.uniform
+    x = tf32_round(rnd(G * Pg, C, 7, 7, seed=3)).contiguous(memory_format=torch.channels_last)
+    xg = x.clone().requires_grad_(True)
+    y = D.grouped_conv3x3(xg, spec)
+    dy = tf32_round(rnd(*y.shape, seed=4))
+    y.backward(dy)
+    for g in range(G):
+        xr = x[g * Pg:(g + 1) * Pg].clone().requires_grad_(True)
+        wr = wrefs[g].w.clone().requires_grad_(True)
+        br = biases[g].clone().requires_grad_(True)
+        yr = F.relu(F.conv2d(xr, wr, br, padding=1))
+        assert rel(y[g * Pg:(g + 1) * Pg], yr) < TF32_TOL
+        yr.backward(dy[g * Pg:(g + 1) * Pg])
+        assert rel(xg.grad[g * Pg:(g + 1) * Pg], xr.grad) < GRAD_TOL
+        assert rel(wrefs[g].grad, wr.grad) < GRAD_TOL
+        assert rel(bgrads[g], br.grad) < GRAD_TOL
