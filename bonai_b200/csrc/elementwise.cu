@@ -156,19 +156,19 @@ act_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ y,
 
 // ---------------------------------------------------------------- im2col / col2im (NHWC)
 // col[(n,ho,wo), (r,s,c)] ; K order matches the [Cout][kh][kw][Cin] weight layout. Kpad >= kh*kw*C.
-__global__ void im2col_kernel(const float* __restrict__ x, float* __restrict__ col, int N, int H,
-                              int W, int C, int kh, int kw, int stride, int pad, int Ho, int Wo,
-                              int Kpad, int nchw) {
-  const long long total = (long long)N * Ho * Wo * Kpad;
-  const int K = kh * kw * C;
+// NHWC input with C % 4 == 0: one thread per (row, tap, 4 channels), 16-byte loads and stores.
+__global__ void im2col_v4_kernel(const float4* __restrict__ x, float4* __restrict__ col, int N,
+                                 int H, int W, int C4, int kh, int kw, int stride, int pad, int Ho,
+                                 int Wo, int K4, int Kpad4) {
+  const long long total = (long long)N * Ho * Wo * Kpad4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)(i % Kpad);
-    const long long m = i / Kpad;
-    float v = 0.f;
-    if (k < K) {
-      const int c = k % C;
-      const int rs = k / C;
+    const int k4 = (int)(i % Kpad4);
+    const long long m = i / Kpad4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k4 < K4) {
+      const int c4 = k4 % C4;
+      const int rs = k4 / C4;
       const int s = rs % kw, r = rs / kw;
       const int wo = (int)(m % Wo);
       const long long t = m / Wo;
@@ -176,28 +176,62 @@ __global__ void im2col_kernel(const float* __restrict__ x, float* __restrict__ c
       const int n = (int)(t / Ho);
       const int h = ho * stride - pad + r, w = wo * stride - pad + s;
       if (h >= 0 && h < H && w >= 0 && w < W) {
-        v = nchw ? x[(((long long)n * C + c) * H + h) * W + w]
-                 : x[(((long long)n * H + h) * W + w) * C + c];
+        v = x[(((long long)n * H + h) * W + w) * C4 + c4];
+        v.x = tf32_rna(v.x);
+        v.y = tf32_rna(v.y);
+        v.z = tf32_rna(v.z);
+        v.w = tf32_rna(v.w);
       }
     }
-    col[i] = tf32_rna(v);
+    col[i] = v;
   }
 }
 
-// dx[n,h,w,c] = sum over taps of dcol[(n,ho,wo),(r,s,c)] (gather form, no atomics)
-__global__ void col2im_kernel(const float* __restrict__ dcol, float* __restrict__ dx,
-                              const float* __restrict__ mask, int N, int H, int W, int C, int kh,
-                              int kw, int stride, int pad, int Ho, int Wo, int Kpad) {
-  const long long total = (long long)N * H * W * C;
+// NCHW fp32 image (the 7x7/2 stem, C = 3): one thread per (row, tap) writes its C channels.
+__global__ void im2col_nchw_kernel(const float* __restrict__ x, float* __restrict__ col, int N, int H,
+                                   int W, int C, int kh, int kw, int stride, int pad, int Ho, int Wo,
+                                   int Kpad) {
+  const int taps = kh * kw;
+  const int K = taps * C;
+  const int slots = taps + (Kpad > K ? 1 : 0);  // last slot zero-fills the padding columns
+  const long long total = (long long)N * Ho * Wo * slots;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    long long t = i / C;
+    const int tap = (int)(i % slots);
+    const long long m = i / slots;
+    float* dst = col + m * Kpad;
+    if (tap == taps) {
+      for (int k = K; k < Kpad; ++k) dst[k] = 0.f;
+      continue;
+    }
+    const int s = tap % kw, r = tap / kw;
+    const int wo = (int)(m % Wo);
+    const long long t = m / Wo;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    const int h = ho * stride - pad + r, w = wo * stride - pad + s;
+    const bool in = (h >= 0 && h < H && w >= 0 && w < W);
+    for (int c = 0; c < C; ++c) {
+      const float v = in ? x[(((long long)n * C + c) * H + h) * W + w] : 0.f;
+      dst[tap * C + c] = tf32_rna(v);
+    }
+  }
+}
+
+// dx[n,h,w,c] = sum over taps of dcol[(n,ho,wo),(r,s,c)] (gather form, no atomics), float4 over c
+__global__ void col2im_v4_kernel(const float4* __restrict__ dcol, float4* __restrict__ dx,
+                                 const float4* __restrict__ mask, int N, int H, int W, int C4, int kh,
+                                 int kw, int stride, int pad, int Ho, int Wo, int Kpad4) {
+  const long long total = (long long)N * H * W * C4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    long long t = i / C4;
     const int w = (int)(t % W);
     t /= W;
     const int h = (int)(t % H);
     const int n = (int)(t / H);
-    float acc = 0.f;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int r = 0; r < kh; ++r) {
       const int hh = h + pad - r;
       if (hh < 0 || hh % stride) continue;
@@ -208,11 +242,22 @@ __global__ void col2im_kernel(const float* __restrict__ dcol, float* __restrict_
         if (ww < 0 || ww % stride) continue;
         const int wo = ww / stride;
         if (wo >= Wo) continue;
-        acc += dcol[(((long long)n * Ho + ho) * Wo + wo) * Kpad + (r * kw + s) * C + c];
+        const float4 v =
+            dcol[(((long long)n * Ho + ho) * Wo + wo) * Kpad4 + (r * kw + s) * C4 + c4];
+        acc.x += v.x;
+        acc.y += v.y;
+        acc.z += v.z;
+        acc.w += v.w;
       }
     }
-    if (mask && !(mask[i] > 0.f)) acc = 0.f;
-    dx[i] = tf32_rna(acc);
+    if (mask) {
+      const float4 mk = mask[i];
+      acc.x = mk.x > 0.f ? acc.x : 0.f;
+      acc.y = mk.y > 0.f ? acc.y : 0.f;
+      acc.z = mk.z > 0.f ? acc.z : 0.f;
+      acc.w = mk.w > 0.f ? acc.w : 0.f;
+    }
+    dx[i] = make_float4(tf32_rna(acc.x), tf32_rna(acc.y), tf32_rna(acc.z), tf32_rna(acc.w));
   }
 }
 
@@ -438,11 +483,19 @@ int loft_im2col(const float* x, float* col, int N, int H, int W, int C, int kh, 
                 int pad, int Kpad, int nchw_input, cudaStream_t stream) {
   LOFT_CHECK_ARG(x && col, "im2col: null pointer");
   const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
-  LOFT_CHECK_SHAPE(Kpad >= kh * kw * C, "im2col: Kpad too small");
-  const long long total = (long long)N * Ho * Wo * Kpad;
-  if (total == 0) return LOFT_OK;
-  im2col_kernel<<<grid_for(total, kT, 148 * 32), kT, 0, stream>>>(x, col, N, H, W, C, kh, kw, stride,
-                                                                 pad, Ho, Wo, Kpad, nchw_input);
+  LOFT_CHECK_SHAPE(Kpad >= kh * kw * C && Kpad % 4 == 0, "im2col: bad Kpad %d", Kpad);
+  if ((long long)N * Ho * Wo == 0) return LOFT_OK;
+  if (nchw_input) {
+    const long long total = (long long)N * Ho * Wo * (kh * kw + 1);
+    im2col_nchw_kernel<<<grid_for(total, kT, 148 * 32), kT, 0, stream>>>(x, col, N, H, W, C, kh, kw,
+                                                                        stride, pad, Ho, Wo, Kpad);
+  } else {
+    LOFT_CHECK_SHAPE(C % 4 == 0, "im2col: NHWC input needs C %% 4 == 0, got %d", C);
+    const long long total = (long long)N * Ho * Wo * (Kpad / 4);
+    im2col_v4_kernel<<<grid_for(total, kT, 148 * 32), kT, 0, stream>>>(
+        reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(col), N, H, W, C / 4, kh, kw,
+        stride, pad, Ho, Wo, kh * kw * C / 4, Kpad / 4);
+  }
   LOFT_CUDA_LAUNCH_CHECK("im2col");
   return LOFT_OK;
 }
@@ -450,11 +503,13 @@ int loft_im2col(const float* x, float* col, int N, int H, int W, int C, int kh, 
 int loft_col2im(const float* dcol, float* dx, const float* mask, int N, int H, int W, int C, int kh,
                 int kw, int stride, int pad, int Kpad, cudaStream_t stream) {
   LOFT_CHECK_ARG(dcol && dx, "col2im: null pointer");
+  LOFT_CHECK_SHAPE(C % 4 == 0 && Kpad % 4 == 0, "col2im: C and Kpad must be multiples of 4");
   const int Ho = (H + 2 * pad - kh) / stride + 1, Wo = (W + 2 * pad - kw) / stride + 1;
-  const long long total = (long long)N * H * W * C;
+  const long long total = (long long)N * H * W * (C / 4);
   if (total == 0) return LOFT_OK;
-  col2im_kernel<<<grid_for(total, kT, 148 * 32), kT, 0, stream>>>(dcol, dx, mask, N, H, W, C, kh, kw,
-                                                                 stride, pad, Ho, Wo, Kpad);
+  col2im_v4_kernel<<<grid_for(total, kT, 148 * 32), kT, 0, stream>>>(
+      reinterpret_cast<const float4*>(dcol), reinterpret_cast<float4*>(dx),
+      reinterpret_cast<const float4*>(mask), N, H, W, C / 4, kh, kw, stride, pad, Ho, Wo, Kpad / 4);
   LOFT_CUDA_LAUNCH_CHECK("col2im");
   return LOFT_OK;
 }

@@ -348,29 +348,30 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
         const float* __restrict__ res = p.residual;
         const float* __restrict__ msk = p.mask;
-        for (int cc = half * 16; cc < p.n_mma; cc += 32) {
-          float v[16];
-          tmem_ld16(taddr + cc, v);
+        constexpr int kCh = 32;  // columns per chunk: 32 independent loads in flight per thread
+        for (int cc = half * kCh; cc < p.n_mma; cc += 2 * kCh) {
+          float v[kCh];
+          tmem_ld32(taddr + cc, v);
           if (!c_ok) continue;
-          int rows[16];
-          float rv[16];
+          int rows[kCh];
+          float rv[kCh];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) rows[j] = s_row[cc + j];
+          for (int j = 0; j < kCh; ++j) rows[j] = s_row[cc + j];
           if (p.res_mode == 1) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
+            for (int j = 0; j < kCh; ++j)
               rv[j] = rows[j] >= 0 ? res[(long long)(rows[j] + row_add) * p.ldr + ocol] : 0.f;
           } else if (p.res_mode == 2) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
+            for (int j = 0; j < kCh; ++j)
               rv[j] = rows[j] >= 0 ? res[(long long)s_rrow[cc + j] * p.ldr + ocol] : 0.f;
           } else if (msk != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
+            for (int j = 0; j < kCh; ++j)
               rv[j] = rows[j] >= 0 ? msk[(long long)(rows[j] + row_add) * p.ldo + ocol] : 0.f;
           }
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
+          for (int j = 0; j < kCh; ++j) {
             if (rows[j] < 0) continue;
             const long long o = (long long)(rows[j] + row_add) * p.ldo + ocol;
             float acc = v[j];

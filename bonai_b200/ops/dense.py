@@ -131,20 +131,29 @@ class _ConvFn(Function):
         # 1. activation / affine backward (+ per-channel reductions)
         need_res = ctx.has_res and ctx.needs_input_grad[1]
         bn = spec.bn
-        dz = torch.empty_like(dyn)
         dres = None
-        if need_res and spec.relu and not spec.res_upsample:
-            dres = torch.empty_like(dyn)
         dgamma = bn.dgamma if (bn is not None and spec.bn_trainable) else None
         dbeta = bn.dbeta if (bn is not None and spec.bn_trainable) else spec.bias_grad
-        L.call('act_bwd', L.ptr(dyn), L.ptr(nhwc(y)) if y is not None else None,
-               L.ptr(z) if dgamma is not None else None,
-               L.ptr(bn.scale) if bn is not None else None,
-               L.ptr(bn.mean) if dgamma is not None else None,
-               L.ptr(bn.rstd) if dgamma is not None else None,
-               L.ptr(dz), L.ptr(dres) if dres is not None else None,
-               L.ptr(dgamma) if dgamma is not None else None,
-               L.ptr(dbeta) if dbeta is not None else None, L.ll(P), i32(Cout), i32(spec.relu), st)
+        if not spec.relu and bn is None:
+            # plain conv + bias: dz == dy, only the bias gradient needs a (read-only) pass.  dy is
+            # fed to the tensor cores as is; unrounded operands only bias *gradients* by ~5e-4.
+            dz = dyn
+            if dbeta is not None:
+                L.call('act_bwd', L.ptr(dyn), None, None, None, None, None, None, None, None,
+                       L.ptr(dbeta), L.ll(P), i32(Cout), i32(0), st)
+        else:
+            dz = torch.empty_like(dyn)
+            if need_res and spec.relu and not spec.res_upsample:
+                dres = torch.empty_like(dyn)
+            L.call('act_bwd', L.ptr(dyn), L.ptr(nhwc(y)) if y is not None else None,
+                   L.ptr(z) if dgamma is not None else None,
+                   L.ptr(bn.scale) if bn is not None else None,
+                   L.ptr(bn.mean) if dgamma is not None else None,
+                   L.ptr(bn.rstd) if dgamma is not None else None,
+                   L.ptr(dz), L.ptr(dres) if dres is not None else None,
+                   L.ptr(dgamma) if dgamma is not None else None,
+                   L.ptr(dbeta) if dbeta is not None else None, L.ll(P), i32(Cout),
+                   i32(spec.relu), st)
         grad_res = None
         if need_res:
             if spec.res_upsample:
@@ -248,10 +257,16 @@ class _LinearFn(Function):
         w = spec.wref.w
         Cout = w.shape[0]
         dy = dy.contiguous()
-        dz = torch.empty_like(dy)
-        L.call('act_bwd', L.ptr(dy), L.ptr(y) if y is not None else None, None, None, None, None,
-               L.ptr(dz), None, None, L.ptr(spec.bias_grad) if spec.bias_grad is not None else None,
-               L.ll(P), i32(Cout), i32(spec.relu), st)
+        if not spec.relu:
+            dz = dy
+            if spec.bias_grad is not None:
+                L.call('act_bwd', L.ptr(dy), None, None, None, None, None, None, None, None,
+                       L.ptr(spec.bias_grad), L.ll(P), i32(Cout), i32(0), st)
+        else:
+            dz = torch.empty_like(dy)
+            L.call('act_bwd', L.ptr(dy), L.ptr(y), None, None, None, None, L.ptr(dz), None, None,
+                   L.ptr(spec.bias_grad) if spec.bias_grad is not None else None, L.ll(P),
+                   i32(Cout), i32(spec.relu), st)
         if spec.wref.grad is not None:
             if Cout % 32 == 0:
                 L.call('gemm_wgrad', L.ptr(dz), L.ptr(x), L.ptr(spec.wref.grad), L.ll(P), i32(K),
