@@ -169,11 +169,24 @@ def cpu_oracle_step(n_img, threads):
     img, gb, gl, gm, go = O.make_inputs(0, n_img, IMG, NUM_GT)
     bufs = {}
 
+    # RoIAlign / NMS through torchvision -- what the reference itself executes on CPU over the
+    # import shim (oracle/shim/mmcv/ops) -- so the baseline is not slowed by the oracle's own
+    # gather-based restatement of those two ops.
+    import torchvision.ops as tvo
+
+    def tv_roi(feat, rois, out, scale, sr, aligned):
+        return tvo.roi_align(feat, rois, (out, out), scale, sr, aligned)
+
+    def tv_bnms(boxes, scores, ids, thr):
+        off = ids.to(boxes) * (boxes.max() + 1)
+        keep = tvo.nms(boxes + off[:, None], scores, thr)
+        return torch.cat([boxes[keep], scores[keep][:, None]], -1), keep
+
     def step():
         t = time.time()
         for k in tk:
             p[k].grad = None
-        losses = O.forward_train(p, img, gb, gl, gm, go)
+        losses = O.forward_train(p, img, gb, gl, gm, go, roi_align_fn=tv_roi, nms_fn=tv_bnms)
         loss, _ = O.parse_losses(losses)
         loss.backward()
         with torch.no_grad():
@@ -225,8 +238,12 @@ def main():
     ap.add_argument('--impl', default='loft_b200', choices=['loft_b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile', action='store_true', help='timed steps only (for ncu)')
+    ap.add_argument('--num-gt', type=int, default=80,
+                    help='GT boxes per tile: 80 = BONAI mean (init-like, P~100/img), 256 = '
+                         'steady-state-like (P=256/img), SURVEY 8(d)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != 'reference' else args.warmup
+    globals()['NUM_GT'] = args.num_gt
     if args.impl == 'reference':
         return run_reference(args)
 

@@ -175,11 +175,14 @@ class Trainer:
         model = self.model
         losses = model(**data)
         log_vars = OrderedDict()
+        def _m(v):                                   # fused losses are already 1-element sums
+            return v.reshape(()) if v.numel() == 1 else v.mean()
+
         for name, value in losses.items():
             if isinstance(value, torch.Tensor):
-                log_vars[name] = value.mean()
+                log_vars[name] = _m(value)
             else:
-                log_vars[name] = sum(v.mean() for v in value)
+                log_vars[name] = sum(_m(v) for v in value)
         loss = sum(v for k, v in log_vars.items() if 'loss' in k)
         log_vars['loss'] = loss
         loss.backward()
@@ -193,6 +196,29 @@ class Trainer:
         if read_logs:
             return self.read_logs()
         return packed
+
+    # ------------------------------------------------------------------ checkpoints
+    def save_checkpoint(self, path, meta=None):
+        """Reference checkpoint layout (mmcv save_checkpoint as used by CheckpointHook,
+        default_runtime.py:1): {'meta', 'state_dict', 'optimizer'}; state_dict keys / shapes are
+        the reference's, tensors are saved contiguous in the reference (OIHW) order."""
+        sd = {k: v.detach().cpu().contiguous() for k, v in self.model.state_dict().items()}
+        opt = {k: v.cpu() for k, v in self.store.momentum_state().items()}
+        m = dict(iter=self.iter, epoch=self.epoch, lr=self.current_lr())
+        m.update(meta or {})
+        torch.save({'meta': m, 'state_dict': sd, 'optimizer': {'momentum_buffer': opt}}, path)
+
+    def load_checkpoint(self, path, resume=True):
+        ck = torch.load(path, map_location='cpu')
+        sd = ck['state_dict'] if 'state_dict' in ck else ck
+        self.model.load_state_dict(sd)
+        self.store.refresh_weights(force=True)
+        if resume:
+            if 'optimizer' in ck and 'momentum_buffer' in ck['optimizer']:
+                self.store.load_momentum_state(ck['optimizer']['momentum_buffer'])
+            self.iter = ck.get('meta', {}).get('iter', 0)
+            self.epoch = ck.get('meta', {}).get('epoch', 0)
+        return ck.get('meta', {})
 
     def read_logs(self):
         """Packed mean over ranks + one host read-back (replaces the 8 all_reduce + .item() pairs

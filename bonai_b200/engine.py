@@ -103,6 +103,8 @@ class ParamStore:
             p.grad = gview
             p._loft = WeightRef(tview, gview)
             self._grad_views.append((p, gview))
+            if o < self.n_train:
+                p._loft_momentum = self.M[o:o + n]
         # BN statistics in two contiguous runs (trainable BNs, frozen BNs)
         self._bn_groups = []
         for group in (tr_bn, fz_bn):
@@ -221,6 +223,26 @@ class ParamStore:
                L.f32(grad_scale), L.ptr(self.sqnorm) if use_clip else None, L.stream())
         self._after_weight_update()
         self._seen_version = self.P._version
+
+    def momentum_state(self):
+        """{parameter name: momentum buffer (reference layout)} for checkpoints."""
+        out = {}
+        for name, p in self.model.named_parameters():
+            m = getattr(p, '_loft_momentum', None)
+            if m is not None:
+                phys = m.view(p.permute(0, 2, 3, 1).shape).permute(0, 3, 1, 2) \
+                    if (p.dim() == 4 and (p.shape[2] > 1 or p.shape[3] > 1)) else m.view(p.shape)
+                out[name] = phys.detach().clone().contiguous()
+        return out
+
+    def load_momentum_state(self, state):
+        for name, p in self.model.named_parameters():
+            m = getattr(p, '_loft_momentum', None)
+            if m is not None and name in state:
+                src = state[name].to(self.device)
+                dst = m.view(p.permute(0, 2, 3, 1).shape).permute(0, 3, 1, 2) \
+                    if (p.dim() == 4 and (p.shape[2] > 1 or p.shape[3] > 1)) else m.view(p.shape)
+                dst.copy_(src)
 
     def grad_norm(self):
         """Global L2 norm of the last step's gradients (device tensor, no sync)."""

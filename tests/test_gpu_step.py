@@ -214,3 +214,47 @@ def test_train_step_with_empty_gt_image():
     assert logs['loss_rpn_bbox'] == 0 and logs['loss_bbox'] == 0
     assert logs['loss_mask'] == 0 and logs['loss_offset'] == 0
     assert logs['loss_rpn_cls'] > 0 and logs['loss_cls'] > 0
+
+
+def test_checkpoint_roundtrip(tmp_path):
+    """save_checkpoint / load_checkpoint keep the reference's state_dict format (keys, OIHW shapes,
+    contiguous) and restore weights + momentum exactly."""
+    from bonai_b200 import Config
+    from bonai_b200.apis import Trainer
+    from bonai_b200.core import BitmapMasks
+    from bonai_b200.models import build_detector
+    from oracle import loft_cpu as O
+    cfg = Config.fromfile(os.path.join(ROOT, 'configs', 'loft', 'loft_foa_r50_fpn_2x_b200.py'))
+
+    def make(seed):
+        torch.manual_seed(seed)
+        m = build_detector(cfg.model, train_cfg=cfg.train_cfg, test_cfg=cfg.test_cfg)
+        m.train()
+        return m, Trainer(m, cfg, torch.device('cuda:0'))
+
+    model, trainer = make(0)
+    img, gb, gl, gm, go = O.make_inputs(0, 1, 256, 6)
+    metas = [dict(img_shape=(256, 256, 3), pad_shape=(256, 256, 3), scale_factor=1.0, flip=False)]
+    data = dict(img=img.cuda(), img_metas=metas, gt_bboxes=gb, gt_labels=gl,
+                gt_masks=[BitmapMasks(m, 256, 256) for m in gm], gt_offsets=go)
+    for _ in range(2):
+        trainer.train_step(data)
+    path = str(tmp_path / 'ck.pth')
+    trainer.save_checkpoint(path)
+    ck = torch.load(path, map_location='cpu')
+    ref = O.init_params(0)
+    assert set(ck['state_dict']) == set(ref)
+    assert all(ck['state_dict'][k].shape == ref[k].shape and ck['state_dict'][k].is_contiguous()
+               for k in ref)
+    model2, trainer2 = make(1)
+    meta = trainer2.load_checkpoint(path)
+    assert meta['iter'] == 2 and trainer2.iter == 2
+    sd1, sd2 = model.state_dict(), model2.state_dict()
+    assert all(torch.equal(sd1[k].cpu(), sd2[k].cpu()) for k in sd1)
+    assert torch.equal(trainer.store.M, trainer2.store.M)
+    # both continue identically (same data, same sampler seed)
+    torch.manual_seed(5)
+    a = trainer.train_step(data, read_logs=True)
+    torch.manual_seed(5)
+    b = trainer2.train_step(data, read_logs=True)
+    assert abs(a['loss'] - b['loss']) < 1e-3 * abs(a['loss'])
