@@ -14,6 +14,7 @@
 // offset_head_expand_feature.py:97-104).
 #include "common.cuh"
 #include "loft_b200.h"
+#include <stdlib.h>
 
 namespace {
 
@@ -135,6 +136,11 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor
+  // prefetch) overlaps the tail of the previous kernel in the stream; global memory is only
+  // touched after the previous grid has completed and flushed.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const bool is_wgrad = p.mode >= WGRAD_2D;
 
@@ -511,8 +517,26 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cu
   }
   if (p.num_tiles <= 0) return LOFT_OK;
   int grid = p.num_tiles < loft_num_sms() ? p.num_tiles : loft_num_sms();
-  loft_gemm_tf32_kernel<<<grid, kThreads, kSmemBytes, stream>>>(ta, tb, p);
-  LOFT_CUDA_LAUNCH_CHECK("loft_gemm_tf32_kernel");
+  static int use_pdl = -1;
+  if (use_pdl < 0) {
+    const char* e = getenv("LOFT_PDL");
+    use_pdl = (e == nullptr || e[0] != '0') ? 1 : 0;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, loft_gemm_tf32_kernel, ta, tb, p);
+  if (le != cudaSuccess) {
+    loft_set_error("loft_gemm_tf32_kernel: launch failed: %s", cudaGetErrorString(le));
+    return LOFT_ERR_CUDA;
+  }
   return LOFT_OK;
 }
 

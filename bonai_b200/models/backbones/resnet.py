@@ -77,13 +77,15 @@ class Bottleneck(nn.Module):
         return self.bn3
 
     def loft_prepare(self, store):
-        def spec(conv, bn, relu):
+        def spec(conv, bn, relu, **kw):
             return D.ConvSpec(conv.weight._loft, ksize=conv.kernel_size[0], stride=conv.stride[0],
                               padding=conv.padding[0], relu=relu, bn=bn._loft_bn,
-                              bn_trainable=bn.weight.requires_grad, store=store)
-        self._s1 = spec(self.conv1, self.bn1, True)
-        self._s2 = spec(self.conv2, self.bn2, True)
-        self._s3 = spec(self.conv3, self.bn3, True)      # ReLU after the residual add
+                              bn_trainable=bn.weight.requires_grad, store=store, **kw)
+        # conv1 -> conv2 -> conv3 is a single-consumer chain: each ReLU's backward mask is applied
+        # by the next conv's dgrad epilogue instead of a separate pass
+        self._s1 = spec(self.conv1, self.bn1, True, grad_premasked=True)
+        self._s2 = spec(self.conv2, self.bn2, True, premask_in=True, grad_premasked=True)
+        self._s3 = spec(self.conv3, self.bn3, True, premask_in=True)   # ReLU after the residual add
         self._sd = spec(self.downsample[0], self.downsample[1], False) \
             if self.downsample is not None else None
         self._trainable = self.conv1.weight.requires_grad

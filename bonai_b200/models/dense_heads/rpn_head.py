@@ -77,7 +77,8 @@ class RPNHead(nn.Module):
         dev = store.device
         c = self.rpn_conv
         self._conv_spec = D.ConvSpec(c.weight._loft, ksize=3, padding=1, relu=True, bias=c.bias,
-                                     bias_grad=c.bias._loft.grad, store=store)
+                                     bias_grad=c.bias._loft.grad, store=store,
+                                     grad_premasked=True)    # only consumer: the fused 1x1 head
         C = self.feat_channels
         A = self.num_anchors
         w = torch.zeros((_FUSED_W, C), device=dev)
@@ -104,7 +105,7 @@ class RPNHead(nn.Module):
 
         store.add_packed(Packed(w, b, gw, gb, build, scatter))
         self._head_spec = D.ConvSpec(WeightRef(w, gw), ksize=1, bias=b, bias_grad=gb,
-                                     round_out=False, store=store)
+                                     round_out=False, store=store, premask_in=True)
         self._base_anchors_dev = [ba.to(dev).contiguous()
                                   for ba in self.anchor_generator.base_anchors]
 

@@ -80,8 +80,9 @@ class OffsetHeadExpandFeature(nn.Module):
 
     def loft_prepare(self, store):
         self._conv_specs = [[D.ConvSpec(c.weight._loft, ksize=3, padding=1, relu=True, bias=c.bias,
-                                        bias_grad=c.bias._loft.grad, store=store) for c in convs]
-                            for convs in self.expand_convs]
+                                        bias_grad=c.bias._loft.grad, store=store,
+                                        premask_in=(i > 0), grad_premasked=True)
+                             for i, c in enumerate(convs)] for convs in self.expand_convs]
         # the same conv layer of all branches in one grouped launch (weights are equally strided
         # in the ParamStore's flat buffers)
         self._group_specs = None
@@ -94,7 +95,7 @@ class OffsetHeadExpandFeature(nn.Module):
                 gs.append(D.GroupedConvSpec([c.weight._loft for c in convs],
                                             [c.bias for c in convs],
                                             [c.bias._loft.grad for c in convs], relu=True,
-                                            store=store))
+                                            store=store, premask_in=(i > 0), grad_premasked=True))
             if all(g.uniform for g in gs):
                 self._group_specs = gs
         area = self.roi_feat_size[0] * self.roi_feat_size[1]
@@ -103,9 +104,12 @@ class OffsetHeadExpandFeature(nn.Module):
             wref = make_hwc_fc(store, fc, self.conv_out_channels, area) if i == 0 \
                 else fc.weight._loft
             self._fc_specs.append(D.ConvSpec(wref, relu=True, bias=fc.bias,
-                                             bias_grad=fc.bias._loft.grad, store=store))
+                                             bias_grad=fc.bias._loft.grad, store=store,
+                                             premask_in=(i > 0 or len(self.expand_convs[0]) > 0),
+                                             grad_premasked=True))
         wref, b, gb = make_fused_head(store, [self.fc_offset], 4)
-        self._head = D.ConvSpec(wref, bias=b, bias_grad=gb, round_out=False, store=store)
+        self._head = D.ConvSpec(wref, bias=b, bias_grad=gb, round_out=False, store=store,
+                                premask_in=len(self.fcs) > 0)
 
     def expand_feature(self, feature, operation_idx):
         if operation_idx >= 4:

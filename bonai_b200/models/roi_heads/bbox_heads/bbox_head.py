@@ -212,11 +212,13 @@ class ConvFCBBoxHead(BBoxHead):
             wref = make_hwc_fc(store, fc, self.in_channels, self.roi_feat_area) if i == 0 \
                 else fc.weight._loft
             self._specs.append(D.ConvSpec(wref, relu=True, bias=fc.bias,
-                                          bias_grad=fc.bias._loft.grad, store=store))
+                                          bias_grad=fc.bias._loft.grad, store=store,
+                                          premask_in=(i > 0), grad_premasked=True))
         n_out = self.fc_cls.weight.shape[0] + self.fc_reg.weight.shape[0]
         width = (n_out + 3) // 4 * 4
         wref, b, gb = make_fused_head(store, [self.fc_cls, self.fc_reg], width)
-        self._head = D.ConvSpec(wref, bias=b, bias_grad=gb, round_out=False, store=store)
+        self._head = D.ConvSpec(wref, bias=b, bias_grad=gb, round_out=False, store=store,
+                                premask_in=True)
 
     def forward(self, x):
         # x: [K, C, 7, 7] with NHWC storage -> [K, 7*7*C]

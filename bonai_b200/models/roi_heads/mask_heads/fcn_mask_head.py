@@ -63,11 +63,12 @@ class FCNMaskHead(nn.Module):
     def loft_prepare(self, store):
         dev = store.device
         self._conv_specs = []
-        for cm in self.convs:
+        for i, cm in enumerate(self.convs):
             c = cm.conv
             self._conv_specs.append(D.ConvSpec(c.weight._loft, ksize=3, padding=1, relu=True,
                                                bias=c.bias, bias_grad=c.bias._loft.grad,
-                                               store=store))
+                                               store=store, premask_in=(i > 0),
+                                               grad_premasked=True))
         up = self.upsample                       # weight [Cin, Co, 2, 2]
         Ci, Co = up.weight.shape[:2]
         w = torch.zeros((4 * Co, Ci), device=dev)
@@ -89,7 +90,8 @@ class FCNMaskHead(nn.Module):
 
         store.add_packed(Packed(w, b4, gw, None, build, scatter))
         self._up_spec = D.ConvSpec(WeightRef(w, gw), relu=True, bias=b4,
-                                   bias_grad=up.bias._loft.grad, store=store)
+                                   bias_grad=up.bias._loft.grad, store=store,
+                                   premask_in=len(self.convs) > 0, grad_premasked=True)
         lg = self.conv_logits
         n_out = lg.weight.shape[0]
         width = (n_out + 3) // 4 * 4
@@ -112,7 +114,7 @@ class FCNMaskHead(nn.Module):
 
         store.add_packed(Packed(lw, lb, lgw, lgb, build2, scatter2))
         self._logit_spec = D.ConvSpec(WeightRef(lw, lgw), ksize=1, bias=lb, bias_grad=lgb,
-                                      round_out=False, store=store)
+                                      round_out=False, store=store, premask_in=True)
         self._n_out = n_out
 
     def forward(self, x):

@@ -77,6 +77,10 @@ class StandardRoIHead(BaseRoIHead):
         num_imgs = len(img_metas)
         if gt_bboxes_ignore is None:
             gt_bboxes_ignore = [None for _ in range(num_imgs)]
+        from ...core.bbox import RandomSampler
+        if type(self.bbox_sampler) is RandomSampler and self.bbox_sampler.neg_pos_ub < 0:
+            return self._assign_and_sample_batched(proposal_list, gt_bboxes, gt_labels,
+                                                   gt_bboxes_ignore)
         sampling_results = []
         for i in range(num_imgs):
             assign_result = self.bbox_assigner.assign(proposal_list[i], gt_bboxes[i],
@@ -84,6 +88,56 @@ class StandardRoIHead(BaseRoIHead):
             sampling_results.append(self.bbox_sampler.sample(
                 assign_result, proposal_list[i], gt_bboxes[i], gt_labels[i]))
         return sampling_results
+
+    def _assign_and_sample_batched(self, proposal_list, gt_bboxes, gt_labels, gt_bboxes_ignore):
+        """Same result as assign + RandomSampler.sample per image (base_sampler.py:34-101), but
+        all images share ONE host synchronisation: the assignments are computed for every image
+        first, the positive / negative candidate lists come from a single `nonzero` over the
+        stacked flags, and `unique()` of an index subset is a device-side sort."""
+        from ...core.bbox import SamplingResult
+        sampler = self.bbox_sampler
+        n_img = len(proposal_list)
+        ars, boxes_l, flags_l = [], [], []
+        for i in range(n_img):
+            ar = self.bbox_assigner.assign(proposal_list[i], gt_bboxes[i], gt_bboxes_ignore[i],
+                                           gt_labels[i])
+            bboxes = proposal_list[i][:, :4]
+            gt_flags = bboxes.new_zeros((bboxes.shape[0],), dtype=torch.uint8)
+            if sampler.add_gt_as_proposals and len(gt_bboxes[i]) > 0:
+                bboxes = torch.cat([gt_bboxes[i], bboxes], dim=0)
+                ar.add_gt_(gt_labels[i])
+                gt_flags = torch.cat([bboxes.new_ones(gt_bboxes[i].shape[0], dtype=torch.uint8),
+                                      gt_flags])
+            ars.append(ar)
+            boxes_l.append(bboxes)
+            flags_l.append(gt_flags)
+        sizes = [ar.gt_inds.numel() for ar in ars]
+        allg = torch.cat([ar.gt_inds for ar in ars])
+        # code 0: positive, 1: negative candidates; one nonzero for everything
+        idx = torch.nonzero(torch.stack([allg > 0, allg == 0]), as_tuple=False)   # the only sync
+        kind, pos = idx[:, 0], idx[:, 1]
+        offs = [0]
+        for n in sizes:
+            offs.append(offs[-1] + n)
+        ends = torch.tensor(offs[1:], device=allg.device)
+        img_of = torch.bucketize(pos, ends, right=True)
+        key = (kind * n_img + img_of)
+        counts = torch.bincount(key, minlength=2 * n_img).tolist()                 # rides the same sync
+        chunks = torch.split(pos, counts)
+        results = []
+        num_expected_pos = int(sampler.num * sampler.pos_fraction)
+        for i in range(n_img):
+            off = offs[i]
+            pos_inds = chunks[i] - off
+            neg_inds = chunks[n_img + i] - off
+            if pos_inds.numel() > num_expected_pos:
+                pos_inds = sampler.random_choice(pos_inds, num_expected_pos).sort()[0]
+            num_expected_neg = sampler.num - pos_inds.numel()
+            if neg_inds.numel() > num_expected_neg:
+                neg_inds = sampler.random_choice(neg_inds, num_expected_neg).sort()[0]
+            results.append(SamplingResult(pos_inds, neg_inds, boxes_l[i], gt_bboxes[i], ars[i],
+                                          flags_l[i]))
+        return results
 
     def forward_train(self, x, img_metas, proposal_list, gt_bboxes, gt_labels,
                       gt_bboxes_ignore=None, gt_masks=None):

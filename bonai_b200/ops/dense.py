@@ -41,7 +41,7 @@ class ConvSpec:
 
     def __init__(self, wref, ksize=1, stride=1, padding=0, relu=False, bias=None, bias_grad=None,
                  bn=None, bn_trainable=False, round_out=True, res_upsample=False, store=None,
-                 cout=None, kpad=None):
+                 cout=None, kpad=None, premask_in=False, grad_premasked=False):
         self.wref = wref
         self.ksize, self.stride, self.padding = ksize, stride, padding
         self.relu = relu
@@ -52,6 +52,11 @@ class ConvSpec:
         self.store = store
         self.cout = cout
         self.kpad = kpad
+        # ReLU-backward fusion along single-consumer chains: a layer with premask_in applies the
+        # ReLU mask of its INPUT (x > 0) in its dgrad epilogue, so the producer of x (which sets
+        # grad_premasked) receives an already-masked gradient and skips its own masking pass.
+        self.premask_in = premask_in
+        self.grad_premasked = grad_premasked
 
 
 def _fprop(spec, x, residual):
@@ -114,13 +119,16 @@ class _ConvFn(Function):
         ctx.x_shape = tuple(x.shape)
         ctx.has_res = residual is not None
         ctx.res_shape = tuple(residual.shape) if residual is not None else None
-        ctx.save_for_backward(saved, y if spec.relu else None, z)
+        relu_eff = spec.relu and not spec.grad_premasked
+        xin = nhwc(x) if spec.premask_in else None
+        ctx.save_for_backward(saved, y if relu_eff else None, z, xin)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         spec = ctx.spec
-        saved, y, z = ctx.saved_tensors
+        saved, y, z, xin = ctx.saved_tensors
+        relu_eff = spec.relu and not spec.grad_premasked
         _queue_finalize(spec.store)
         st = L.stream()
         N, Cin, H, W = ctx.x_shape
@@ -134,16 +142,17 @@ class _ConvFn(Function):
         dres = None
         dgamma = bn.dgamma if (bn is not None and spec.bn_trainable) else None
         dbeta = bn.dbeta if (bn is not None and spec.bn_trainable) else spec.bias_grad
-        if not spec.relu and bn is None:
-            # plain conv + bias: dz == dy, only the bias gradient needs a (read-only) pass.  dy is
-            # fed to the tensor cores as is; unrounded operands only bias *gradients* by ~5e-4.
+        if not relu_eff and bn is None:
+            # plain conv + bias (or ReLU already applied by the consumer's dgrad epilogue):
+            # dz == dy, only the bias gradient needs a (read-only) pass.  dy is fed to the tensor
+            # cores as is; unrounded operands only bias *gradients* by ~5e-4.
             dz = dyn
             if dbeta is not None:
                 L.call('act_bwd', L.ptr(dyn), None, None, None, None, None, None, None, None,
                        L.ptr(dbeta), L.ll(P), i32(Cout), i32(0), st)
         else:
             dz = torch.empty_like(dyn)
-            if need_res and spec.relu and not spec.res_upsample:
+            if need_res and relu_eff and not spec.res_upsample:
                 dres = torch.empty_like(dyn)
             L.call('act_bwd', L.ptr(dyn), L.ptr(nhwc(y)) if y is not None else None,
                    L.ptr(z) if dgamma is not None else None,
@@ -153,18 +162,18 @@ class _ConvFn(Function):
                    L.ptr(dz), L.ptr(dres) if dres is not None else None,
                    L.ptr(dgamma) if dgamma is not None else None,
                    L.ptr(dbeta) if dbeta is not None else None, L.ll(P), i32(Cout),
-                   i32(spec.relu), st)
+                   i32(relu_eff), st)
         grad_res = None
         if need_res:
             if spec.res_upsample:
                 # residual was nearest-upsampled x2: its gradient is the 2x2 sum of g
-                g = dz if not spec.relu else dres
+                g = dz if not relu_eff else dres
                 rn, rc, rh, rw = ctx.res_shape
                 out = torch.empty((rn, rh, rw, rc), device=dev, dtype=torch.float32)
                 L.call('sum2x2_add', L.ptr(g), None, L.ptr(out), i32(rn), i32(rh), i32(rw), i32(rc),
                        st)
                 grad_res = out.permute(0, 3, 1, 2)
-            elif spec.relu:
+            elif relu_eff:
                 grad_res = dres.permute(0, 3, 1, 2)
             else:
                 grad_res = dy
@@ -186,7 +195,7 @@ class _ConvFn(Function):
         # 3. data gradient
         dx = None
         if ctx.needs_input_grad[0]:
-            e = L.make_epilogue(round_out=True)
+            e = L.make_epilogue(round_out=True, mask=xin if (xin is not None and s == 1) else None)
             if conv3:
                 dx = new_nhwc(N, Cin, H, W, dev)
                 L.call('conv3x3_dgrad', L.ptr(dz), L.ptr(w), L.ptr(dx.permute(0, 2, 3, 1)), i32(N),
@@ -197,8 +206,8 @@ class _ConvFn(Function):
                        L.ll(Cout), L.ll(Cin), L.ll(Cin), ctypes.byref(e), st)
                 if s == 2:
                     dx = new_nhwc(N, Cin, H, W, dev)
-                    L.call('subsample2_bwd', L.ptr(dxs), L.ptr(dx.permute(0, 2, 3, 1)), None, i32(N),
-                           i32(H), i32(W), i32(Cin), st)
+                    L.call('subsample2_bwd', L.ptr(dxs), L.ptr(dx.permute(0, 2, 3, 1)), L.ptr(xin),
+                           i32(N), i32(H), i32(W), i32(Cin), st)
                 else:
                     dx = dxs.permute(0, 3, 1, 2)
             else:
@@ -207,8 +216,8 @@ class _ConvFn(Function):
                 L.call('gemm_dgrad', L.ptr(dz), L.ptr(w), L.ptr(dcol), L.ll(P), i32(K), i32(Cout),
                        L.ll(Cout), L.ll(K), L.ll(K), None, st)
                 dx = new_nhwc(N, Cin, H, W, dev)
-                L.call('col2im', L.ptr(dcol), L.ptr(dx.permute(0, 2, 3, 1)), None, i32(N), i32(H),
-                       i32(W), i32(Cin), i32(k), i32(k), i32(s), i32(pad), i32(K), st)
+                L.call('col2im', L.ptr(dcol), L.ptr(dx.permute(0, 2, 3, 1)), L.ptr(xin), i32(N),
+                       i32(H), i32(W), i32(Cin), i32(k), i32(k), i32(s), i32(pad), i32(K), st)
         return (dx, grad_res, None) + (None,) * (len(ctx.needs_input_grad) - 3)
 
 
@@ -244,7 +253,7 @@ class _LinearFn(Function):
         L.call('gemm_fprop', L.ptr(x), L.ptr(w), L.ptr(y), L.ll(P), i32(K), i32(Cout), L.ll(K),
                L.ll(K), L.ll(Cout), i32(1), i32(P), ctypes.byref(e), L.stream())
         ctx.spec = spec
-        ctx.save_for_backward(x, y if spec.relu else None)
+        ctx.save_for_backward(x, y if (spec.relu and not spec.grad_premasked) else None)
         return y
 
     @staticmethod
@@ -257,7 +266,7 @@ class _LinearFn(Function):
         w = spec.wref.w
         Cout = w.shape[0]
         dy = dy.contiguous()
-        if not spec.relu:
+        if not (spec.relu and not spec.grad_premasked):
             dz = dy
             if spec.bias_grad is not None:
                 L.call('act_bwd', L.ptr(dy), None, None, None, None, None, None, None, None,
@@ -279,7 +288,7 @@ class _LinearFn(Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty((P, K), device=dy.device, dtype=torch.float32)
-            e = L.make_epilogue(round_out=True)
+            e = L.make_epilogue(round_out=True, mask=x if spec.premask_in else None)
             L.call('gemm_dgrad', L.ptr(dz), L.ptr(w), L.ptr(dx), L.ll(P), i32(K), i32(Cout),
                    L.ll(Cout), L.ll(K), L.ll(K), ctypes.byref(e), st)
         return (dx, None) + (None,) * (len(ctx.needs_input_grad) - 2)
@@ -324,7 +333,7 @@ class _Deconv2x2Fn(Function):
                i32(Cin), i32(4 * Co), L.ll(Cin), L.ll(Cin), L.ll(Co), i32(H), i32(W),
                ctypes.byref(e), L.stream())
         ctx.spec = spec
-        ctx.save_for_backward(xn, y if spec.relu else None)
+        ctx.save_for_backward(xn, y if (spec.relu and not spec.grad_premasked) else None)
         return y
 
     @staticmethod
@@ -337,11 +346,16 @@ class _Deconv2x2Fn(Function):
         w = spec.wref.w
         Co = w.shape[0] // 4
         dyn = nhwc(dy)
-        dz = torch.empty_like(dyn)
-        L.call('act_bwd', L.ptr(dyn), L.ptr(nhwc(y)) if y is not None else None, None, None, None,
-               None, L.ptr(dz), None, None,
-               L.ptr(spec.bias_grad) if spec.bias_grad is not None else None, L.ll(N * 4 * H * W),
-               i32(Co), i32(spec.relu), st)
+        if y is None:
+            dz = dyn
+            if spec.bias_grad is not None:
+                L.call('act_bwd', L.ptr(dyn), None, None, None, None, None, None, None, None,
+                       L.ptr(spec.bias_grad), L.ll(N * 4 * H * W), i32(Co), i32(0), st)
+        else:
+            dz = torch.empty_like(dyn)
+            L.call('act_bwd', L.ptr(dyn), L.ptr(nhwc(y)), None, None, None, None, L.ptr(dz), None,
+                   None, L.ptr(spec.bias_grad) if spec.bias_grad is not None else None,
+                   L.ll(N * 4 * H * W), i32(Co), i32(1), st)
         # space-to-depth: dz[n,2h+i,2w+j,co] -> dzp[(n,h,w), (i,j,co)]
         dzp = dz.view(N, H, 2, W, 2, Co).permute(0, 1, 3, 2, 4, 5).contiguous().view(N * H * W,
                                                                                      4 * Co)
@@ -352,7 +366,7 @@ class _Deconv2x2Fn(Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = new_nhwc(N, Cin, H, W, dy.device)
-            e = L.make_epilogue(round_out=True)
+            e = L.make_epilogue(round_out=True, mask=xn if spec.premask_in else None)
             L.call('gemm_dgrad', L.ptr(dzp), L.ptr(w), L.ptr(dx.permute(0, 2, 3, 1)), L.ll(P),
                    i32(Cin), i32(4 * Co), L.ll(4 * Co), L.ll(Cin), L.ll(Cin), ctypes.byref(e), st)
         return (dx, None) + (None,) * (len(ctx.needs_input_grad) - 2)
@@ -371,7 +385,9 @@ class GroupedConvSpec:
     images in ONE launch.  The per-group weights / biases / gradients must be equally strided in
     memory (true for the FOA branches in the ParamStore's flat buffers)."""
 
-    def __init__(self, wrefs, biases, bias_grads, relu=True, store=None):
+    def __init__(self, wrefs, biases, bias_grads, relu=True, store=None, premask_in=False,
+                 grad_premasked=False):
+        self.premask_in, self.grad_premasked = premask_in, grad_premasked
         self.G = len(wrefs)
         self.w0 = wrefs[0].w
         self.gw0 = wrefs[0].grad
@@ -418,21 +434,28 @@ class _GroupedConv3x3Fn(Function):
         Cout, G = spec.cout, spec.G
         dyn = nhwc(dy)
         yn = nhwc(y)
-        dz = torch.empty_like(dyn)
+        relu_eff = spec.relu and not spec.grad_premasked
+        dz = torch.empty_like(dyn) if relu_eff else dyn
         rows_g = (N // G) * H * W
         for g in range(G):
             o = g * rows_g * Cout * 4
-            L.call('act_bwd', ctypes.c_void_p(dyn.data_ptr() + o), ctypes.c_void_p(yn.data_ptr() + o),
-                   None, None, None, None, ctypes.c_void_p(dz.data_ptr() + o), None, None,
-                   L.ptr(spec.bias_grads[g]) if spec.bias_grads[g] is not None else None,
-                   L.ll(rows_g), i32(Cout), i32(spec.relu), st)
+            if relu_eff:
+                L.call('act_bwd', ctypes.c_void_p(dyn.data_ptr() + o),
+                       ctypes.c_void_p(yn.data_ptr() + o), None, None, None, None,
+                       ctypes.c_void_p(dz.data_ptr() + o), None, None,
+                       L.ptr(spec.bias_grads[g]) if spec.bias_grads[g] is not None else None,
+                       L.ll(rows_g), i32(Cout), i32(1), st)
+            elif spec.bias_grads[g] is not None:
+                L.call('act_bwd', ctypes.c_void_p(dyn.data_ptr() + o), None, None, None, None, None,
+                       None, None, None, L.ptr(spec.bias_grads[g]), L.ll(rows_g), i32(Cout), i32(0),
+                       st)
         if spec.gw0 is not None:
             L.call('conv3x3_wgrad_grouped', L.ptr(dz), L.ptr(xn), L.ptr(spec.gw0), i32(N), i32(H),
                    i32(W), i32(Cin), i32(Cout), i32(G), L.ll(spec.gw_gstride), st)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = new_nhwc(N, Cin, H, W, dy.device)
-            e = L.make_epilogue(round_out=True)
+            e = L.make_epilogue(round_out=True, mask=xn if spec.premask_in else None)
             L.call('conv3x3_dgrad_grouped', L.ptr(dz), L.ptr(spec.w0), L.ptr(dx.permute(0, 2, 3, 1)),
                    i32(N), i32(H), i32(W), i32(Cin), i32(Cout), i32(G), L.ll(spec.w_gstride),
                    ctypes.byref(e), st)
