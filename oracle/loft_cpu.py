@@ -683,28 +683,33 @@ def trainable_keys(p):
 
 def make_inputs(seed, n_img, size, num_gt, device='cpu'):
     """Synthetic tile batch of SURVEY.md section 8(d): randn image, G boxes with log-uniform sides,
-    inscribed-ellipse roof masks, U(-40,40) offsets."""
+    inscribed-ellipse roof masks, U(-40,40) offsets.  `size` is an int (square) or (H, W);
+    `num_gt` an int or one count per image (ragged batches)."""
+    H, W = (size, size) if isinstance(size, int) else size
+    counts = [num_gt] * n_img if isinstance(num_gt, int) else list(num_gt)
     g = torch.Generator().manual_seed(seed)
-    img = torch.randn(n_img, 3, size, size, generator=g)
+    img = torch.randn(n_img, 3, H, W, generator=g)
     gt_bboxes, gt_labels, gt_masks, gt_offsets = [], [], [], []
-    smin, smax = 16.0, min(160.0, size / 2.0)
-    yy, xx = torch.meshgrid(torch.arange(size, dtype=torch.float32),
-                            torch.arange(size, dtype=torch.float32), indexing='ij')
-    for _ in range(n_img):
-        cxy = torch.rand(num_gt, 2, generator=g) * size
-        wh = torch.exp(torch.rand(num_gt, 2, generator=g) * math.log(smax / smin)) * smin
-        b = torch.cat([cxy - wh / 2, cxy + wh / 2], dim=1).clamp(0, size)
+    lim = torch.tensor([W, H, W, H], dtype=torch.float32)
+    smin, smax = 16.0, min(160.0, min(H, W) / 2.0)
+    yy, xx = torch.meshgrid(torch.arange(H, dtype=torch.float32),
+                            torch.arange(W, dtype=torch.float32), indexing='ij')
+    for i in range(n_img):
+        n = counts[i]
+        cxy = torch.rand(n, 2, generator=g) * lim[:2]
+        wh = torch.exp(torch.rand(n, 2, generator=g) * math.log(smax / smin)) * smin
+        b = torch.min(torch.cat([cxy - wh / 2, cxy + wh / 2], dim=1).clamp(min=0), lim)
         small = (b[:, 2:] - b[:, :2]) < 2
-        b[:, 2:] = torch.where(small, (b[:, :2] + 2).clamp(max=size), b[:, 2:])
+        b[:, 2:] = torch.where(small, torch.min(b[:, :2] + 2, lim[2:]), b[:, 2:])
         b[:, :2] = torch.min(b[:, :2], b[:, 2:] - 2)
         gt_bboxes.append(b)
-        gt_labels.append(torch.zeros(num_gt, dtype=torch.long))
+        gt_labels.append(torch.zeros(n, dtype=torch.long))
         cx, cy = (b[:, 0] + b[:, 2]) / 2, (b[:, 1] + b[:, 3]) / 2
         rx, ry = (b[:, 2] - b[:, 0]) / 2, (b[:, 3] - b[:, 1]) / 2
         m = (((xx[None] + 0.5 - cx[:, None, None]) / rx[:, None, None]) ** 2 +
              ((yy[None] + 0.5 - cy[:, None, None]) / ry[:, None, None]) ** 2) <= 1.0
         gt_masks.append(m.to(torch.uint8))
-        gt_offsets.append(torch.rand(num_gt, 2, generator=g) * 80 - 40)
+        gt_offsets.append(torch.rand(n, 2, generator=g) * 80 - 40)
     return img, gt_bboxes, gt_labels, gt_masks, gt_offsets
 
 

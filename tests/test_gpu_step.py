@@ -258,3 +258,23 @@ def test_checkpoint_roundtrip(tmp_path):
     torch.manual_seed(5)
     b = trainer2.train_step(data, read_logs=True)
     assert abs(a['loss'] - b['loss']) < 1e-3 * abs(a['loss'])
+
+
+def test_step_parity_non_square_ragged_batch():
+    """320x416 tiles (odd pyramid sizes 13 -> 7 at the coarse levels, partial TMA tiles) and a
+    different number of GT boxes per image."""
+    import e2e_check
+    rep = e2e_check.run(size=(320, 416), n_img=2, num_gt=[9, 3], seed=2, verbose=False)
+    assert rep['worst_loss_rel'] < LOSS_TOL, rep['losses']
+    assert 'missing' not in rep['grads'].values()
+
+
+def test_too_many_gt_is_a_loud_error():
+    from bonai_b200._lib import LoftError
+    from bonai_b200.core import MaxIoUAssigner
+    boxes = torch.rand(100, 4, device='cuda') * 50
+    boxes[:, 2:] += boxes[:, :2] + 1
+    gts = torch.rand(1500, 4, device='cuda') * 50
+    gts[:, 2:] += gts[:, :2] + 1
+    with pytest.raises(LoftError):
+        MaxIoUAssigner(0.5, 0.5).assign(boxes, gts)

@@ -22,6 +22,7 @@ CFG = os.path.join(ROOT, 'configs', 'loft', 'loft_foa_r50_fpn_2x_b200.py')
 def run(size=256, n_img=1, num_gt=10, seed=0, force_proposals=True, verbose=True, diag=False):
     p = O.randomize_bn(O.init_params(seed), seed)
     img, gb, gl, gm, go = O.make_inputs(seed, n_img, size, num_gt)
+    H, W = (size, size) if isinstance(size, int) else size
     tk = set(O.trainable_keys(p))
     po = {k: (v.clone().requires_grad_(True) if k in tk else v) for k, v in p.items()}
     torch.manual_seed(123)
@@ -39,7 +40,7 @@ def run(size=256, n_img=1, num_gt=10, seed=0, force_proposals=True, verbose=True
     dev = torch.device('cuda:0')
     RandomSampler.forced_choices = [r.clone() for r in rec]
     RPNHead.forced_proposals = [q.clone() for q in aux['proposals']] if force_proposals else None
-    metas = [dict(img_shape=(size, size, 3), pad_shape=(size, size, 3), ori_shape=(size, size, 3),
+    metas = [dict(img_shape=(H, W, 3), pad_shape=(H, W, 3), ori_shape=(H, W, 3),
                   scale_factor=1.0, flip=False) for _ in range(n_img)]
     caps = {}
     if diag:
@@ -54,7 +55,7 @@ def run(size=256, n_img=1, num_gt=10, seed=0, force_proposals=True, verbose=True
         model.roi_head.offset_head.register_forward_hook(cap('offset_pred'))
         model.roi_head.bbox_head.register_forward_hook(cap('bbox_out'))
     losses = model.forward_train(img.to(dev), metas, gb, gl,
-                                 gt_masks=[BitmapMasks(m, size, size) for m in gm], gt_offsets=go)
+                                 gt_masks=[BitmapMasks(m, H, W) for m in gm], gt_offsets=go)
     loss, logs = model._parse_losses(losses)
     loss.backward()
     torch.cuda.synchronize()
@@ -83,7 +84,7 @@ def run(size=256, n_img=1, num_gt=10, seed=0, force_proposals=True, verbose=True
         sr = model.roi_head._last_sampling_results
         from bonai_b200.core import mask_target as MT
         print('mask targets equal:', bool(torch.equal(
-            model.roi_head.mask_head.get_targets(sr, [BitmapMasks(m, size, size) for m in gm],
+            model.roi_head.mask_head.get_targets(sr, [BitmapMasks(m, H, W) for m in gm],
                                                  model.roi_head.train_cfg).cpu(), mt)))
     worst = 0.0
     for k, v in logs_o.items():
