@@ -190,11 +190,10 @@ class ParamStore:
         self.refresh_weights()
         self.G.zero_()
         self.sqnorm.zero_()
-        for pk in self.packed:
-            if pk.gw is not None:
-                pk.gw.zero_()
-            if pk.gb is not None:
-                pk.gb.zero_()
+        if not hasattr(self, '_packed_grads'):
+            self._packed_grads = [t for pk in self.packed for t in (pk.gw, pk.gb) if t is not None]
+        if self._packed_grads:
+            torch._foreach_zero_(self._packed_grads)
         self._callback_queued = False
 
     def queue_finalize(self):
