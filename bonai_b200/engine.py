@@ -153,6 +153,13 @@ class ParamStore:
         self._seen_version = None
         self._frozen_ready = False
         self._callback_queued = False
+        # optional (LOFT_WSTREAM=1): weight-gradient kernels of small layers on a side stream so
+        # they overlap the data-gradient chain.  Measured on B200: 23.97 ms/step with vs 23.56
+        # without -- the 200 KB-smem GEMM CTAs cannot co-reside, so it stays off by default.
+        import os
+        self.wstream = torch.cuda.Stream(device=dev) if os.environ.get('LOFT_WSTREAM', '0') != '0' \
+            else None
+        self._w_pending = False
         model._loft_store = self
 
     # ------------------------------------------------------------------ packed weights
@@ -203,7 +210,26 @@ class ParamStore:
         self._callback_queued = True
         torch.autograd.Variable._execution_engine.queue_callback(self.finalize_grads)
 
+    def side_stream_for_wgrad(self, *tensors):
+        """Returns the side stream (after making it wait for the current stream and registering
+        the operand tensors with it) or None when disabled."""
+        ws = self.wstream
+        if ws is None:
+            return None
+        ws.wait_stream(torch.cuda.current_stream(self.device))
+        for t in tensors:
+            if t is not None:
+                t.record_stream(ws)
+        self._w_pending = True
+        return ws
+
+    def join_wgrad_stream(self):
+        if self._w_pending and self.wstream is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self.wstream)
+            self._w_pending = False
+
     def finalize_grads(self):
+        self.join_wgrad_stream()
         for pk in self.packed:
             pk.scatter()
         for p, g in self._grad_views:

@@ -163,8 +163,10 @@ class FCNMaskHead(nn.Module):
         if rescale:
             img_h, img_w = ori_shape[:2]
         else:
-            img_h = np.round(ori_shape[0] * scale_factor).astype(np.int32)
-            img_w = np.round(ori_shape[1] * scale_factor).astype(np.int32)
+            # plain ints: numpy >= 2 keeps `N * np.int32 * np.int32` in int32, which overflows for
+            # N >= 512 detections at 1024^2 (the reference ran on numpy 1.x value-based casting)
+            img_h = int(np.round(ori_shape[0] * scale_factor))
+            img_w = int(np.round(ori_shape[1] * scale_factor))
             scale_factor = 1.0
         if not isinstance(scale_factor, (float, torch.Tensor)):
             scale_factor = bboxes.new_tensor(scale_factor)

@@ -36,6 +36,27 @@ def _queue_finalize(store):
         store.queue_finalize()
 
 
+class _maybe_side_stream:
+    """Context: run the enclosed wgrad launch on the store's side stream when the launch is too
+    small to fill the GPU (work items < SM count), else stay on the current stream."""
+
+    def __init__(self, store, small, *tensors):
+        self.ws = None
+        if small and store is not None and hasattr(store, 'side_stream_for_wgrad'):
+            self.ws = store.side_stream_for_wgrad(*tensors)
+        self.ctx = torch.cuda.stream(self.ws) if self.ws is not None else None
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
+        return False
+
+
 class ConvSpec:
     """Static description of one conv / linear layer instance (weights + fused epilogue)."""
 
@@ -183,15 +204,19 @@ class _ConvFn(Function):
         gw = spec.wref.grad
         conv3 = (k == 3 and s == 1 and pad == 1)
         if gw is not None:
-            if conv3:
-                L.call('conv3x3_wgrad', L.ptr(dz), L.ptr(saved), L.ptr(gw), i32(N), i32(H), i32(W),
-                       i32(Cin), i32(Cout), st)
-            elif Cout % 32 != 0:
-                _narrow_wgrad(dz.view(P, Cout), saved.view(P, -1), gw, st)
-            else:
-                K = saved.shape[-1]
-                L.call('gemm_wgrad', L.ptr(dz), L.ptr(saved), L.ptr(gw), L.ll(P), i32(K), i32(Cout),
-                       L.ll(Cout), L.ll(K), L.ll(K), st)
+            # small layers: overlap the weight gradient with the data-gradient chain
+            small = P <= 16384 and ctx.needs_input_grad[0]
+            with _maybe_side_stream(spec.store, small, dz, saved):
+                st2 = L.stream()
+                if conv3:
+                    L.call('conv3x3_wgrad', L.ptr(dz), L.ptr(saved), L.ptr(gw), i32(N), i32(H),
+                           i32(W), i32(Cin), i32(Cout), st2)
+                elif Cout % 32 != 0:
+                    _narrow_wgrad(dz.view(P, Cout), saved.view(P, -1), gw, st2)
+                else:
+                    K = saved.shape[-1]
+                    L.call('gemm_wgrad', L.ptr(dz), L.ptr(saved), L.ptr(gw), L.ll(P), i32(K),
+                           i32(Cout), L.ll(Cout), L.ll(K), L.ll(K), st2)
         # 3. data gradient
         dx = None
         if ctx.needs_input_grad[0]:
@@ -278,8 +303,9 @@ class _LinearFn(Function):
                    i32(Cout), i32(spec.relu), st)
         if spec.wref.grad is not None:
             if Cout % 32 == 0:
-                L.call('gemm_wgrad', L.ptr(dz), L.ptr(x), L.ptr(spec.wref.grad), L.ll(P), i32(K),
-                       i32(Cout), L.ll(Cout), L.ll(K), L.ll(K), st)
+                with _maybe_side_stream(spec.store, ctx.needs_input_grad[0], dz, x):
+                    L.call('gemm_wgrad', L.ptr(dz), L.ptr(x), L.ptr(spec.wref.grad), L.ll(P), i32(K),
+                           i32(Cout), L.ll(Cout), L.ll(K), L.ll(K), L.stream())
             else:
                 # narrow heads (Cout < 32): dW^T[K, Cout] = x^T dz via the same kernel with the
                 # roles swapped would need Cout%32==0 as well; use the transposed problem
@@ -450,8 +476,10 @@ class _GroupedConv3x3Fn(Function):
                        None, None, None, L.ptr(spec.bias_grads[g]), L.ll(rows_g), i32(Cout), i32(0),
                        st)
         if spec.gw0 is not None:
-            L.call('conv3x3_wgrad_grouped', L.ptr(dz), L.ptr(xn), L.ptr(spec.gw0), i32(N), i32(H),
-                   i32(W), i32(Cin), i32(Cout), i32(G), L.ll(spec.gw_gstride), st)
+            with _maybe_side_stream(spec.store, ctx.needs_input_grad[0], dz, xn):
+                L.call('conv3x3_wgrad_grouped', L.ptr(dz), L.ptr(xn), L.ptr(spec.gw0), i32(N),
+                       i32(H), i32(W), i32(Cin), i32(Cout), i32(G), L.ll(spec.gw_gstride),
+                       L.stream())
         dx = None
         if ctx.needs_input_grad[0]:
             dx = new_nhwc(N, Cin, H, W, dy.device)
