@@ -193,6 +193,8 @@ class Trainer:
         self.iter += 1
         packed = torch.stack([v.detach().reshape(()) for v in log_vars.values()])
         self._last_logs = (list(log_vars.keys()), packed)
+        if read_logs == 'async':
+            return self.read_logs_async()
         if read_logs:
             return self.read_logs()
         return packed
@@ -219,6 +221,33 @@ class Trainer:
             self.iter = ck.get('meta', {}).get('iter', 0)
             self.epoch = ck.get('meta', {}).get('epoch', 0)
         return ck.get('meta', {})
+
+    def read_logs_async(self):
+        """Non-blocking variant: enqueue the device->host copy of THIS step's packed log vector
+        into pinned memory and return the PREVIOUS step's values (None on the first call).  The
+        launch thread never waits for the GPU; `flush_logs()` returns the last step's values."""
+        keys, packed = self._last_logs
+        if self.distributed:
+            packed = packed / self.world
+            dist.all_reduce(packed)
+        prev = self.flush_logs() if getattr(self, '_pending', None) is not None else None
+        if not hasattr(self, '_pin'):
+            self._pin = [torch.empty(packed.numel(), dtype=torch.float32).pin_memory()
+                         for _ in range(2)]
+            self._pin_i = 0
+        buf = self._pin[self._pin_i]
+        self._pin_i ^= 1
+        buf.copy_(packed, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._pending = (keys, buf, ev)
+        return prev
+
+    def flush_logs(self):
+        keys, buf, ev = self._pending
+        ev.synchronize()
+        self._pending = None
+        return OrderedDict(zip(keys, buf.tolist()))
 
     def read_logs(self):
         """Packed mean over ranks + one host read-back (replaces the 8 all_reduce + .item() pairs
