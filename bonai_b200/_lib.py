@@ -32,6 +32,9 @@ class Epilogue(ctypes.Structure):
         ('relu', ctypes.c_int),
         ('deconv_shuffle', ctypes.c_int),
         ('round_out', ctypes.c_int),
+        ('colsum', ctypes.c_void_p),
+        ('colsum2', ctypes.c_void_p),
+        ('colsum_gstride', ctypes.c_longlong),
     ]
 
 
@@ -71,9 +74,30 @@ LAUNCHES = [0]          # kernels launched through this binding (bench.py reads 
 _KERNELS_PER_CALL = {'iou_assign': 2, 'grad_sqnorm': 1}
 
 
+TRACE = None            # set to a list to record (name, int args, start event, end event) per call
+
+
+def _arg_summary(args):
+    out = []
+    for a in args:
+        if isinstance(a, (ctypes.c_int, ctypes.c_longlong)):
+            out.append(int(a.value))
+    return tuple(out)
+
+
 def call(name, *args):
     """Call ``loft_<name>`` and raise LoftError on a non-zero return code."""
     fn = getattr(lib(), 'loft_' + name)
+    if TRACE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        TRACE.append((name, _arg_summary(args), e0, e1))
+        if rc != 0:
+            msg = lib().loft_last_error()
+            raise LoftError(f'loft_{name} failed ({rc}): {msg.decode() if msg else ""}')
+        return
     if name == 'nms_sorted':
         LAUNCHES[0] += 3 * int(args[2].value) + 1      # per image: fill+max+mask; one scan
     else:
@@ -85,7 +109,8 @@ def call(name, *args):
 
 
 def make_epilogue(raw_out=None, scale=None, shift=None, residual=None, mask=None, ldr=0,
-                  res_upsample2x=False, relu=False, deconv_shuffle=False, round_out=False):
+                  res_upsample2x=False, relu=False, deconv_shuffle=False, round_out=False,
+                  colsum=None, colsum2=None, colsum_gstride=0):
     e = Epilogue()
     e.raw_out = raw_out.data_ptr() if raw_out is not None else None
     e.scale = scale.data_ptr() if scale is not None else None
@@ -93,8 +118,11 @@ def make_epilogue(raw_out=None, scale=None, shift=None, residual=None, mask=None
     e.residual = residual.data_ptr() if residual is not None else None
     e.mask = mask.data_ptr() if mask is not None else None
     e.ldr = int(ldr)
-    e.res_upsample2x = int(bool(res_upsample2x))
+    e.res_upsample2x = int(res_upsample2x)        # 0 none, 1 nearest x2, 2 zero-stuffed x2
     e.relu = int(bool(relu))
     e.deconv_shuffle = int(bool(deconv_shuffle))
     e.round_out = int(bool(round_out))
+    e.colsum = colsum.data_ptr() if colsum is not None else None
+    e.colsum2 = colsum2.data_ptr() if colsum2 is not None else None
+    e.colsum_gstride = int(colsum_gstride)
     return e

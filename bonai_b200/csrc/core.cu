@@ -26,5 +26,5 @@ int loft_num_sms() {
 
 extern "C" {
 const char* loft_last_error(void) { return g_err; }
-int loft_abi_version(void) { return 1; }
+int loft_abi_version(void) { return 2; }
 }

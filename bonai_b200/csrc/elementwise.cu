@@ -79,6 +79,74 @@ __global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __r
   if (rstd) rstd[c] = r;
 }
 
+// ---------------------------------------------------------------- BN folded into conv weights
+// Eval-mode BN after a conv is y = s_c * (W_c . x) + shift_c with s_c = gamma_c * rstd_c.  The
+// tensor cores read W'_c = tf32(s_c * W_c), so the forward epilogue is shift-only, the data
+// gradient needs no per-channel scaling pass, and the weight-gradient kernels produce dW'.
+// One block per weight row (= output channel); rows are described by a table built once.
+__global__ void __launch_bounds__(128)
+bn_fold_weights_kernel(const float* __restrict__ P, float* __restrict__ T,
+                       const long long* __restrict__ row_off, const int* __restrict__ row_k,
+                       const int* __restrict__ row_ch, const float* __restrict__ scale) {
+  const long long r = blockIdx.x;
+  const long long off = row_off[r];
+  const int K = row_k[r];
+  const float s = scale[row_ch[r]];
+  if (((off | K) & 3) == 0) {
+    const float4* src = reinterpret_cast<const float4*>(P + off);
+    float4* dst = reinterpret_cast<float4*>(T + off);
+    for (int i = threadIdx.x; i < (K >> 2); i += blockDim.x) {
+      float4 v = src[i];
+      dst[i] = make_float4(tf32_rna(v.x * s), tf32_rna(v.y * s), tf32_rna(v.z * s),
+                           tf32_rna(v.w * s));
+    }
+  } else {
+    for (int i = threadIdx.x; i < K; i += blockDim.x) T[off + i] = tf32_rna(P[off + i] * s);
+  }
+}
+
+// After backward: G rows hold dW'.  dgamma_c += rstd_c * (W_c . dW'_c - mean_c * dbeta_c)
+// (dL/dgamma through W' = gamma*rstd*W and shift = beta - mean*gamma*rstd), then
+// dW_c = s_c * dW'_c in place.  Replaces the sum over pixels of dy * x_hat that
+// torch.nn.BatchNorm2d's backward computes from the saved conv output (resnet.py:260-300).
+__global__ void __launch_bounds__(128)
+bn_finalize_kernel(const float* __restrict__ P, float* __restrict__ G,
+                   const long long* __restrict__ row_off, const int* __restrict__ row_k,
+                   const int* __restrict__ row_ch, const float* __restrict__ scale,
+                   const float* __restrict__ rstd, const float* __restrict__ mean,
+                   const float* __restrict__ dbeta, float* __restrict__ dgamma) {
+  __shared__ float red[4];
+  const long long r = blockIdx.x;
+  const long long off = row_off[r];
+  const int K = row_k[r];
+  const int ch = row_ch[r];
+  const float s = scale[ch];
+  float dot = 0.f;
+  if (((off | K) & 3) == 0) {
+    const float4* w = reinterpret_cast<const float4*>(P + off);
+    float4* g = reinterpret_cast<float4*>(G + off);
+    for (int i = threadIdx.x; i < (K >> 2); i += blockDim.x) {
+      const float4 a = w[i];
+      float4 b = g[i];
+      dot += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+      g[i] = make_float4(b.x * s, b.y * s, b.z * s, b.w * s);
+    }
+  } else {
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+      const float b = G[off + i];
+      dot += P[off + i] * b;
+      G[off + i] = b * s;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    dot = red[0] + red[1] + red[2] + red[3];
+    dgamma[ch] += rstd[ch] * (dot - mean[ch] * dbeta[ch]);
+  }
+}
+
 // g = dy * (y>0 if relu);  dz = round(g*scale) ; dres = g ; dbeta += sum g ; dgamma += sum g*xhat
 // float4 along C; a block covers `rpb` rows per iteration over its slab of rows, partial channel
 // sums are combined in shared memory before one atomicAdd per channel per block.
@@ -450,6 +518,28 @@ int loft_bn_fold(const float* gamma, const float* beta, const float* mean, const
   bn_fold_kernel<<<loft_cdiv(C, 128), 128, 0, stream>>>(gamma, beta, mean, var, eps, scale, shift,
                                                         rstd, C);
   LOFT_CUDA_LAUNCH_CHECK("bn_fold");
+  return LOFT_OK;
+}
+
+int loft_bn_fold_weights(const float* P, float* T, const long long* row_off, const int* row_k,
+                         const int* row_ch, const float* scale, long long rows,
+                         cudaStream_t stream) {
+  LOFT_CHECK_ARG(P && T && row_off && row_k && row_ch && scale, "bn_fold_weights: null pointer");
+  if (rows == 0) return LOFT_OK;
+  bn_fold_weights_kernel<<<(unsigned)rows, 128, 0, stream>>>(P, T, row_off, row_k, row_ch, scale);
+  LOFT_CUDA_LAUNCH_CHECK("bn_fold_weights");
+  return LOFT_OK;
+}
+
+int loft_bn_finalize(const float* P, float* G, const long long* row_off, const int* row_k,
+                     const int* row_ch, const float* scale, const float* rstd, const float* mean,
+                     const float* dbeta, float* dgamma, long long rows, cudaStream_t stream) {
+  LOFT_CHECK_ARG(P && G && row_off && row_k && row_ch && scale && rstd && mean && dbeta && dgamma,
+                 "bn_finalize: null pointer");
+  if (rows == 0) return LOFT_OK;
+  bn_finalize_kernel<<<(unsigned)rows, 128, 0, stream>>>(P, G, row_off, row_k, row_ch, scale, rstd,
+                                                         mean, dbeta, dgamma);
+  LOFT_CUDA_LAUNCH_CHECK("bn_finalize");
   return LOFT_OK;
 }
 

@@ -69,10 +69,14 @@ struct GemmParams {
   const float* residual;
   const float* mask;
   long long ldo, ldr;
-  int res_mode;   // 0 none, 1 same pixel, 2 nearest-upsample x2 (residual has H/2 x W/2 pixels)
+  int res_mode;   // 0 none, 1 same pixel, 2 nearest-upsample x2 (residual has H/2 x W/2 pixels),
+                  // 3 zero-stuffed x2 (residual only at even (h,w): backward of a stride-2 1x1)
   int relu;
   int out_map;    // 0 plain rows, 1 deconv 2x2/s2 pixel shuffle (out is [N,2H,2W,Cm/4])
   int round_out;  // round `out` to TF32 (RNA) so the next MMA's operand truncation is exact
+  float* colsum;  // per-channel sum over pixels of the value written to `out` (atomic accumulate):
+  float* colsum2; //   the bias / BN-beta gradient of the layer that produced this dgrad's input
+  long long colsum_gstride;  // stride of colsum between groups (floats)
   long long ldw;  // WGRAD: row pitch of dW
   int tap_stride; // WGRAD_CONV: column offset per tap in dW (= Cin)
   // grouped conv modes (FOA: 4 branches with their own weights in one launch)
@@ -305,7 +309,7 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
           } else {
             pix = (long long)pt * p.n_mma + col;
             ok = pix < p.P;
-            if (ok && (p.res_mode == 2 || p.out_map == 1)) {
+            if (ok && (p.res_mode >= 2 || p.out_map == 1)) {
               pw_ = (int)(pix % p.W);
               const long long r = pix / p.W;
               ph_ = (int)(r % p.H);
@@ -315,6 +319,10 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (ok) {
             row = (p.out_map == 1) ? (pn * (2 * p.H) + 2 * ph_) * (2 * p.W) + 2 * pw_ : (int)pix;
             if (p.res_mode == 2) rrow = (pn * (p.H >> 1) + (ph_ >> 1)) * (p.W >> 1) + (pw_ >> 1);
+            if (p.res_mode == 3)
+              rrow = ((ph_ | pw_) & 1) ? -1
+                                       : (pn * ((p.H + 1) >> 1) + (ph_ >> 1)) * ((p.W + 1) >> 1) +
+                                             (pw_ >> 1);
           }
         }
         s_row[col] = row;
@@ -364,6 +372,14 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const float* __restrict__ res = p.residual;
         const float* __restrict__ msk = p.mask;
         constexpr int kCh = 32;  // columns per chunk: 32 independent loads in flight per thread
+        const long long ldo = p.ldo, ldr = p.ldr;
+        float* __restrict__ outb = p.out + (long long)row_add * ldo + ocol;
+        float* __restrict__ rawb = p.raw_out ? p.raw_out + (long long)row_add * ldo + ocol : nullptr;
+        const float* __restrict__ mskb = msk ? msk + (long long)row_add * ldo + ocol : nullptr;
+        const float* __restrict__ resb =
+            res ? res + (p.res_mode == 1 ? (long long)row_add * ldr : 0) + ocol : nullptr;
+        const int res_mode = p.res_mode, relu = p.relu, round_out = p.round_out;
+        float csum = 0.f;
         for (int cc = half * kCh; cc < p.n_mma; cc += 2 * kCh) {
           float v[kCh];
           tmem_ld32(taddr + cc, v);
@@ -372,36 +388,57 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
           float rv[kCh];
 #pragma unroll
           for (int j = 0; j < kCh; ++j) rows[j] = s_row[cc + j];
-          if (p.res_mode == 1) {
+          if (rawb != nullptr) {
 #pragma unroll
             for (int j = 0; j < kCh; ++j)
-              rv[j] = rows[j] >= 0 ? res[(long long)(rows[j] + row_add) * p.ldr + ocol] : 0.f;
-          } else if (p.res_mode == 2) {
-#pragma unroll
-            for (int j = 0; j < kCh; ++j)
-              rv[j] = rows[j] >= 0 ? res[(long long)s_rrow[cc + j] * p.ldr + ocol] : 0.f;
-          } else if (msk != nullptr) {
-#pragma unroll
-            for (int j = 0; j < kCh; ++j)
-              rv[j] = rows[j] >= 0 ? msk[(long long)(rows[j] + row_add) * p.ldo + ocol] : 0.f;
+              if (rows[j] >= 0) rawb[(long long)rows[j] * ldo] = v[j];
           }
+#pragma unroll
+          for (int j = 0; j < kCh; ++j) v[j] = fmaf(v[j], sc, sh);
+          if (res_mode != 0) {
+            if (res_mode == 1) {
+#pragma unroll
+              for (int j = 0; j < kCh; ++j)
+                rv[j] = rows[j] >= 0 ? __ldg(resb + (long long)rows[j] * ldr) : 0.f;
+            } else {
+#pragma unroll
+              for (int j = 0; j < kCh; ++j) {
+                const int rr = s_rrow[cc + j];
+                rv[j] = (rows[j] >= 0 && rr >= 0) ? __ldg(resb + (long long)rr * ldr) : 0.f;
+              }
+            }
+            asm volatile("" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < kCh; ++j) v[j] += rv[j];
+          }
+          if (relu) {
+#pragma unroll
+            for (int j = 0; j < kCh; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (mskb != nullptr) {
+#pragma unroll
+            for (int j = 0; j < kCh; ++j)
+              rv[j] = rows[j] >= 0 ? __ldg(mskb + (long long)rows[j] * ldo) : 0.f;
+          }
+          // the ReLU-mask select lives in the (branchy) store loop on purpose: uses in a later
+          // basic block keep the 32 mask loads above issued back to back
 #pragma unroll
           for (int j = 0; j < kCh; ++j) {
             if (rows[j] < 0) continue;
-            const long long o = (long long)(rows[j] + row_add) * p.ldo + ocol;
             float acc = v[j];
-            if (p.raw_out != nullptr) p.raw_out[o] = acc;
-            acc = fmaf(acc, sc, sh);
-            if (p.res_mode != 0) acc += rv[j];
-            if (p.relu) acc = fmaxf(acc, 0.f);
-            if (msk != nullptr) acc = (rv[j] > 0.f) ? acc : 0.f;
-            if (p.round_out) {
+            if (mskb != nullptr) acc = (rv[j] > 0.f) ? acc : 0.f;
+            if (round_out) {
               uint32_t rr;
               asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(rr) : "f"(acc));
               acc = __uint_as_float(rr);
             }
-            p.out[o] = acc;
+            csum += acc;
+            outb[(long long)rows[j] * ldo] = acc;
           }
+        }
+        if (p.colsum != nullptr && c_ok) {
+          atomicAdd(p.colsum + (long long)grp * p.colsum_gstride + ocol, csum);
+          if (p.colsum2 != nullptr) atomicAdd(p.colsum2 + ocol, csum);
         }
       }
       tc_fence_before();
@@ -585,9 +622,7 @@ void pixel_tile_for(int target, int N, int H, int W, int& tn, int& th, int& tw) 
 
 void pick_pixel_tile(int N, int H, int W, int nct, int& tn, int& th, int& tw) {
   long long bc = -1;
-  for (int target : {256, 128, 64}) {
-    int a, b, c;
-    pixel_tile_for(target, N, H, W, a, b, c);
+  auto consider = [&](int a, int b, int c) {
     const long long tiles =
         (long long)nct * loft_cdiv(W, c) * loft_cdiv(H, b) * loft_cdiv(N, a);
     const long long cost = wave_cost(tiles, round16(a * b * c));
@@ -597,7 +632,16 @@ void pick_pixel_tile(int N, int H, int W, int nct, int& tn, int& th, int& tw) {
       th = b;
       tw = c;
     }
+  };
+  for (int target : {256, 128, 64}) {
+    int a, b, c;
+    pixel_tile_for(target, N, H, W, a, b, c);
+    consider(a, b, c);
   }
+  // small maps (RoI heads: 7x7, 14x14): whole images per tile, any count that fits 256 columns --
+  // picks the count that leaves the fewest idle SMs in the last wave
+  if (W <= 16 && H * W <= kMaxN)
+    for (int a = 1; a <= N && a * H * W <= kMaxN; ++a) consider(a, H, W);
 }
 
 // Pixel patch of exactly kKB (=32) positions for the K side of WGRAD_CONV (OOB -> zero fill).
@@ -618,7 +662,10 @@ void set_epilogue(GemmParams& p, const loft_epilogue_t* e, float* out, long long
   p.residual = e ? e->residual : nullptr;
   p.mask = e ? e->mask : nullptr;
   p.ldr = e ? (e->ldr ? e->ldr : ldo) : ldo;
-  p.res_mode = (e && e->residual) ? (e->res_upsample2x ? 2 : 1) : 0;
+  p.res_mode = (e && e->residual) ? (e->res_upsample2x == 1 ? 2 : (e->res_upsample2x == 2 ? 3 : 1)) : 0;
+  p.colsum = e ? e->colsum : nullptr;
+  p.colsum2 = e ? e->colsum2 : nullptr;
+  p.colsum_gstride = e ? e->colsum_gstride : 0;
   p.relu = e ? e->relu : 0;
   p.out_map = e ? e->deconv_shuffle : 0;
   p.round_out = e ? e->round_out : 0;
@@ -684,9 +731,9 @@ int loft_gemm_fprop(const float* x, const float* w, float* y, long long P, int K
 }
 
 // dx[P,Cin] = maskrelu( dy[P,Cout] . w[Cout,Cin] )
-int loft_gemm_dgrad(const float* dy, const float* w, float* dx, long long P, int Cin, int Cout,
-                    long long lddy, long long ldw, long long lddx, const loft_epilogue_t* epi,
-                    cudaStream_t stream) {
+int loft_gemm_dgrad_hw(const float* dy, const float* w, float* dx, long long P, int Cin, int Cout,
+                       long long lddy, long long ldw, long long lddx, int H, int W,
+                       const loft_epilogue_t* epi, cudaStream_t stream) {
   LOFT_CHECK_ARG(dy && w && dx, "gemm_dgrad: null pointer");
   LOFT_CHECK_SHAPE(Cin % 32 == 0, "gemm_dgrad: Cin=%d must be a multiple of 32", Cin);
   LOFT_CHECK_SHAPE(lddy % 4 == 0 && ldw % 4 == 0, "gemm_dgrad: row pitches must be multiples of 4");
@@ -706,8 +753,8 @@ int loft_gemm_dgrad(const float* dy, const float* w, float* dx, long long P, int
   p.P = (int)P;
   p.Cm = Cin;
   p.N = 1;
-  p.H = 1;
-  p.W = (int)P;
+  p.H = H > 0 ? H : 1;
+  p.W = W > 0 ? W : (int)P;
   fill_descs(p, true, false);
   set_epilogue(p, epi, dx, lddx);
   CUtensorMap ta, tb;
@@ -726,6 +773,12 @@ int loft_gemm_dgrad(const float* dy, const float* w, float* dx, long long P, int
     if (r) return r;
   }
   return launch(ta, tb, p, stream);
+}
+
+int loft_gemm_dgrad(const float* dy, const float* w, float* dx, long long P, int Cin, int Cout,
+                    long long lddy, long long ldw, long long lddx, const loft_epilogue_t* epi,
+                    cudaStream_t stream) {
+  return loft_gemm_dgrad_hw(dy, w, dx, P, Cin, Cout, lddy, ldw, lddx, 0, 0, epi, stream);
 }
 
 // dw[Cout,Cin] += dy[P,Cout]^T . x[P,Cin]   (atomic accumulate; caller zero-fills once per step)

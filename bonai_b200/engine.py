@@ -147,9 +147,11 @@ class ParamStore:
                 if b is not None:
                     m._buffers[k] = b.to(dev)
         self.packed = []
+        self._fold_pairs = []
         for m in model.modules():
             if hasattr(m, 'loft_prepare'):
                 m.loft_prepare(self)
+        self._build_fold_tables()
         self._seen_version = None
         self._frozen_ready = False
         self._callback_queued = False
@@ -161,6 +163,55 @@ class ParamStore:
             else None
         self._w_pending = False
         model._loft_store = self
+
+    # ------------------------------------------------------------------ BN folded into weights
+    def fold_bn(self, conv_weight, bn):
+        """Declare that eval-mode `bn` directly follows the conv owning `conv_weight`: the TF32
+        copy the tensor cores read becomes scale*W (loft_bn_fold_weights) and gamma's gradient is
+        recovered from the weight gradient after backward (loft_bn_finalize)."""
+        self._fold_pairs.append((conv_weight, bn))
+
+    def _build_fold_tables(self):
+        """Row tables (flat offset, K, BN channel) per BN group: [0] trainable, [1] frozen."""
+        dev = self.device
+        self._fold_tables = [None, None]
+        base = self.P.data_ptr()
+        rows = [([], [], []), ([], [], [])]
+        for w, bn in self._fold_pairs:
+            gi = 0 if bn.weight.requires_grad else 1
+            g = self._bn_groups[gi]
+            assert w.requires_grad == bn.weight.requires_grad, \
+                'a conv and the BN folded into it must be frozen / trainable together'
+            cout = w.shape[0]
+            K = w.numel() // cout
+            off = (w.data.data_ptr() - base) // 4
+            ch0 = (bn._loft_bn.scale.data_ptr() - g['scale'].data_ptr()) // 4
+            ro, rk, rc = rows[gi]
+            ro.extend(off + c * K for c in range(cout))
+            rk.extend([K] * cout)
+            rc.extend(ch0 + c for c in range(cout))
+        for gi, (ro, rk, rc) in enumerate(rows):
+            if ro:
+                self._fold_tables[gi] = dict(
+                    off=torch.tensor(ro, dtype=torch.int64, device=dev),
+                    k=torch.tensor(rk, dtype=torch.int32, device=dev),
+                    ch=torch.tensor(rc, dtype=torch.int32, device=dev), rows=len(ro))
+
+    def _fold_weights(self, gi):
+        t, g = self._fold_tables[gi], self._bn_groups[gi]
+        if t is None:
+            return
+        L.call('bn_fold_weights', L.ptr(self.P), L.ptr(self.T), L.ptr(t['off']), L.ptr(t['k']),
+               L.ptr(t['ch']), L.ptr(g['scale']), L.ll(t['rows']), L.stream())
+
+    def _bn_finalize(self):
+        t, g = self._fold_tables[0], self._bn_groups[0]
+        if t is None:
+            return
+        C = g['C']
+        L.call('bn_finalize', L.ptr(self.P), L.ptr(self.G), L.ptr(t['off']), L.ptr(t['k']),
+               L.ptr(t['ch']), L.ptr(g['scale']), L.ptr(g['rstd']), L.ptr(g['mean']),
+               L.ptr(self.G[C:2 * C]), L.ptr(self.G[0:C]), L.ll(t['rows']), L.stream())
 
     # ------------------------------------------------------------------ packed weights
     def add_packed(self, packed):
@@ -178,6 +229,7 @@ class ParamStore:
         end = self.total
         L.call('copy2d', L.ptr(self.P), L.ll(end), L.ptr(self.T), L.ll(end), L.ll(1),
                ctypes.c_int(end), ctypes.c_int(0), ctypes.c_int(1), L.stream())
+        self._frozen_ready = False          # the full copy overwrote the folded frozen weights
         self._after_weight_update()
         self._seen_version = ver
 
@@ -188,6 +240,7 @@ class ParamStore:
             L.call('bn_fold', ctypes.c_void_p(g['gamma_ptr']), ctypes.c_void_p(g['beta_ptr']),
                    L.ptr(g['mean']), L.ptr(g['var']), L.f32(g['eps']), L.ptr(g['scale']),
                    L.ptr(g['shift']), L.ptr(g['rstd']), ctypes.c_int(g['C']), L.stream())
+            self._fold_weights(gi)
         self._frozen_ready = True
         for pk in self.packed:
             pk.build()
@@ -230,6 +283,7 @@ class ParamStore:
 
     def finalize_grads(self):
         self.join_wgrad_stream()
+        self._bn_finalize()
         for pk in self.packed:
             pk.scatter()
         for p, g in self._grad_views:

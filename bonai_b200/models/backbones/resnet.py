@@ -89,6 +89,14 @@ class Bottleneck(nn.Module):
         self._sd = spec(self.downsample[0], self.downsample[1], False) \
             if self.downsample is not None else None
         self._trainable = self.conv1.weight.requires_grad
+        store.fold_bn(self.conv1.weight, self.bn1)
+        store.fold_bn(self.conv2.weight, self.bn2)
+        store.fold_bn(self.conv3.weight, self.bn3)
+        if self.downsample is not None:
+            store.fold_bn(self.downsample[0].weight, self.downsample[1])
+        if self._trainable:
+            # beta gradients of bn1 / bn2 come out of conv2's / conv3's dgrad epilogues
+            D.link_chain([self._s1, self._s2, self._s3])
 
     def forward(self, x):
         if not self._trainable or not torch.is_grad_enabled():
@@ -196,6 +204,7 @@ class ResNet(nn.Module):
         from ... import _lib as L
         import ctypes
         w = self.conv1.weight                          # [64,3,7,7], physically [64,7,7,3]
+        store.fold_bn(w, self.bn1)
         K = w.shape[1] * 49
         self._kpad = (K + 3) // 4 * 4
         self._stem_w = torch.zeros((w.shape[0], self._kpad), device=store.device)
@@ -210,7 +219,7 @@ class ResNet(nn.Module):
     def forward(self, x):
         bn = self.bn1._loft_bn
         with torch.no_grad():
-            x = M.stem_conv(x, self._stem_w, self._kpad, bn.scale, bn.shift)
+            x = M.stem_conv(x, self._stem_w, self._kpad, None, bn.shift)
             x = M.maxpool3x3s2(x)
         outs = []
         for i, name in enumerate(self.res_layers):

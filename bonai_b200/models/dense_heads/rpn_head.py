@@ -106,6 +106,7 @@ class RPNHead(nn.Module):
         store.add_packed(Packed(w, b, gw, gb, build, scatter))
         self._head_spec = D.ConvSpec(WeightRef(w, gw), ksize=1, bias=b, bias_grad=gb,
                                      round_out=False, store=store, premask_in=True)
+        D.link_chain([self._conv_spec, self._head_spec])
         self._base_anchors_dev = [ba.to(dev).contiguous()
                                   for ba in self.anchor_generator.base_anchors]
 

@@ -98,6 +98,10 @@ class OffsetHeadExpandFeature(nn.Module):
                                             store=store, premask_in=(i > 0), grad_premasked=True))
             if all(g.uniform for g in gs):
                 self._group_specs = gs
+                D.link_chain(gs)
+        if self._group_specs is None:
+            for specs in self._conv_specs:
+                D.link_chain(specs)
         area = self.roi_feat_size[0] * self.roi_feat_size[1]
         self._fc_specs = []
         for i, fc in enumerate(self.fcs):
@@ -110,6 +114,7 @@ class OffsetHeadExpandFeature(nn.Module):
         wref, b, gb = make_fused_head(store, [self.fc_offset], 4)
         self._head = D.ConvSpec(wref, bias=b, bias_grad=gb, round_out=False, store=store,
                                 premask_in=len(self.fcs) > 0)
+        D.link_chain(self._fc_specs + [self._head])
 
     def expand_feature(self, feature, operation_idx):
         if operation_idx >= 4:

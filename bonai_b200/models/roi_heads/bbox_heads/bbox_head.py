@@ -219,6 +219,7 @@ class ConvFCBBoxHead(BBoxHead):
         wref, b, gb = make_fused_head(store, [self.fc_cls, self.fc_reg], width)
         self._head = D.ConvSpec(wref, bias=b, bias_grad=gb, round_out=False, store=store,
                                 premask_in=True)
+        D.link_chain(self._specs + [self._head])
 
     def forward(self, x):
         # x: [K, C, 7, 7] with NHWC storage -> [K, 7*7*C]

@@ -63,11 +63,22 @@ class ConvSpec:
     def __init__(self, wref, ksize=1, stride=1, padding=0, relu=False, bias=None, bias_grad=None,
                  bn=None, bn_trainable=False, round_out=True, res_upsample=False, store=None,
                  cout=None, kpad=None, premask_in=False, grad_premasked=False):
+        # bias gradient by the consumer: a layer whose (single) consumer has in_colsum set gets
+        # its bias gradient as the column sum the consumer's dgrad epilogue accumulates, and
+        # skips its own read-only reduction pass (see link_bias_colsum)
+        self.in_colsum, self.in_colsum_gstride = None, 0
+        self.bias_by_consumer = False
         self.wref = wref
         self.ksize, self.stride, self.padding = ksize, stride, padding
         self.relu = relu
         self.bias, self.bias_grad = bias, bias_grad
+        # eval-mode BN is folded into the weights the tensor cores read (engine.fold_bn): the
+        # epilogue only adds bn.shift, beta's gradient is the layer's "bias gradient" and gamma's
+        # comes from the weight gradient (loft_bn_finalize) -- no pass over the activations
         self.bn, self.bn_trainable = bn, bn_trainable
+        if bn is not None:
+            self.bias = bn.shift
+            self.bias_grad = bn.dbeta if bn_trainable else None
         self.round_out = round_out
         self.res_upsample = res_upsample
         self.store = store
@@ -78,6 +89,34 @@ class ConvSpec:
         # grad_premasked) receives an already-masked gradient and skips its own masking pass.
         self.premask_in = premask_in
         self.grad_premasked = grad_premasked
+
+
+def link_bias_colsum(producer, consumer, gstride=0):
+    """Wire producer -> consumer (a single-consumer chain): the consumer's dgrad epilogue writes
+    dZ of the producer (it applies the producer's ReLU mask, or the producer has no ReLU), so the
+    per-channel sum of what it writes IS the producer's bias gradient."""
+    import os
+    if os.environ.get('LOFT_NO_COLSUM', '0') != '0':
+        return False
+    pg = producer.bias_grads[0] if isinstance(producer, GroupedConvSpec) else producer.bias_grad
+    if pg is None:
+        return False
+    if producer.relu and not (consumer.premask_in and producer.grad_premasked):
+        return False
+    if isinstance(consumer, ConvSpec) and not (
+            (consumer.ksize == 3 and consumer.stride == 1 and consumer.padding == 1) or
+            (consumer.ksize == 1 and consumer.stride == 1)):
+        return False
+    consumer.in_colsum = pg
+    consumer.in_colsum_gstride = gstride
+    producer.bias_by_consumer = True
+    return True
+
+
+def link_chain(specs):
+    for a, b in zip(specs[:-1], specs[1:]):
+        gs = a.b_grad_gstride if isinstance(a, GroupedConvSpec) else 0
+        link_bias_colsum(a, b, gs)
 
 
 def _fprop(spec, x, residual):
@@ -93,12 +132,8 @@ def _fprop(spec, x, residual):
     y = new_nhwc(N, Cout, Ho, Wo, dev)
     yn = y.permute(0, 2, 3, 1)
     z = None
-    if spec.bn is not None and spec.bn_trainable:
-        z = torch.empty((N, Ho, Wo, Cout), device=dev, dtype=torch.float32)
-    scale = spec.bn.scale if spec.bn is not None else None
-    shift = spec.bn.shift if spec.bn is not None else spec.bias
     rn = nhwc(residual) if residual is not None else None
-    e = L.make_epilogue(raw_out=z, scale=scale, shift=shift, residual=rn,
+    e = L.make_epilogue(shift=spec.bias, residual=rn,
                         ldr=(rn.shape[-1] if rn is not None else 0),
                         res_upsample2x=spec.res_upsample, relu=spec.relu,
                         round_out=spec.round_out)
@@ -157,33 +192,25 @@ class _ConvFn(Function):
         _, Ho, Wo, Cout = dyn.shape
         P = N * Ho * Wo
         dev = dy.device
-        # 1. activation / affine backward (+ per-channel reductions)
+        # 1. ReLU backward (+ the bias / BN-beta gradient = per-channel sum of dz)
         need_res = ctx.has_res and ctx.needs_input_grad[1]
-        bn = spec.bn
+        dbeta = spec.bias_grad
         dres = None
-        dgamma = bn.dgamma if (bn is not None and spec.bn_trainable) else None
-        dbeta = bn.dbeta if (bn is not None and spec.bn_trainable) else spec.bias_grad
-        if not relu_eff and bn is None:
-            # plain conv + bias (or ReLU already applied by the consumer's dgrad epilogue):
-            # dz == dy, only the bias gradient needs a (read-only) pass.  dy is fed to the tensor
-            # cores as is; unrounded operands only bias *gradients* by ~5e-4.
+        if not relu_eff:
+            # no ReLU, or its mask was already applied by the consumer's dgrad epilogue:
+            # dz == dy, only the bias gradient needs a (read-only) pass unless the consumer's
+            # epilogue produced it too.  dy is fed to the tensor cores as is; unrounded operands
+            # only bias *gradients* by ~5e-4.
             dz = dyn
-            if dbeta is not None:
+            if dbeta is not None and not spec.bias_by_consumer:
                 L.call('act_bwd', L.ptr(dyn), None, None, None, None, None, None, None, None,
                        L.ptr(dbeta), L.ll(P), i32(Cout), i32(0), st)
         else:
             dz = torch.empty_like(dyn)
-            if need_res and relu_eff and not spec.res_upsample:
-                dres = torch.empty_like(dyn)
-            L.call('act_bwd', L.ptr(dyn), L.ptr(nhwc(y)) if y is not None else None,
-                   L.ptr(z) if dgamma is not None else None,
-                   L.ptr(bn.scale) if bn is not None else None,
-                   L.ptr(bn.mean) if dgamma is not None else None,
-                   L.ptr(bn.rstd) if dgamma is not None else None,
-                   L.ptr(dz), L.ptr(dres) if dres is not None else None,
-                   L.ptr(dgamma) if dgamma is not None else None,
-                   L.ptr(dbeta) if dbeta is not None else None, L.ll(P), i32(Cout),
-                   i32(relu_eff), st)
+            L.call('act_bwd', L.ptr(dyn), L.ptr(nhwc(y)), None, None, None, None, L.ptr(dz), None,
+                   None, L.ptr(dbeta) if dbeta is not None else None, L.ll(P), i32(Cout), i32(1),
+                   st)
+            dres = dz
         grad_res = None
         if need_res:
             if spec.res_upsample:
@@ -220,7 +247,8 @@ class _ConvFn(Function):
         # 3. data gradient
         dx = None
         if ctx.needs_input_grad[0]:
-            e = L.make_epilogue(round_out=True, mask=xin if (xin is not None and s == 1) else None)
+            e = L.make_epilogue(round_out=True, mask=xin if (xin is not None and s == 1) else None,
+                                colsum=spec.in_colsum)
             if conv3:
                 dx = new_nhwc(N, Cin, H, W, dev)
                 L.call('conv3x3_dgrad', L.ptr(dz), L.ptr(w), L.ptr(dx.permute(0, 2, 3, 1)), i32(N),
@@ -293,7 +321,7 @@ class _LinearFn(Function):
         dy = dy.contiguous()
         if not (spec.relu and not spec.grad_premasked):
             dz = dy
-            if spec.bias_grad is not None:
+            if spec.bias_grad is not None and not spec.bias_by_consumer:
                 L.call('act_bwd', L.ptr(dy), None, None, None, None, None, None, None, None,
                        L.ptr(spec.bias_grad), L.ll(P), i32(Cout), i32(0), st)
         else:
@@ -314,7 +342,8 @@ class _LinearFn(Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty((P, K), device=dy.device, dtype=torch.float32)
-            e = L.make_epilogue(round_out=True, mask=x if spec.premask_in else None)
+            e = L.make_epilogue(round_out=True, mask=x if spec.premask_in else None,
+                                colsum=spec.in_colsum)
             L.call('gemm_dgrad', L.ptr(dz), L.ptr(w), L.ptr(dx), L.ll(P), i32(K), i32(Cout),
                    L.ll(Cout), L.ll(K), L.ll(K), ctypes.byref(e), st)
         return (dx, None) + (None,) * (len(ctx.needs_input_grad) - 2)
@@ -374,7 +403,7 @@ class _Deconv2x2Fn(Function):
         dyn = nhwc(dy)
         if y is None:
             dz = dyn
-            if spec.bias_grad is not None:
+            if spec.bias_grad is not None and not spec.bias_by_consumer:
                 L.call('act_bwd', L.ptr(dyn), None, None, None, None, None, None, None, None,
                        L.ptr(spec.bias_grad), L.ll(N * 4 * H * W), i32(Co), i32(0), st)
         else:
@@ -392,7 +421,8 @@ class _Deconv2x2Fn(Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = new_nhwc(N, Cin, H, W, dy.device)
-            e = L.make_epilogue(round_out=True, mask=xn if spec.premask_in else None)
+            e = L.make_epilogue(round_out=True, mask=xn if spec.premask_in else None,
+                                colsum=spec.in_colsum)
             L.call('gemm_dgrad', L.ptr(dzp), L.ptr(w), L.ptr(dx.permute(0, 2, 3, 1)), L.ll(P),
                    i32(Cin), i32(4 * Co), L.ll(4 * Co), L.ll(Cin), L.ll(Cin), ctypes.byref(e), st)
         return (dx, None) + (None,) * (len(ctx.needs_input_grad) - 2)
@@ -414,6 +444,7 @@ class GroupedConvSpec:
     def __init__(self, wrefs, biases, bias_grads, relu=True, store=None, premask_in=False,
                  grad_premasked=False):
         self.premask_in, self.grad_premasked = premask_in, grad_premasked
+        self.in_colsum, self.in_colsum_gstride, self.bias_by_consumer = None, 0, False
         self.G = len(wrefs)
         self.w0 = wrefs[0].w
         self.gw0 = wrefs[0].grad
@@ -433,7 +464,10 @@ class GroupedConvSpec:
         self.gw_gstride = 0
         if self.gw0 is not None:
             self.gw_gstride, ok3 = stride([r.grad for r in wrefs])
-        self.uniform = ok1 and ok2 and ok3
+        self.b_grad_gstride, ok4 = (0, True)
+        if all(g is not None for g in bias_grads):
+            self.b_grad_gstride, ok4 = stride(list(bias_grads))
+        self.uniform = ok1 and ok2 and ok3 and ok4
 
 
 class _GroupedConv3x3Fn(Function):
@@ -471,7 +505,7 @@ class _GroupedConv3x3Fn(Function):
                        ctypes.c_void_p(dz.data_ptr() + o), None, None,
                        L.ptr(spec.bias_grads[g]) if spec.bias_grads[g] is not None else None,
                        L.ll(rows_g), i32(Cout), i32(1), st)
-            elif spec.bias_grads[g] is not None:
+            elif spec.bias_grads[g] is not None and not spec.bias_by_consumer:
                 L.call('act_bwd', ctypes.c_void_p(dyn.data_ptr() + o), None, None, None, None, None,
                        None, None, None, L.ptr(spec.bias_grads[g]), L.ll(rows_g), i32(Cout), i32(0),
                        st)
@@ -483,7 +517,8 @@ class _GroupedConv3x3Fn(Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = new_nhwc(N, Cin, H, W, dy.device)
-            e = L.make_epilogue(round_out=True, mask=xn if spec.premask_in else None)
+            e = L.make_epilogue(round_out=True, mask=xn if spec.premask_in else None,
+                                colsum=spec.in_colsum, colsum_gstride=spec.in_colsum_gstride)
             L.call('conv3x3_dgrad_grouped', L.ptr(dz), L.ptr(spec.w0), L.ptr(dx.permute(0, 2, 3, 1)),
                    i32(N), i32(H), i32(W), i32(Cin), i32(Cout), i32(G), L.ll(spec.w_gstride),
                    ctypes.byref(e), st)

@@ -30,8 +30,12 @@ int loft_abi_version(void);
  *   acc = sum_k ...;  if (raw_out) raw_out[p,c] = acc;           (pre-BN conv output)
  *   v = acc*scale[c] + shift[c]                                   (BN-eval affine / bias)
  *   v += residual[p,c]  (or residual[up2x(p),c] if res_upsample2x: FPN top-down, fpn.py:185-186)
+ *      (res_upsample2x == 2: zero-stuffed -- residual[p/2,c] only where h and w are even: the
+ *       backward of a stride-2 1x1 conv on the same input, resnet.py:151-156 downsample path)
  *   if (relu) v = max(v,0);  if (mask) v = mask[p,c] > 0 ? v : 0  (ReLU backward)
  *   out[p,c] = v   (deconv_shuffle: c=(i*2+j)*Co+co scatters to pixel (2h+i,2w+j), channel co)
+ *   colsum[g*colsum_gstride + c] += sum_p v  (and colsum2[c]): in a dgrad launch this is the
+ *      bias / BN-beta gradient of the layer that produced the dgrad's input, for free
  */
 typedef struct loft_epilogue_t {
   float* raw_out;
@@ -44,6 +48,9 @@ typedef struct loft_epilogue_t {
   int relu;
   int deconv_shuffle;
   int round_out; /* round out[] to TF32 (round-to-nearest) for the consuming tensor-core op */
+  float* colsum;
+  float* colsum2;
+  long long colsum_gstride;
 } loft_epilogue_t;
 
 /* ---- dense contractions on tcgen05 (TF32 operands, fp32 accumulate in TMEM) -------------------
@@ -56,6 +63,11 @@ int loft_gemm_fprop(const float* x, const float* w, float* y, long long P, int K
 int loft_gemm_dgrad(const float* dy, const float* w, float* dx, long long P, int Cin, int Cout,
                     long long lddy, long long ldw, long long lddx, const loft_epilogue_t* epi,
                     cudaStream_t stream);
+/* gemm_dgrad with the pixel rows laid out as an [N,H,W] grid (needed by the zero-stuffed
+ * residual mode of the epilogue) */
+int loft_gemm_dgrad_hw(const float* dy, const float* w, float* dx, long long P, int Cin, int Cout,
+                       long long lddy, long long ldw, long long lddx, int H, int W,
+                       const loft_epilogue_t* epi, cudaStream_t stream);
 int loft_gemm_wgrad(const float* dy, const float* x, float* dw, long long P, int Cin, int Cout,
                     long long lddy, long long ldx, long long lddw, cudaStream_t stream);
 int loft_conv3x3_fprop(const float* x, const float* w, float* y, int N, int H, int W, int Cin,
@@ -93,6 +105,16 @@ int loft_permute_acb(const float* src, float* dst, int A, int B, int C, int accu
                      int round_tf32, cudaStream_t stream);
 int loft_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var,
                  float eps, float* scale, float* shift, float* rstd, int C, cudaStream_t stream);
+/* BN folded into the conv weights the tensor cores read: T[row] = tf32(scale[ch] * P[row]) for the
+ * rows (output channels) listed in the table; after backward, bn_finalize turns the accumulated
+ * dW' rows into dW and adds dgamma[ch] += rstd*(W.dW' - mean*dbeta[ch]) -- no pass over the
+ * activations (replaces BatchNorm2d eval backward, resnet.py:260-300 with norm_eval=True). */
+int loft_bn_fold_weights(const float* P, float* T, const long long* row_off, const int* row_k,
+                         const int* row_ch, const float* scale, long long rows,
+                         cudaStream_t stream);
+int loft_bn_finalize(const float* P, float* G, const long long* row_off, const int* row_k,
+                     const int* row_ch, const float* scale, const float* rstd, const float* mean,
+                     const float* dbeta, float* dgamma, long long rows, cudaStream_t stream);
 int loft_act_bwd(const float* dy, const float* y, const float* z, const float* scale,
                  const float* mean, const float* rstd, float* dz, float* dres, float* dgamma,
                  float* dbeta, long long P, int C, int relu, cudaStream_t stream);

@@ -98,7 +98,21 @@ def test_conv_bn_residual_paths(cfg):
     scale, shift = gamma * rstd, beta - mean * gamma * rstd
     dgamma, dbeta = torch.zeros(Co, device='cuda'), torch.zeros(Co, device='cuda')
     bn = BNRef(scale, shift, rstd, mean, dgamma, dbeta)
-    wref = _wref(w)
+    # eval-mode BN is folded into the weights the tensor cores read: T = tf32(scale * W)
+    import ctypes
+    from bonai_b200 import _lib as L
+    Kw = Ci * k * k
+    wflat = w.permute(0, 2, 3, 1).contiguous().view(-1) if k > 1 else w.contiguous().view(-1)
+    tflat = torch.empty_like(wflat)
+    gflat = torch.zeros_like(wflat)
+    off = (torch.arange(Co, dtype=torch.int64) * Kw).cuda()
+    rk = torch.full((Co,), Kw, dtype=torch.int32).cuda()
+    ch = torch.arange(Co, dtype=torch.int32).cuda()
+    L.call('bn_fold_weights', L.ptr(wflat), L.ptr(tflat), L.ptr(off), L.ptr(rk), L.ptr(ch),
+           L.ptr(scale), L.ll(Co), L.stream())
+    shape4 = (Co, k, k, Ci)
+    from bonai_b200.engine import WeightRef
+    wref = WeightRef(tflat.view(shape4).permute(0, 3, 1, 2), gflat.view(shape4).permute(0, 3, 1, 2))
     spec = D.ConvSpec(wref, ksize=k, stride=s, padding=pad, relu=True, bn=bn, bn_trainable=True,
                       store=_Store())
     Ho = (H + 2 * pad - k) // s + 1
@@ -114,6 +128,10 @@ def test_conv_bn_residual_paths(cfg):
     dy = tf32_round(rnd(*y.shape, seed=8))
     y.backward(dy)
     yr.backward(dy)
+    # gamma's gradient and the un-folded weight gradient come from the accumulated dW' rows
+    L.call('bn_finalize', L.ptr(wflat), L.ptr(gflat), L.ptr(off), L.ptr(rk), L.ptr(ch),
+           L.ptr(scale), L.ptr(rstd), L.ptr(mean), L.ptr(dbeta), L.ptr(dgamma), L.ll(Co),
+           L.stream())
     assert rel(xg.grad, xr.grad) < GRAD_TOL
     assert rel(rg.grad, rr.grad) < GRAD_TOL
     assert rel(wref.grad, wr.grad) < GRAD_TOL
