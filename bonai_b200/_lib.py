@@ -74,6 +74,7 @@ LAUNCHES = [0]          # kernels launched through this binding (bench.py reads 
 _KERNELS_PER_CALL = {'iou_assign': 2, 'grad_sqnorm': 1}
 
 
+RECORD = None           # set to a list to record (fn, args) of every call (trunk.Tape)
 TRACE = None            # set to a list to record (name, int args, start event, end event) per call
 
 
@@ -88,6 +89,8 @@ def _arg_summary(args):
 def call(name, *args):
     """Call ``loft_<name>`` and raise LoftError on a non-zero return code."""
     fn = getattr(lib(), 'loft_' + name)
+    if RECORD is not None:
+        RECORD.append((name, fn, args))
     if TRACE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -65,6 +65,14 @@ __global__ void permute_acb_kernel(const float* __restrict__ src, float* __restr
   }
 }
 
+__global__ void fill_kernel(float4* __restrict__ p4, float* __restrict__ p, long long n4,
+                            long long n, float v) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long k = i; k < n4; k += stride) p4[k] = make_float4(v, v, v, v);
+  for (long long k = 4 * n4 + i; k < n; k += stride) p[k] = v;
+}
+
 // ---------------------------------------------------------------- BN fold / activation backward
 __global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
                                const float* __restrict__ mean, const float* __restrict__ var,
@@ -518,6 +526,17 @@ int loft_bn_fold(const float* gamma, const float* beta, const float* mean, const
   bn_fold_kernel<<<loft_cdiv(C, 128), 128, 0, stream>>>(gamma, beta, mean, var, eps, scale, shift,
                                                         rstd, C);
   LOFT_CUDA_LAUNCH_CHECK("bn_fold");
+  return LOFT_OK;
+}
+
+int loft_fill(float* p, long long n, float v, cudaStream_t stream) {
+  LOFT_CHECK_ARG(p, "fill: null pointer");
+  if (n == 0) return LOFT_OK;
+  const bool al = (reinterpret_cast<uintptr_t>(p) & 15) == 0;
+  const long long n4 = al ? n / 4 : 0;
+  fill_kernel<<<grid_for(n4 > 0 ? n4 : n, kT, 148 * 8), kT, 0, stream>>>(
+      reinterpret_cast<float4*>(p), p, n4, n, v);
+  LOFT_CUDA_LAUNCH_CHECK("fill");
   return LOFT_OK;
 }
 

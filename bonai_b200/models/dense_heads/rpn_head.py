@@ -125,9 +125,22 @@ class RPNHead(nn.Module):
         outs = [self.forward_single(f) for f in feats]
         return [o[0] for o in outs], [o[1] for o in outs]
 
+    def outs_from_fused(self, fused_maps):
+        """(cls_scores, bbox_preds) from fused [N, 5A(+pad), h, w] head outputs computed elsewhere
+        (bonai_b200.trunk)."""
+        A = self.num_anchors
+        cls, reg = [], []
+        for fused in fused_maps:
+            c, r = fused[:, :A], fused[:, A:5 * A]
+            c._loft_fused = fused
+            r._loft_fused = fused
+            cls.append(c)
+            reg.append(r)
+        return cls, reg
+
     def forward_train(self, x, img_metas, gt_bboxes, gt_labels=None, gt_bboxes_ignore=None,
-                      proposal_cfg=None, **kwargs):
-        outs = self(x)
+                      proposal_cfg=None, rpn_outs=None, **kwargs):
+        outs = rpn_outs if rpn_outs is not None else self(x)
         if gt_labels is None:
             loss_inputs = outs + (gt_bboxes, img_metas)
         else:

@@ -50,6 +50,14 @@ class TwoStageDetector(BaseDetector):
         if self.with_roi_head:
             self.roi_head.init_weights(pretrained)
 
+    def _loft_trunk(self, store):
+        t = self.__dict__.get('_trunk', False)
+        if t is False:
+            from ...trunk import Trunk
+            ok = self.with_rpn and self.with_neck and self.training and Trunk.eligible(self)
+            t = self.__dict__['_trunk'] = Trunk(self, store) if ok else None
+        return t
+
     def extract_feat(self, img):
         x = self.backbone(img)
         if self.with_neck:
@@ -73,13 +81,21 @@ class TwoStageDetector(BaseDetector):
                 kwargs[k] = [t.to(dev, non_blocking=True) for t in v]
         if self.with_rpn and hasattr(self.rpn_head, 'prefetch_targets') and len(gt_bboxes) > 0:
             self.rpn_head.prefetch_targets(gt_bboxes, img_metas, img.shape[-2:], ready_event)
-        x = self.extract_feat(img)
+        # static part (backbone + FPN + RPN convs): two recorded CUDA-graph programs when the
+        # model is the R50-FPN-RPN composition (bonai_b200.trunk), else module by module
+        rpn_outs = None
+        trunk = self._loft_trunk(store) if torch.is_grad_enabled() else None
+        if trunk is not None:
+            x, fused = trunk(img)
+            rpn_outs = self.rpn_head.outs_from_fused(fused)
+        else:
+            x = self.extract_feat(img)
         losses = dict()
         if self.with_rpn:
             proposal_cfg = self.train_cfg.get('rpn_proposal', self.test_cfg.rpn)
             rpn_losses, proposal_list = self.rpn_head.forward_train(
                 x, img_metas, gt_bboxes, gt_labels=None, gt_bboxes_ignore=gt_bboxes_ignore,
-                proposal_cfg=proposal_cfg)
+                proposal_cfg=proposal_cfg, rpn_outs=rpn_outs)
             losses.update(rpn_losses)
         else:
             proposal_list = proposals

@@ -1,0 +1,488 @@
+"""The static part of the LOFT training step as two recorded launch programs.
+
+Everything between the input tile and the RoI heads has shapes that depend only on (N, H, W):
+the frozen stem + layer1, the trainable ResNet stages (mmdet/models/backbones/resnet.py:260-300,
+623-638), FPN (necks/fpn.py:164-216) and the RPN convolutions (dense_heads/rpn_head.py:38-44).
+Instead of ~150 autograd nodes that each allocate, wrap and launch, this module writes that part
+as ONE autograd.Function whose forward and backward are fixed sequences of C-ABI launches over
+buffers allocated once: the sequence is *recorded* the first time it runs (`Tape`), then replayed
+as a CUDA graph -- one graph launch for the forward, one for the backward.
+
+Because the whole backward is one hand-ordered program, ReLU / BN / residual backward never
+touches HBM on its own: every data-gradient launch applies, in its epilogue, the ReLU mask of
+the tensor it differentiates, adds the gradient arriving over the other branch (identity path,
+FPN lateral, RPN), and accumulates the per-channel sum that is the producer's BN-beta / bias
+gradient; BN-gamma gradients come from the weight gradients (engine._bn_finalize).
+"""
+import ctypes
+import os
+
+import torch
+from torch.autograd import Function
+
+from . import _lib as L
+
+i32 = ctypes.c_int
+
+
+class Tape:
+    """Records C-ABI calls made while active; `launch()` re-issues them (same pointers, current
+    stream) -- as a captured CUDA graph after `capture()`."""
+
+    def __init__(self, name='tape'):
+        self.name = name
+        self.calls = []
+        self.graph = None
+
+    def __enter__(self):
+        assert L.RECORD is None, 'nested tape recording'
+        L.RECORD = self.calls
+        return self
+
+    def __exit__(self, *a):
+        L.RECORD = None
+        return False
+
+    def replay(self):
+        st = L.stream()
+        for name, fn, args in self.calls:
+            rc = fn(*args[:-1], st)
+            if rc != 0:
+                msg = L.lib().loft_last_error()
+                raise L.LoftError(f'loft_{name} failed ({rc}) in tape replay: '
+                                  f'{msg.decode() if msg else ""}')
+
+    def capture(self):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, capture_error_mode='thread_local'):
+            self.replay()
+        self.graph = g
+
+    def launch(self):
+        L.LAUNCHES[0] += len(self.calls)
+        if L.TRACE is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            self.graph.replay() if self.graph is not None else self.replay()
+            e1.record()
+            L.TRACE.append((self.name, (len(self.calls),), e0, e1))
+            return
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.replay()
+
+
+def _empty(*shape, dev):
+    return torch.empty(shape, device=dev, dtype=torch.float32)
+
+
+def _epi(**kw):
+    return ctypes.byref(L.make_epilogue(**kw))
+
+
+class _Program:
+    """Builds (by executing once under a Tape) the forward / backward programs for one input
+    shape.  All tensors are NHWC; `self.keep` pins every buffer the recorded pointers refer to."""
+
+    def __init__(self, model, N, H, W, dev, train):
+        self.model, self.N, self.H, self.W, self.dev, self.train = model, N, H, W, dev, train
+        self.img = torch.empty((N, 3, H, W), device=dev, dtype=torch.float32)
+        self.fwd, self.bwd = Tape('trunk_forward_graph'), Tape('trunk_backward_graph')
+        self.fwd_ready = self.bwd_ready = False
+        self.use_graph = os.environ.get('LOFT_GRAPH', '1') != '0'
+        self.keep = []
+
+    # ---------------------------------------------------------------- primitive launches
+    def gemm_f(self, x, w, y, P, K, Co, Ho, Wo, **epi):
+        L.call('gemm_fprop', L.ptr(x), L.ptr(w), L.ptr(y), L.ll(P), i32(K), i32(Co), L.ll(K),
+               L.ll(K), L.ll(y.shape[-1]), i32(Ho), i32(Wo), _epi(**epi), L.stream())
+
+    def conv3_f(self, x, w, y, **epi):
+        N, H, W, Ci = x.shape
+        L.call('conv3x3_fprop', L.ptr(x), L.ptr(w), L.ptr(y), i32(N), i32(H), i32(W), i32(Ci),
+               i32(y.shape[-1]), _epi(**epi), L.stream())
+
+    def gemm_d(self, dy, w, dx, P, Cin, Cout, H=0, W=0, **epi):
+        L.call('gemm_dgrad_hw', L.ptr(dy), L.ptr(w), L.ptr(dx), L.ll(P), i32(Cin), i32(Cout),
+               L.ll(Cout), L.ll(Cin), L.ll(Cin), i32(H), i32(W), _epi(**epi), L.stream())
+
+    def gemm_w(self, dy, x, gw, P, Cin, Cout):
+        L.call('gemm_wgrad', L.ptr(dy), L.ptr(x), L.ptr(gw), L.ll(P), i32(Cin), i32(Cout),
+               L.ll(Cout), L.ll(Cin), L.ll(Cin), L.stream())
+
+    def conv3_d(self, dy, w, dx, **epi):
+        N, H, W, Ci = dx.shape
+        L.call('conv3x3_dgrad', L.ptr(dy), L.ptr(w), L.ptr(dx), i32(N), i32(H), i32(W), i32(Ci),
+               i32(dy.shape[-1]), _epi(**epi), L.stream())
+
+    def conv3_w(self, dy, x, gw):
+        N, H, W, Ci = x.shape
+        L.call('conv3x3_wgrad', L.ptr(dy), L.ptr(x), L.ptr(gw), i32(N), i32(H), i32(W), i32(Ci),
+               i32(dy.shape[-1]), L.stream())
+
+    def colsum(self, g, P, C, out):
+        """out[c] += sum_p g[p,c] (read-only pass; used where no dgrad epilogue can do it)."""
+        L.call('act_bwd', L.ptr(g), None, None, None, None, None, None, None, None, L.ptr(out),
+               L.ll(P), i32(C), i32(0), L.stream())
+
+    def buf(self, *shape):
+        t = _empty(*shape, dev=self.dev)
+        self.keep.append(t)
+        return t
+
+    # ---------------------------------------------------------------- forward program
+    def _block_fwd(self, x, blk):
+        s1, s2, s3, sd = blk._s1, blk._s2, blk._s3, blk._sd
+        N, H, W, Ci = x.shape
+        p = s1.wref.w.shape[0]
+        P1 = N * H * W
+        h1 = self.buf(N, H, W, p)
+        self.gemm_f(x, s1.wref.w, h1, P1, Ci, p, H, W, shift=s1.bias, relu=True, round_out=True)
+        st = s2.stride
+        col = None
+        if st == 1:
+            Ho, Wo = H, W
+            h2 = self.buf(N, H, W, p)
+            self.conv3_f(h1, s2.wref.w, h2, shift=s2.bias, relu=True, round_out=True)
+        else:
+            Ho, Wo = (H + 2 - 3) // st + 1, (W + 2 - 3) // st + 1
+            col = self.buf(N * Ho * Wo, 9 * p)
+            L.call('im2col', L.ptr(h1), L.ptr(col), i32(N), i32(H), i32(W), i32(p), i32(3), i32(3),
+                   i32(st), i32(1), i32(9 * p), i32(0), L.stream())
+            h2 = self.buf(N, Ho, Wo, p)
+            self.gemm_f(col, s2.wref.w, h2, N * Ho * Wo, 9 * p, p, Ho, Wo, shift=s2.bias,
+                        relu=True, round_out=True)
+        P3 = N * Ho * Wo
+        xs = x
+        if sd is not None:
+            if sd.stride == 2:
+                xs = self.buf(N, Ho, Wo, Ci)
+                L.call('subsample2', L.ptr(x), L.ptr(xs), i32(N), i32(H), i32(W), i32(Ci),
+                       L.stream())
+            else:
+                assert sd.stride == 1
+            idn = self.buf(N, Ho, Wo, 4 * p)
+            self.gemm_f(xs, sd.wref.w, idn, P3, Ci, 4 * p, Ho, Wo, shift=sd.bias, round_out=True)
+        else:
+            idn = x
+        out = self.buf(N, Ho, Wo, 4 * p)
+        self.gemm_f(h2, s3.wref.w, out, P3, p, 4 * p, Ho, Wo, shift=s3.bias, residual=idn,
+                    ldr=4 * p, relu=True, round_out=True)
+        return out, dict(blk=blk, x=x, xs=xs, h1=h1, h2=h2, col=col, out=out, stride=st)
+
+    def build_forward(self):
+        m = self.model
+        bb, neck, rpn = m.backbone, m.neck, m.rpn_head
+        N, H, W = self.N, self.H, self.W
+        with self.fwd:
+            # frozen stem: im2col from the NCHW image + GEMM (+folded BN, ReLU) + 3x3/2 max-pool
+            Ho, Wo = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+            kpad = bb._kpad
+            col = self.buf(N * Ho * Wo, kpad)
+            L.call('im2col', L.ptr(self.img), L.ptr(col), i32(N), i32(H), i32(W), i32(3), i32(7),
+                   i32(7), i32(2), i32(3), i32(kpad), i32(1), L.stream())
+            c1 = self.buf(N, Ho, Wo, bb._stem_w.shape[0])
+            self.gemm_f(col, bb._stem_w, c1, N * Ho * Wo, kpad, c1.shape[-1], Ho, Wo,
+                        shift=bb.bn1._loft_bn.shift, relu=True, round_out=True)
+            Hp, Wp = (Ho - 1) // 2 + 1, (Wo - 1) // 2 + 1
+            x = self.buf(N, Hp, Wp, c1.shape[-1])
+            L.call('maxpool3x3s2', L.ptr(c1), L.ptr(x), i32(N), i32(Ho), i32(Wo),
+                   i32(c1.shape[-1]), L.stream())
+            self.stages = []
+            C = []
+            for name in bb.res_layers:
+                recs = []
+                for blk in getattr(bb, name):
+                    x, rec = self._block_fwd(x, blk)
+                    recs.append(rec)
+                self.stages.append(recs)
+                C.append(x)
+            self.C = C
+            # FPN: laterals top-down (the upsample-add rides in the lateral's epilogue), 3x3 outs
+            n = len(neck._lat)
+            lat = [None] * n
+            for i in range(n - 1, -1, -1):
+                sp = neck._lat[i]
+                Ni, Hi, Wi, Ci = C[i].shape
+                lat[i] = self.buf(Ni, Hi, Wi, neck.out_channels)
+                res = lat[i + 1] if i < n - 1 else None
+                if res is not None:
+                    assert Hi == 2 * res.shape[1] and Wi == 2 * res.shape[2], \
+                        'FPN levels must differ by exactly 2x (pad inputs to a multiple of 32)'
+                self.gemm_f(C[i], sp.wref.w, lat[i], Ni * Hi * Wi, Ci, neck.out_channels, Hi, Wi,
+                            shift=sp.bias, residual=res, ldr=neck.out_channels,
+                            res_upsample2x=1 if res is not None else 0, round_out=True)
+            outs = []
+            for i in range(n):
+                sp = neck._out[i]
+                o = self.buf(*lat[i].shape)
+                self.conv3_f(lat[i], sp.wref.w, o, shift=sp.bias, round_out=True)
+                outs.append(o)
+            while len(outs) < neck.num_outs:
+                src = outs[-1]
+                Ns, Hs, Ws, Cs = src.shape
+                o = self.buf(Ns, (Hs + 1) // 2, (Ws + 1) // 2, Cs)
+                L.call('subsample2', L.ptr(src), L.ptr(o), i32(Ns), i32(Hs), i32(Ws), i32(Cs),
+                       L.stream())
+                outs.append(o)
+            self.lat, self.P = lat, outs
+            # RPN: shared 3x3 conv + ReLU, fused cls/reg 1x1 head, per level
+            cs, hs = rpn._conv_spec, rpn._head_spec
+            self.rpn_t, self.rpn_out = [], []
+            Wd = hs.wref.w.shape[0]
+            for f in outs:
+                Nf, Hf, Wf, Cf = f.shape
+                t = self.buf(Nf, Hf, Wf, cs.wref.w.shape[0])
+                self.conv3_f(f, cs.wref.w, t, shift=cs.bias, relu=True, round_out=True)
+                o = self.buf(Nf, Hf, Wf, Wd)
+                self.gemm_f(t, hs.wref.w, o, Nf * Hf * Wf, t.shape[-1], Wd, Hf, Wf, shift=hs.bias,
+                            round_out=False)
+                self.rpn_t.append(t)
+                self.rpn_out.append(o)
+        self.fwd_ready = True
+
+    # ---------------------------------------------------------------- backward program
+    def _block_bwd(self, rec, g, prev=None):
+        """g = dL/d(pre-ReLU block output), already masked by (out > 0).  Launches the block's
+        weight gradients and the data gradients down to conv1's input.  With `prev` (the block
+        producing this block's input, same stage, so no downsample here) it also returns
+        dL/d(input) = (x > 0) * (conv1 dgrad + g over the identity path), accumulating prev's
+        beta gradients on the way; otherwise returns None and leaves rec['_dz1'] for the caller."""
+        blk = rec['blk']
+        s1, s2, s3, sd = blk._s1, blk._s2, blk._s3, blk._sd
+        x, xs, h1, h2, col = rec['x'], rec['xs'], rec['h1'], rec['h2'], rec['col']
+        N, H, W, Ci = x.shape
+        _, Ho, Wo, p = h2.shape
+        P1, P3 = N * H * W, N * Ho * Wo
+        # conv3 (1x1)
+        self.gemm_w(g, h2, s3.wref.grad, P3, p, 4 * p)
+        dz2 = self.buf(N, Ho, Wo, p)
+        self.gemm_d(g, s3.wref.w, dz2, P3, p, 4 * p, mask=h2, colsum=s2.bias_grad, round_out=True)
+        # conv2 (3x3, stride 1 direct / stride 2 through im2col)
+        dz1 = self.buf(N, H, W, p)
+        if rec['stride'] == 1:
+            self.conv3_w(dz2, h1, s2.wref.grad)
+            self.conv3_d(dz2, s2.wref.w, dz1, mask=h1, colsum=s1.bias_grad, round_out=True)
+        else:
+            self.gemm_w(dz2, col, s2.wref.grad, P3, 9 * p, p)
+            dcol = self.buf(P3, 9 * p)
+            self.gemm_d(dz2, s2.wref.w, dcol, P3, 9 * p, p)
+            L.call('col2im', L.ptr(dcol), L.ptr(dz1), L.ptr(h1), i32(N), i32(H), i32(W), i32(p),
+                   i32(3), i32(3), i32(rec['stride']), i32(1), i32(9 * p), L.stream())
+            self.colsum(dz1, P1, p, s1.bias_grad)
+        # conv1 (1x1) and the downsample branch
+        self.gemm_w(dz1, x, s1.wref.grad, P1, Ci, p)
+        if sd is not None:
+            self.gemm_w(g, xs, sd.wref.grad, P3, Ci, 4 * p)
+        rec['_dz1'] = dz1
+        if prev is None:
+            return None
+        assert sd is None, 'only the first block of a stage may have a downsample branch'
+        dx = self.buf(N, H, W, Ci)
+        self.gemm_d(dz1, s1.wref.w, dx, P1, Ci, p, residual=g, ldr=Ci, mask=x,
+                    colsum=prev._s3.bias_grad,
+                    colsum2=prev._sd.bias_grad if prev._sd is not None else None, round_out=True)
+        return dx
+
+    def build_backward(self):
+        m = self.model
+        bb, neck, rpn = m.backbone, m.neck, m.rpn_head
+        dev = self.dev
+        nlev = len(self.P)
+        n = len(self.lat)
+        with self.bwd:
+            cs, hs = rpn._conv_spec, rpn._head_spec
+            Wd = hs.wref.w.shape[0]
+            Cr = cs.wref.w.shape[0]
+            # narrow-head weight gradient: dW[Wd,Cr] = gR^T t through 32-column padded copies
+            wtmp = self.buf(32, Cr)
+            L.call('fill', L.ptr(wtmp), L.ll(wtmp.numel()), L.f32(0.0), L.stream())
+            gtot = [None] * nlev
+            carry = None                       # gradient handed down from an extra (subsampled) level
+            for l in range(nlev - 1, -1, -1):
+                f, t, gR = self.P[l], self.rpn_t[l], self.gR[l]
+                Nf, Hf, Wf, Cf = f.shape
+                Pl = Nf * Hf * Wf
+                self.colsum(gR, Pl, Wd, hs.bias_grad)
+                pad = torch.zeros((Pl, 32), device=dev)
+                self.keep.append(pad)
+                L.call('copy2d', L.ptr(gR), L.ll(Wd), L.ptr(pad), L.ll(32), L.ll(Pl), i32(Wd),
+                       i32(0), i32(0), L.stream())
+                self.gemm_w(pad, t, wtmp, Pl, Cr, 32)
+                dt = self.buf(Nf, Hf, Wf, Cr)
+                self.gemm_d(gR, hs.wref.w, dt, Pl, Cr, Wd, mask=t, colsum=cs.bias_grad,
+                            round_out=True)
+                self.conv3_w(dt, f, cs.wref.grad)
+                res = self.gP[l]
+                if carry is not None:
+                    Nc, Hc, Wc, Cc = carry.shape
+                    u = self.buf(Nf, Hf, Wf, Cf)
+                    L.call('subsample2_bwd', L.ptr(carry), L.ptr(u), None, i32(Nf), i32(Hf),
+                           i32(Wf), i32(Cf), L.stream())
+                    r2 = self.buf(Nf, Hf, Wf, Cf)
+                    L.call('add', L.ptr(res), L.ptr(u), L.ptr(r2), L.ll(r2.numel()), i32(0),
+                           L.stream())
+                    res = r2
+                g = self.buf(Nf, Hf, Wf, Cf)
+                self.conv3_d(dt, cs.wref.w, g, residual=res, ldr=Cf,
+                             colsum=(neck._out[l].bias_grad if l < n else None), round_out=True)
+                gtot[l] = g
+                carry = g if l >= n else None
+            L.call('copy2d', L.ptr(wtmp), L.ll(Cr), L.ptr(hs.wref.grad), L.ll(Cr), L.ll(Wd), i32(Cr),
+                   i32(1), i32(0), L.stream())
+            # FPN 3x3 output convs, fine -> coarse (the top-down path's gradient flows that way)
+            dlat = [None] * n
+            for l in range(n):
+                sp = neck._out[l]
+                self.conv3_w(gtot[l], self.lat[l], sp.wref.grad)
+                d = self.buf(*self.lat[l].shape)
+                self.conv3_d(gtot[l], sp.wref.w, d,
+                             colsum=(neck._lat[0].bias_grad if l == 0 else None), round_out=True)
+                if l == 0:
+                    dlat[0] = d
+                else:
+                    Nl, Hl, Wl, Cl = d.shape
+                    dl = self.buf(Nl, Hl, Wl, Cl)
+                    L.call('sum2x2_add', L.ptr(dlat[l - 1]), L.ptr(d), L.ptr(dl), i32(Nl), i32(Hl),
+                           i32(Wl), i32(Cl), L.stream())
+                    self.colsum(dl, Nl * Hl * Wl, Cl, neck._lat[l].bias_grad)
+                    dlat[l] = dl
+            for l in range(n):
+                Nl, Hl, Wl, Cc = self.C[l].shape
+                self.gemm_w(dlat[l], self.C[l], neck._lat[l].wref.grad, Nl * Hl * Wl, Cc,
+                            neck.out_channels)
+            # ResNet stages, top down.  The gradient of stage output C[s] is
+            #   (C[s] > 0) * (lateral dgrad + next stage's conv1 dgrad + its strided-downsample dgrad)
+            # assembled by chaining epilogue residuals, never by a separate add / mask pass.
+            g = None
+            for s in range(len(self.stages) - 1, -1, -1):
+                recs = self.stages[s]
+                if not recs[0]['blk']._trainable:
+                    break
+                last = recs[-1]['blk']
+                ldb = last._s3.bias_grad
+                ldb2 = last._sd.bias_grad if last._sd is not None else None
+                Ns, Hs, Ws, Cc = self.C[s].shape
+                Ps = Ns * Hs * Ws
+                if s == len(self.stages) - 1:
+                    g = self.buf(Ns, Hs, Ws, Cc)
+                    self.gemm_d(dlat[s], neck._lat[s].wref.w, g, Ps, Cc, neck.out_channels,
+                                mask=self.C[s], colsum=ldb, colsum2=ldb2, round_out=True)
+                # else: g was produced by the block-0 backward of stage s+1 (below)
+                for bi in range(len(recs) - 1, -1, -1):
+                    rec = recs[bi]
+                    if bi > 0:
+                        g = self._block_bwd(rec, g, prev=recs[bi - 1]['blk'])
+                    else:
+                        self._block_bwd(rec, g)
+                        below = s > 0 and self.stages[s - 1][0]['blk']._trainable
+                        g = self._stage_boundary_bwd(rec, g, s - 1, dlat[s - 1]) if below else None
+        self.bwd_ready = True
+
+    def _stage_boundary_bwd(self, rec, g, s_in, dlat_in):
+        """Block 0 of a stage (after _block_bwd): its input C[s_in] also feeds FPN lateral s_in.
+        Returns the masked gradient of C[s_in] (= the `g` of stage s_in's last block) and
+        accumulates that block's beta gradient:
+            t  = dgrad of the (strided) downsample 1x1            [half resolution]
+            u  = lateral dgrad + zero-stuffed t                   [epilogue residual]
+            dx = (x > 0) * (conv1 dgrad + u)                      [epilogue residual + mask]"""
+        neck = self.model.neck
+        blk = rec['blk']
+        s1, sd = blk._s1, blk._sd
+        x, h2, dz1 = rec['x'], rec['h2'], rec['_dz1']
+        N, H, W, Ci = x.shape
+        _, Ho, Wo, p = h2.shape
+        P1, P3 = N * H * W, N * Ho * Wo
+        prev = self.stages[s_in][-1]['blk']
+        assert sd is not None and sd.stride in (1, 2)
+        t = self.buf(N, Ho, Wo, Ci)
+        self.gemm_d(g, sd.wref.w, t, P3, Ci, 4 * p)
+        u = self.buf(N, H, W, Ci)
+        self.gemm_d(dlat_in, neck._lat[s_in].wref.w, u, P1, Ci, neck.out_channels, H, W,
+                    residual=t, ldr=Ci, res_upsample2x=(2 if sd.stride == 2 else 0))
+        dx = self.buf(N, H, W, Ci)
+        self.gemm_d(dz1, s1.wref.w, dx, P1, Ci, p, residual=u, ldr=Ci, mask=x,
+                    colsum=prev._s3.bias_grad,
+                    colsum2=prev._sd.bias_grad if prev._sd is not None else None, round_out=True)
+        return dx
+
+
+class _TrunkFn(Function):
+    """(img, trainable parameters as autograd triggers) -> (FPN maps..., fused RPN maps...)."""
+
+    @staticmethod
+    def forward(ctx, img, trunk, *params):
+        prog = trunk.run_forward(img)
+        ctx.prog, ctx.trunk = prog, trunk
+        outs = [t.permute(0, 3, 1, 2) for t in prog.P] + \
+               [t.permute(0, 3, 1, 2) for t in prog.rpn_out]
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        prog = ctx.prog
+        ctx.trunk.store.queue_finalize()
+        for buf, g in zip(prog.gP + prog.gR, grads):
+            if g is None:
+                buf.zero_()
+            else:
+                buf.copy_(g.permute(0, 2, 3, 1))
+        if not prog.bwd_ready:
+            prog.build_backward()              # executes the program once while recording it
+            if prog.use_graph:
+                prog.bwd.capture()
+        else:
+            prog.bwd.launch()
+        return (None,) * len(ctx.needs_input_grad)
+
+
+class Trunk:
+    """Per-model manager: one recorded program pair per input shape (at most two shapes cached)."""
+
+    def __init__(self, model, store):
+        self.model, self.store = model, store
+        self.progs = {}
+        self.params = [p for mod in (model.backbone, model.neck, model.rpn_head)
+                       for p in mod.parameters() if p.requires_grad]
+
+    @staticmethod
+    def eligible(model):
+        from .models.backbones.resnet import Bottleneck, ResNet
+        from .models.dense_heads.rpn_head import RPNHead
+        from .models.necks.fpn import FPN
+        if os.environ.get('LOFT_TRUNK', '1') == '0':
+            return False
+        bb, neck, rpn = getattr(model, 'backbone', None), getattr(model, 'neck', None), \
+            getattr(model, 'rpn_head', None)
+        if type(bb) is not ResNet or type(neck) is not FPN or type(rpn) is not RPNHead:
+            return False
+        if bb.style != 'pytorch' or neck.start_level != 0 or \
+                len(neck.lateral_convs) != len(bb.res_layers) or \
+                tuple(bb.out_indices) != tuple(range(len(bb.res_layers))):
+            return False
+        return all(isinstance(b, Bottleneck) for n in bb.res_layers for b in getattr(bb, n))
+
+    def run_forward(self, img):
+        N, _, H, W = img.shape
+        key = (N, H, W, torch.is_grad_enabled())
+        prog = self.progs.get(key)
+        if prog is None:
+            if len(self.progs) >= 2:
+                self.progs.pop(next(iter(self.progs)))
+            prog = self.progs[key] = _Program(self.model, N, H, W, self.store.device, True)
+        prog.img.copy_(img)
+        if not prog.fwd_ready:
+            prog.build_forward()
+            prog.gP = [torch.zeros_like(f) for f in prog.P]
+            prog.gR = [torch.zeros_like(o) for o in prog.rpn_out]
+            if prog.use_graph:
+                prog.fwd.capture()
+        else:
+            prog.fwd.launch()
+        return prog
+
+    def __call__(self, img):
+        outs = _TrunkFn.apply(img, self, *self.params)
+        n = len(outs) // 2
+        return tuple(outs[:n]), list(outs[n:])

@@ -99,6 +99,7 @@ void loft_debug_set_desc(long long a_desc, long long b_desc, long long a_kstep, 
  * top-down backward: fpn.py:185-199; FOA rotation: offset_head_expand_feature.py:163-196
  * (affine_grid+grid_sample == rot90); optimizer: mmcv OptimizerHook(grad_clip) +
  * torch.optim.SGD as configured by configs/_base_/schedules/schedule_2x_bonai.py:2-3. */
+int loft_fill(float* p, long long n, float v, cudaStream_t stream);
 int loft_copy2d(const float* src, long long lds, float* dst, long long ldd, long long rows, int cols,
                 int accumulate, int round_tf32, cudaStream_t stream);
 int loft_permute_acb(const float* src, float* dst, int A, int B, int C, int accumulate,

@@ -278,3 +278,63 @@ def test_too_many_gt_is_a_loud_error():
     gts[:, 2:] += gts[:, :2] + 1
     with pytest.raises(LoftError):
         MaxIoUAssigner(0.5, 0.5).assign(boxes, gts)
+
+
+def test_recorded_trunk_graph_matches_module_path(monkeypatch):
+    """The static part of the step (ResNet + FPN + RPN convs) runs as two recorded CUDA-graph
+    programs (bonai_b200/trunk.py).  Over three SGD steps -- record, capture, replay -- it must
+    give the same losses, gradient norm and weights as the module-by-module autograd path."""
+    from bonai_b200 import Config
+    from bonai_b200.apis import Trainer
+    from bonai_b200.core import BitmapMasks
+    from bonai_b200.models import build_detector
+    from oracle import loft_cpu as O
+    cfg = Config.fromfile(os.path.join(ROOT, 'configs', 'loft', 'loft_foa_r50_fpn_2x_b200.py'))
+    p = O.randomize_bn(O.init_params(1), 1)
+    img, gb, gl, gm, go = O.make_inputs(1, 2, 256, 6)
+    metas = [dict(img_shape=(256, 256, 3), pad_shape=(256, 256, 3), scale_factor=1.0, flip=False)] * 2
+
+    # fixed proposals (jittered GT + random boxes): without them tiny score differences reorder
+    # the NMS output and the two runs sample different RoIs -- chaos, not error
+    from bonai_b200.models.dense_heads import RPNHead
+    g = torch.Generator().manual_seed(5)
+    props = []
+    for b in gb:
+        jit = b.repeat(20, 1) + torch.randn(b.shape[0] * 20, 4, generator=g) * 4
+        xy = torch.rand(150, 2, generator=g) * 200
+        wh = torch.rand(150, 2, generator=g) * 50 + 4
+        box = torch.cat([jit, torch.cat([xy, xy + wh], 1)]).clamp(0, 256)
+        props.append(torch.cat([box, torch.rand(box.shape[0], 1, generator=g)], 1))
+    monkeypatch.setattr(RPNHead, 'forced_proposals', props)
+
+    def run(trunk):
+        monkeypatch.setenv('LOFT_TRUNK', '1' if trunk else '0')
+        model = build_detector(cfg.model, train_cfg=cfg.train_cfg, test_cfg=cfg.test_cfg)
+        model.load_state_dict(p)
+        model.train()
+        trainer = Trainer(model, cfg, torch.device('cuda:0'))
+        data = dict(img=img.cuda(), img_metas=metas, gt_bboxes=gb, gt_labels=gl,
+                    gt_masks=[BitmapMasks(m, 256, 256) for m in gm], gt_offsets=go)
+        out = []
+        for it in range(3):
+            torch.manual_seed(100 + it)
+            logs = trainer.train_step(data, read_logs=True)
+            out.append((logs, float(trainer.store.grad_norm())))
+        assert (model.__dict__.get('_trunk') is not None) == trunk
+        if trunk:
+            prog = next(iter(model._trunk.progs.values()))
+            assert prog.fwd.graph is not None and prog.bwd.graph is not None
+        w = {k: v.detach().float().cpu().clone() for k, v in model.state_dict().items()
+             if v.dtype == torch.float32}
+        return out, w
+
+    a, wa = run(True)
+    b, wb = run(False)
+    for (la, na), (lb, nb) in zip(a, b):
+        for k in lb:
+            if 'loss' in k:
+                assert abs(la[k] - lb[k]) <= 2e-3 * max(abs(lb[k]), 1e-3), (k, la[k], lb[k])
+        assert abs(na - nb) <= 2e-2 * nb, (na, nb)
+    for k in wb:
+        d = float((wa[k] - wb[k]).norm())
+        assert d <= 2e-2 * float(wb[k].norm()) + 1e-6, (k, d)

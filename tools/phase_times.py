@@ -1,4 +1,5 @@
-"""Per-phase GPU (CUDA events) and host (wall) time of one training step, to find host-bound phases."""
+"""Host (wall) vs GPU (CUDA events) time of one training step, split at the forward/backward
+boundary, to see whether the launch thread or the GPU bounds the step."""
 import os, sys, time, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -14,7 +15,7 @@ model.train()
 dev = torch.device('cuda:0')
 trainer = Trainer(model, cfg, dev)
 data = bench.to_model_inputs(bench.make_batch(0, device=dev))
-for _ in range(3):
+for _ in range(5):
     trainer.train_step(data)
 torch.cuda.synchronize()
 
@@ -28,8 +29,7 @@ def wrap(obj, meth, name):
         mark(name + ':begin'); r = f(*a, **k); mark(name + ':end'); return r
     setattr(obj, meth, g)
 
-wrap(model, 'extract_feat', 'extract_feat')
-wrap(model.rpn_head, 'forward', 'rpn_fwd')
+wrap(model, 'forward_train', 'forward')
 wrap(model.rpn_head, 'loss', 'rpn_loss')
 wrap(model.rpn_head, 'get_bboxes', 'rpn_proposals')
 wrap(model.roi_head, 'assign_and_sample', 'rcnn_sample')
@@ -37,23 +37,21 @@ wrap(model.roi_head, '_bbox_forward_train', 'bbox_branch')
 wrap(model.roi_head, '_mask_forward_train', 'mask_branch')
 wrap(model.roi_head, '_offset_forward_train', 'offset_branch')
 wrap(trainer.store, 'sgd_step', 'sgd')
-wrap(trainer.store, 'begin_step', 'begin_step')
-for it in range(2):
+for it in range(3):
     marks.clear()
     torch.cuda.synchronize()
     mark('step:begin')
     trainer.train_step(data)
     mark('step:end')
     torch.cuda.synchronize()
-print(f'{"phase":22s} {"gpu_ms":>8s} {"host_ms":>8s}')
-d = {n: (e, t) for n, e, t in marks}
-names = []
-for n, _, _ in marks:
-    b = n.split(':')[0]
-    if b not in names: names.append(b)
-for b in names:
-    e0, t0 = d[b + ':begin']; e1, t1 = d[b + ':end']
-    print(f'{b:22s} {e0.elapsed_time(e1):8.3f} {(t1 - t0) * 1e3:8.3f}')
-# backward = from offset_branch:end to sgd:begin
-e0, t0 = d['offset_branch:end']; e1, t1 = d['sgd:begin']
-print(f'{"loss-sum+backward":22s} {e0.elapsed_time(e1):8.3f} {(t1 - t0) * 1e3:8.3f}')
+    d = {n: (e, t) for n, e, t in marks}
+    names = []
+    for n, _, _ in marks:
+        b = n.split(':')[0]
+        if b not in names: names.append(b)
+    print(f'--- iteration {it}\n{"phase":22s} {"gpu_ms":>8s} {"host_ms":>8s}')
+    for b in names:
+        e0, t0 = d[b + ':begin']; e1, t1 = d[b + ':end']
+        print(f'{b:22s} {e0.elapsed_time(e1):8.3f} {(t1 - t0) * 1e3:8.3f}')
+    e0, t0 = d['forward:end']; e1, t1 = d['sgd:begin']
+    print(f'{"loss-sum+backward":22s} {e0.elapsed_time(e1):8.3f} {(t1 - t0) * 1e3:8.3f}')
