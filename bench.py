@@ -152,7 +152,7 @@ def roofline_probe(model, device, pk):
     return dict(bound='tensor', kernel='loft_gemm_tf32_kernel (FPROP_CONV 131072x2304x256)',
                 achieved=round(achieved, 1), peak=pk['tensor'], unit='TFLOP/s',
                 frac=round(achieved / pk['tensor'], 4),
-                traffic=228.55e6,   # dram read+write bytes/launch, profiles/r01_ncu_gemm_fprop_p2.txt
+                traffic=225.73e6,   # dram read+write bytes/launch, profiles/r01_ncu_gemm_fprop_p2_v6.txt
                 algorithmic_bytes=2 * N * H * W * C * 4 + 9 * C * C * 4,
                 peak_source=f"{pk['source']} bf16 dense burst; TF32 operands run at half that rate",
                 frac_of_tf32_half_peak=round(achieved / (pk['tensor'] / 2), 4),
@@ -242,7 +242,7 @@ def main():
                     help='GT boxes per tile: 80 = BONAI mean (init-like, P~100/img), 256 = '
                          'steady-state-like (P=256/img), SURVEY 8(d)')
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl != 'reference' else args.warmup
+    args.warmup = max(args.warmup, 10) if args.impl != 'reference' else args.warmup
     globals()['NUM_GT'] = args.num_gt
     if args.impl == 'reference':
         return run_reference(args)
@@ -290,6 +290,10 @@ def main():
     sync_all()
     launches = L.LAUNCHES[0]
     ms = e0.elapsed_time(e1)
+    if getattr(trainer, '_comm_events', None):
+        ts = [a.elapsed_time(b) for a, b in trainer._comm_events[-args.steps:]]
+        print(f'[rank {rank}] grad all-reduce ms/step: mean {sum(ts) / len(ts):.3f} min {min(ts):.3f} '
+              f'max {max(ts):.3f}; step {ms / args.steps:.3f}', file=sys.stderr)
     clk = clocks.stop() if rank == 0 else None
     logs = trainer.read_logs()
     n_pos = sum(s.pos_bboxes.shape[0] for s in model.roi_head._last_sampling_results)

@@ -187,7 +187,14 @@ class Trainer:
         log_vars['loss'] = loss
         loss.backward()
         if self.distributed:
-            allreduce_flat(self.store.G, bucket_bytes=self.bucket_bytes)
+            if os.environ.get('LOFT_TIME_COMM'):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                allreduce_flat(self.store.G, bucket_bytes=self.bucket_bytes)
+                e1.record()
+                self.__dict__.setdefault('_comm_events', []).append((e0, e1))
+            else:
+                allreduce_flat(self.store.G, bucket_bytes=self.bucket_bytes)
         self.store.sgd_step(self.current_lr(), self.momentum, self.weight_decay, self.max_norm,
                             grad_scale=1.0 / self.world)
         self.iter += 1

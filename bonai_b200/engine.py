@@ -147,6 +147,7 @@ class ParamStore:
                 if b is not None:
                     m._buffers[k] = b.to(dev)
         self.packed = []
+        self.pre_finalize = []           # callables run at the start of finalize_grads
         self._fold_pairs = []
         for m in model.modules():
             if hasattr(m, 'loft_prepare'):
@@ -282,6 +283,8 @@ class ParamStore:
             self._w_pending = False
 
     def finalize_grads(self):
+        for fn in self.pre_finalize:
+            fn()
         self.join_wgrad_stream()
         self._bn_finalize()
         for pk in self.packed:

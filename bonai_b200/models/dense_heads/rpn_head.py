@@ -139,13 +139,15 @@ class RPNHead(nn.Module):
         return cls, reg
 
     def forward_train(self, x, img_metas, gt_bboxes, gt_labels=None, gt_bboxes_ignore=None,
-                      proposal_cfg=None, rpn_outs=None, **kwargs):
+                      proposal_cfg=None, rpn_outs=None, after_loss=None, **kwargs):
         outs = rpn_outs if rpn_outs is not None else self(x)
         if gt_labels is None:
             loss_inputs = outs + (gt_bboxes, img_metas)
         else:
             loss_inputs = outs + (gt_bboxes, gt_labels, img_metas)
         losses = self.loss(*loss_inputs, gt_bboxes_ignore=gt_bboxes_ignore)
+        if after_loss is not None:
+            losses = after_loss(losses)
         if proposal_cfg is None:
             return losses
         return losses, self.get_bboxes(*outs, img_metas, cfg=proposal_cfg)

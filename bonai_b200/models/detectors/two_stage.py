@@ -79,23 +79,30 @@ class TwoStageDetector(BaseDetector):
         for k, v in list(kwargs.items()):
             if isinstance(v, (list, tuple)) and len(v) and isinstance(v[0], torch.Tensor):
                 kwargs[k] = [t.to(dev, non_blocking=True) for t in v]
-        if self.with_rpn and hasattr(self.rpn_head, 'prefetch_targets') and len(gt_bboxes) > 0:
-            self.rpn_head.prefetch_targets(gt_bboxes, img_metas, img.shape[-2:], ready_event)
-        # static part (backbone + FPN + RPN convs): two recorded CUDA-graph programs when the
-        # model is the R50-FPN-RPN composition (bonai_b200.trunk), else module by module
+        # static part (backbone + FPN + RPN convs): recorded CUDA-graph programs when the model is
+        # the R50-FPN-RPN composition (bonai_b200.trunk), else module by module.  The RPN targets
+        # (assignment + sampling, several host syncs) are built on a side stream: with the trunk
+        # they are issued AFTER the one-launch forward graph so the syncs hide under it.
         rpn_outs = None
         trunk = self._loft_trunk(store) if torch.is_grad_enabled() else None
+        prefetch = self.with_rpn and hasattr(self.rpn_head, 'prefetch_targets') and \
+            len(gt_bboxes) > 0
         if trunk is not None:
             x, fused = trunk(img)
             rpn_outs = self.rpn_head.outs_from_fused(fused)
+            if prefetch:
+                self.rpn_head.prefetch_targets(gt_bboxes, img_metas, img.shape[-2:], ready_event)
         else:
+            if prefetch:
+                self.rpn_head.prefetch_targets(gt_bboxes, img_metas, img.shape[-2:], ready_event)
             x = self.extract_feat(img)
         losses = dict()
         if self.with_rpn:
             proposal_cfg = self.train_cfg.get('rpn_proposal', self.test_cfg.rpn)
             rpn_losses, proposal_list = self.rpn_head.forward_train(
                 x, img_metas, gt_bboxes, gt_labels=None, gt_bboxes_ignore=gt_bboxes_ignore,
-                proposal_cfg=proposal_cfg, rpn_outs=rpn_outs)
+                proposal_cfg=proposal_cfg, rpn_outs=rpn_outs,
+                after_loss=trunk.early_rpn_backward if trunk is not None else None)
             losses.update(rpn_losses)
         else:
             proposal_list = proposals

@@ -89,7 +89,9 @@ class _Program:
         self.model, self.N, self.H, self.W, self.dev, self.train = model, N, H, W, dev, train
         self.img = torch.empty((N, 3, H, W), device=dev, dtype=torch.float32)
         self.fwd, self.bwd = Tape('trunk_forward_graph'), Tape('trunk_backward_graph')
-        self.fwd_ready = self.bwd_ready = False
+        self.bwd_rpn = Tape('trunk_rpn_backward_graph')
+        self.fwd_ready = self.bwd_ready = self.bwd_rpn_ready = False
+        self.rpn_done, self.rpn_event = False, None
         self.use_graph = os.environ.get('LOFT_GRAPH', '1') != '0'
         self.keep = []
 
@@ -285,22 +287,21 @@ class _Program:
                     colsum2=prev._sd.bias_grad if prev._sd is not None else None, round_out=True)
         return dx
 
-    def build_backward(self):
-        m = self.model
-        bb, neck, rpn = m.backbone, m.neck, m.rpn_head
+    def build_backward_rpn(self):
+        """RPN part of the backward (needs only the RPN losses' gradient gR): fused-head and shared
+        3x3 conv weight / bias gradients over all levels, and the gradient the RPN path sends into
+        each FPN map, written to self.B[l].  Runs early, on a side stream, while the launch thread
+        is busy with proposals / sampling (two_stage.forward_train)."""
+        rpn = self.model.rpn_head
         dev = self.dev
-        nlev = len(self.P)
-        n = len(self.lat)
-        with self.bwd:
+        with self.bwd_rpn:
             cs, hs = rpn._conv_spec, rpn._head_spec
             Wd = hs.wref.w.shape[0]
             Cr = cs.wref.w.shape[0]
             # narrow-head weight gradient: dW[Wd,Cr] = gR^T t through 32-column padded copies
             wtmp = self.buf(32, Cr)
             L.call('fill', L.ptr(wtmp), L.ll(wtmp.numel()), L.f32(0.0), L.stream())
-            gtot = [None] * nlev
-            carry = None                       # gradient handed down from an extra (subsampled) level
-            for l in range(nlev - 1, -1, -1):
+            for l in range(len(self.P)):
                 f, t, gR = self.P[l], self.rpn_t[l], self.gR[l]
                 Nf, Hf, Wf, Cf = f.shape
                 Pl = Nf * Hf * Wf
@@ -314,23 +315,31 @@ class _Program:
                 self.gemm_d(gR, hs.wref.w, dt, Pl, Cr, Wd, mask=t, colsum=cs.bias_grad,
                             round_out=True)
                 self.conv3_w(dt, f, cs.wref.grad)
-                res = self.gP[l]
-                if carry is not None:
-                    Nc, Hc, Wc, Cc = carry.shape
-                    u = self.buf(Nf, Hf, Wf, Cf)
-                    L.call('subsample2_bwd', L.ptr(carry), L.ptr(u), None, i32(Nf), i32(Hf),
-                           i32(Wf), i32(Cf), L.stream())
-                    r2 = self.buf(Nf, Hf, Wf, Cf)
-                    L.call('add', L.ptr(res), L.ptr(u), L.ptr(r2), L.ll(r2.numel()), i32(0),
-                           L.stream())
-                    res = r2
-                g = self.buf(Nf, Hf, Wf, Cf)
-                self.conv3_d(dt, cs.wref.w, g, residual=res, ldr=Cf,
-                             colsum=(neck._out[l].bias_grad if l < n else None), round_out=True)
-                gtot[l] = g
-                carry = g if l >= n else None
+                self.conv3_d(dt, cs.wref.w, self.B[l])
             L.call('copy2d', L.ptr(wtmp), L.ll(Cr), L.ptr(hs.wref.grad), L.ll(Cr), L.ll(Wd), i32(Cr),
                    i32(1), i32(0), L.stream())
+        self.bwd_rpn_ready = True
+
+    def build_backward(self):
+        """Everything below the FPN maps.  self.B[l] holds the TOTAL gradient of FPN map l (RPN
+        path from build_backward_rpn + what the RoI heads sent, added by _TrunkFn.backward)."""
+        m = self.model
+        bb, neck, rpn = m.backbone, m.neck, m.rpn_head
+        nlev = len(self.P)
+        n = len(self.lat)
+        with self.bwd:
+            gtot = self.B
+            # extra levels (P6 = P5-out subsampled): fold their gradient into the level below
+            for l in range(nlev - 1, n - 1, -1):
+                Nf, Hf, Wf, Cf = self.P[l - 1].shape
+                u = self.buf(Nf, Hf, Wf, Cf)
+                L.call('subsample2_bwd', L.ptr(gtot[l]), L.ptr(u), None, i32(Nf), i32(Hf), i32(Wf),
+                       i32(Cf), L.stream())
+                L.call('add', L.ptr(gtot[l - 1]), L.ptr(u), L.ptr(gtot[l - 1]),
+                       L.ll(u.numel()), i32(1), L.stream())
+            for l in range(n):
+                Nf, Hf, Wf, Cf = self.P[l].shape
+                self.colsum(gtot[l], Nf * Hf * Wf, Cf, neck._out[l].bias_grad)
             # FPN 3x3 output convs, fine -> coarse (the top-down path's gradient flows that way)
             dlat = [None] * n
             for l in range(n):
@@ -421,30 +430,30 @@ class _TrunkFn(Function):
 
     @staticmethod
     def backward(ctx, *grads):
-        prog = ctx.prog
-        ctx.trunk.store.queue_finalize()
-        for buf, g in zip(prog.gP + prog.gR, grads):
-            if g is None:
-                buf.zero_()
-            else:
-                buf.copy_(g.permute(0, 2, 3, 1))
-        if not prog.bwd_ready:
-            prog.build_backward()              # executes the program once while recording it
-            if prog.use_graph:
-                prog.bwd.capture()
-        else:
-            prog.bwd.launch()
+        prog, trunk = ctx.prog, ctx.trunk
+        trunk.store.queue_finalize()
+        n = len(prog.P)
+        if not prog.rpn_done:
+            # the RPN losses were not back-propagated early: their gradient arrives here
+            trunk.run_rpn_backward(prog, grads[n:], side=False)
+        trunk.run_main_backward(prog, grads[:n])
         return (None,) * len(ctx.needs_input_grad)
 
 
 class Trunk:
-    """Per-model manager: one recorded program pair per input shape (at most two shapes cached)."""
+    """Per-model manager: one recorded program set per input shape (at most two shapes cached)."""
 
     def __init__(self, model, store):
         self.model, self.store = model, store
         self.progs = {}
         self.params = [p for mod in (model.backbone, model.neck, model.rpn_head)
                        for p in mod.parameters() if p.requires_grad]
+        self.side = torch.cuda.Stream(device=store.device)
+        # measured on B200: no gain (the bubbles it should fill are spread over the whole RoI-head
+        # phase, the RPN backward is done 1.5 ms after it starts) -- off unless LOFT_EARLY_RPN=1
+        self.early_rpn = os.environ.get('LOFT_EARLY_RPN', '0') != '0'
+        self.current = None
+        store.pre_finalize.append(self.flush)
 
     @staticmethod
     def eligible(model):
@@ -465,7 +474,7 @@ class Trunk:
 
     def run_forward(self, img):
         N, _, H, W = img.shape
-        key = (N, H, W, torch.is_grad_enabled())
+        key = (N, H, W)
         prog = self.progs.get(key)
         if prog is None:
             if len(self.progs) >= 2:
@@ -474,15 +483,88 @@ class Trunk:
         prog.img.copy_(img)
         if not prog.fwd_ready:
             prog.build_forward()
-            prog.gP = [torch.zeros_like(f) for f in prog.P]
-            prog.gR = [torch.zeros_like(o) for o in prog.rpn_out]
+            prog.B = [torch.zeros_like(f) for f in prog.P]          # total gradient of FPN map l
+            prog.gR = [torch.zeros_like(o) for o in prog.rpn_out]   # gradient of fused RPN map l
             if prog.use_graph:
                 prog.fwd.capture()
         else:
             prog.fwd.launch()
+        prog.rpn_done = False
+        self.current = prog
         return prog
+
+    def run_rpn_backward(self, prog, grads, side):
+        for buf, g in zip(prog.gR, grads):
+            if g is None:
+                buf.zero_()
+            else:
+                buf.copy_(g.permute(0, 2, 3, 1))
+        main = torch.cuda.current_stream(self.store.device)
+        if side:
+            self.side.wait_stream(main)
+            ctx = torch.cuda.stream(self.side)
+        else:
+            import contextlib
+            ctx = contextlib.nullcontext()
+        with ctx:
+            if not prog.bwd_rpn_ready:
+                prog.build_backward_rpn()          # executes the program once while recording it
+                if prog.use_graph:
+                    prog.bwd_rpn.capture()
+            else:
+                prog.bwd_rpn.launch()
+            if side:
+                prog.rpn_event = self.side.record_event()
+        prog.rpn_done = True
+
+    def run_main_backward(self, prog, grads):
+        main = torch.cuda.current_stream(self.store.device)
+        if prog.rpn_event is not None:
+            main.wait_event(prog.rpn_event)
+            prog.rpn_event = None
+        for buf, g in zip(prog.B, grads):
+            if g is not None:
+                gn = g.permute(0, 2, 3, 1)
+                if not gn.is_contiguous():
+                    gn = gn.contiguous()
+                L.call('add', L.ptr(buf), L.ptr(gn), L.ptr(buf), L.ll(buf.numel()), i32(1),
+                       L.stream())
+        if not prog.bwd_ready:
+            prog.build_backward()
+            if prog.use_graph:
+                prog.bwd.capture()
+        else:
+            prog.bwd.launch()
+        prog.rpn_done = False
+
+    def early_rpn_backward(self, losses):
+        """Back-propagate the RPN losses right after they are computed: the RPN part of the trunk
+        backward then runs on a side stream underneath the host-bound proposal / sampling phase.
+        Returns the same dict with detached values (the outer loss.backward() must not visit
+        them again)."""
+        prog = self.current
+        if prog is None or not self.early_rpn or not torch.is_grad_enabled():
+            return losses
+        terms = [t for v in losses.values() for t in (v if isinstance(v, (list, tuple)) else [v])]
+        if not any(t.requires_grad for t in terms):
+            return losses
+        total = terms[0]
+        for t in terms[1:]:
+            total = total + t
+        grads = torch.autograd.grad(total, self.rpn_outs, allow_unused=True)
+        self.run_rpn_backward(prog, grads, side=True)
+        return {k: ([t.detach() for t in v] if isinstance(v, (list, tuple)) else v.detach())
+                for k, v in losses.items()}
+
+    def flush(self):
+        """Called before gradient finalisation: if the RPN part ran early but nothing reached the
+        FPN maps from the RoI heads, the main backward still has to run."""
+        prog = self.current
+        if prog is not None and prog.rpn_done:
+            self.run_main_backward(prog, [None] * len(prog.P))
 
     def __call__(self, img):
         outs = _TrunkFn.apply(img, self, *self.params)
         n = len(outs) // 2
-        return tuple(outs[:n]), list(outs[n:])
+        self.rpn_outs = list(outs[n:])
+        return tuple(outs[:n]), self.rpn_outs
