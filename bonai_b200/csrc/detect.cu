@@ -262,6 +262,165 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, int n, int nwords, 
   if (t == 0) num_keep[img] = s_count;
 }
 
+
+// ---------------------------------------------------------------- segmented (per-level) NMS
+// batched_nms never lets boxes of different idx suppress each other (their coordinates are
+// pushed (max+1) apart), so the 12 768 x 12 768 pair matrix of the RPN is block diagonal: one
+// block per FPN level.  Boxes arrive SEGMENT-MAJOR (all of level 0, then level 1, ...), each
+// segment sorted by score; `order` lists them in global score order.  Per segment: pair mask and
+// greedy scan (same kernels' arithmetic, same fp32 coordinate offset => identical decisions),
+// then one compaction pass walks the global order and emits the first max_keep kept boxes.
+constexpr int kMaxSeg = 16;
+struct SegTable {
+  int L;
+  int off[kMaxSeg + 1];        // box offsets of the segments
+  long long moff[kMaxSeg + 1]; // mask word offsets of the segments
+};
+
+__global__ void nms_mask_seg_kernel(const float* __restrict__ boxes, const float* __restrict__ maxc,
+                                    int n, float thr, unsigned long long* __restrict__ ws,
+                                    long long ws_stride_words, long long maxc_off_words,
+                                    const SegTable tab) {
+  const int s = blockIdx.z % tab.L, b = blockIdx.z / tab.L;
+  const int ks = tab.off[s + 1] - tab.off[s];
+  const int nw = (ks + 63) >> 6;
+  const int row = blockIdx.y, colb = blockIdx.x;
+  if (row >= nw || colb >= nw || colb < row) return;
+  unsigned long long* wsb = ws + (long long)b * ws_stride_words;
+  const float mx = *reinterpret_cast<const float*>(wsb + maxc_off_words);
+  (void)maxc;
+  const float off1 = __fadd_rn(mx, 1.f);
+  const float o = __fmul_rn((float)s, off1);
+  const float* bx = boxes + ((long long)b * n + tab.off[s]) * 4;
+  unsigned long long* mask = wsb + tab.moff[s];
+  __shared__ float sb[64][5];
+  const int t = threadIdx.x;
+  const int cj = colb * 64 + t;
+  if (cj < ks) {
+    const float x1 = __fadd_rn(bx[cj * 4 + 0], o), y1 = __fadd_rn(bx[cj * 4 + 1], o);
+    const float x2 = __fadd_rn(bx[cj * 4 + 2], o), y2 = __fadd_rn(bx[cj * 4 + 3], o);
+    sb[t][0] = x1;
+    sb[t][1] = y1;
+    sb[t][2] = x2;
+    sb[t][3] = y2;
+    sb[t][4] = __fmul_rn(__fsub_rn(x2, x1), __fsub_rn(y2, y1));
+  }
+  __syncthreads();
+  const int i = row * 64 + t;
+  if (i >= ks) return;
+  const float x1 = __fadd_rn(bx[i * 4 + 0], o), y1 = __fadd_rn(bx[i * 4 + 1], o);
+  const float x2 = __fadd_rn(bx[i * 4 + 2], o), y2 = __fadd_rn(bx[i * 4 + 3], o);
+  const float area = __fmul_rn(__fsub_rn(x2, x1), __fsub_rn(y2, y1));
+  unsigned long long bits = 0ull;
+  const int jstart = (row == colb) ? t + 1 : 0;
+  const int jend = min(64, ks - colb * 64);
+  for (int j = jstart; j < jend; ++j) {
+    const float w = fmaxf(0.f, __fsub_rn(fminf(x2, sb[j][2]), fmaxf(x1, sb[j][0])));
+    const float h = fmaxf(0.f, __fsub_rn(fminf(y2, sb[j][3]), fmaxf(y1, sb[j][1])));
+    const float inter = __fmul_rn(w, h);
+    const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area, sb[j][4]), inter));
+    if (iou > thr) bits |= 1ull << j;
+  }
+  mask[(long long)i * nw + colb] = bits;
+}
+
+// One block per (image, segment): the chunked greedy scan of nms_scan_kernel over the segment's
+// own mask; kept boxes are flagged at their segment-major position.
+__global__ void __launch_bounds__(kScanThreads)
+nms_scan_seg_kernel(unsigned long long* __restrict__ ws, long long ws_stride_words,
+                    long long keep_off_words, long long flag_off_words, int n, int max_keep,
+                    const SegTable tab) {
+  __shared__ unsigned long long diag[64];
+  __shared__ unsigned long long warp_or[kScanThreads / 32];
+  __shared__ int s_count;
+  const int s = blockIdx.x % tab.L, b = blockIdx.x / tab.L;
+  const int ks = tab.off[s + 1] - tab.off[s];
+  const int nw = (ks + 63) >> 6;
+  unsigned long long* wsb = ws + (long long)b * ws_stride_words;
+  const unsigned long long* mask = wsb + tab.moff[s];
+  int* keep = reinterpret_cast<int*>(wsb + keep_off_words) + tab.off[s];
+  unsigned char* flags = reinterpret_cast<unsigned char*>(wsb + flag_off_words) + tab.off[s];
+  const int lim_keep = min(max_keep, ks);
+  const int t = threadIdx.x;
+  if (t == 0) s_count = 0;
+  __syncthreads();
+  for (int c = 0; c < nw; ++c) {
+    const int cnt0 = s_count;
+    if (cnt0 >= lim_keep) break;
+    unsigned long long acc = 0ull;
+    for (int k = t; k < cnt0; k += kScanThreads) acc |= mask[(long long)keep[k] * nw + c];
+    if (t < 64) {
+      const int i = c * 64 + t;
+      diag[t] = (i < ks) ? mask[(long long)i * nw + c] : 0ull;
+    }
+    unsigned int lo = (unsigned int)acc, hi = (unsigned int)(acc >> 32);
+    lo = __reduce_or_sync(0xffffffffu, lo);
+    hi = __reduce_or_sync(0xffffffffu, hi);
+    if ((t & 31) == 0) warp_or[t >> 5] = ((unsigned long long)hi << 32) | lo;
+    __syncthreads();
+    if (t == 0) {
+      unsigned long long rem = 0ull;
+      for (int w = 0; w < kScanThreads / 32; ++w) rem |= warp_or[w];
+      int cnt = cnt0;
+      const int lim = min(64, ks - c * 64);
+      for (int bb = 0; bb < lim && cnt < lim_keep; ++bb) {
+        if (!((rem >> bb) & 1ull)) {
+          keep[cnt++] = c * 64 + bb;
+          rem |= diag[bb];
+        }
+      }
+      s_count = cnt;
+    }
+    __syncthreads();
+  }
+  const int cnt = s_count;
+  for (int k = t; k < cnt; k += kScanThreads) flags[keep[k]] = 1;
+}
+
+// One block per image: walk the global score order, keep[pos] = global rank of the pos-th kept box.
+__global__ void __launch_bounds__(1024)
+nms_compact_kernel(const unsigned long long* __restrict__ ws, long long ws_stride_words,
+                   long long flag_off_words, const long long* __restrict__ order, int n,
+                   int max_keep, long long* __restrict__ keep, int* __restrict__ num_keep) {
+  __shared__ int wsum[32];
+  __shared__ int s_base;
+  const int b = blockIdx.x, t = threadIdx.x;
+  const unsigned char* flags =
+      reinterpret_cast<const unsigned char*>(ws + (long long)b * ws_stride_words + flag_off_words);
+  const long long* ord = order + (long long)b * n;
+  long long* kp = keep + (long long)b * n;
+  if (t == 0) s_base = 0;
+  __syncthreads();
+  for (int g0 = 0; g0 < n; g0 += 1024) {
+    const int g = g0 + t;
+    const int f = (g < n) ? (int)flags[ord[g]] : 0;
+    int incl = f;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((t & 31) >= o) incl += v;
+    }
+    if ((t & 31) == 31) wsum[t >> 5] = incl;
+    __syncthreads();
+    if (t < 32) {
+      int v = wsum[t];
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, v, o);
+        if (t >= o) v += u;
+      }
+      wsum[t] = v;
+    }
+    __syncthreads();
+    const int base = s_base + ((t >> 5) ? wsum[(t >> 5) - 1] : 0);
+    const int pos = base + incl - f;
+    if (f && pos < max_keep) kp[pos] = g;
+    __syncthreads();
+    if (t == 1023) s_base = base + incl;
+    __syncthreads();
+    if (s_base >= max_keep) break;
+  }
+  if (t == 0) num_keep[b] = min(s_base, max_keep);
+}
+
 // ---------------------------------------------------------------- soft-NMS (linear), test time
 // mmcv.ops.soft_nms(method='linear') [mmcv-full 1.0.5, CPU-only there]: repeatedly select the
 // highest-scoring live box, decay every other live box j by (1 - iou) if iou > thr, drop boxes whose
@@ -502,6 +661,77 @@ int loft_nms_sorted(const float* boxes, const long long* idxs, int B, int n, flo
       reinterpret_cast<const unsigned long long*>(workspace), n, nwords, max_keep, keep, num_keep,
       (long long)(per_img / 8), (long long)n);
   LOFT_CUDA_LAUNCH_CHECK("nms_scan");
+  return LOFT_OK;
+}
+
+namespace {
+int build_seg_table(const int* seg_off, int L, SegTable& tab, int n) {
+  if (L < 1 || L > kMaxSeg || seg_off[0] != 0 || seg_off[L] != n) return -1;
+  tab.L = L;
+  long long m = 0;
+  for (int s = 0; s <= L; ++s) tab.off[s] = seg_off[s];
+  for (int s = 0; s < L; ++s) {
+    const long long ks = seg_off[s + 1] - seg_off[s];
+    if (ks < 0) return -1;
+    tab.moff[s] = m;
+    m += ks * ((ks + 63) / 64);
+  }
+  tab.moff[L] = m;
+  return 0;
+}
+}  // namespace
+
+// per-image workspace: [pair masks][keep lists n x i32][flags n x u8][max coord]
+size_t loft_nms_segmented_workspace(const int* seg_off, int L) {
+  SegTable tab;
+  if (L < 1 || L > kMaxSeg) return 0;
+  const int n = seg_off[L];
+  if (build_seg_table(seg_off, L, tab, n)) return 0;
+  const size_t keep_words = ((size_t)n * 4 + 7) / 8, flag_words = ((size_t)n + 7) / 8;
+  return ((size_t)tab.moff[L] + keep_words + flag_words + 8) * 8;
+}
+
+int loft_nms_segmented(const float* boxes, const int* seg_off, int L, const long long* order, int B,
+                       int n, float iou_thr, int max_keep, long long* keep, int* num_keep,
+                       void* workspace, size_t ws_bytes, cudaStream_t stream) {
+  LOFT_CHECK_ARG(boxes && seg_off && order && keep && num_keep && workspace,
+                 "nms_segmented: null pointer");
+  SegTable tab;
+  LOFT_CHECK_SHAPE(build_seg_table(seg_off, L, tab, n) == 0,
+                   "nms_segmented: bad segment table (L=%d, n=%d)", L, n);
+  const size_t per_img = loft_nms_segmented_workspace(seg_off, L);
+  LOFT_CHECK_ARG(ws_bytes >= (size_t)B * per_img, "nms_segmented: workspace too small");
+  if (n == 0 || B == 0) {
+    if (B) cudaMemsetAsync(num_keep, 0, sizeof(int) * B, stream);
+    return LOFT_OK;
+  }
+  const long long stride_w = (long long)(per_img / 8);
+  const long long keep_off = tab.moff[L];
+  const long long flag_off = keep_off + (long long)(((size_t)n * 4 + 7) / 8);
+  const long long maxc_off = flag_off + (long long)(((size_t)n + 7) / 8);
+  unsigned long long* ws = reinterpret_cast<unsigned long long*>(workspace);
+  int max_ks = 0;
+  for (int s = 0; s < L; ++s) max_ks = max(max_ks, seg_off[s + 1] - seg_off[s]);
+  const int max_nw = (max_ks + 63) / 64;
+  for (int b = 0; b < B; ++b) {
+    unsigned long long* wsb = ws + (long long)b * stride_w;
+    float* maxc = reinterpret_cast<float*>(wsb + maxc_off);
+    cudaMemsetAsync(wsb + flag_off, 0, (size_t)n, stream);
+    fill_f32_kernel<<<1, 1, 0, stream>>>(maxc, -INFINITY);
+    max_coord_kernel<<<32, 256, 0, stream>>>(boxes + (size_t)b * n * 4, (long long)n * 4, maxc);
+    LOFT_CUDA_LAUNCH_CHECK("max_coord");
+  }
+  if (max_keep <= 0 || max_keep > n) max_keep = n;
+  dim3 grid(max_nw, max_nw, B * L);
+  nms_mask_seg_kernel<<<grid, 64, 0, stream>>>(boxes, nullptr, n, iou_thr, ws, stride_w, maxc_off,
+                                               tab);
+  LOFT_CUDA_LAUNCH_CHECK("nms_mask_seg");
+  nms_scan_seg_kernel<<<B * L, kScanThreads, 0, stream>>>(ws, stride_w, keep_off, flag_off, n,
+                                                         max_keep, tab);
+  LOFT_CUDA_LAUNCH_CHECK("nms_scan_seg");
+  nms_compact_kernel<<<B, 1024, 0, stream>>>(ws, stride_w, flag_off, order, n, max_keep, keep,
+                                             num_keep);
+  LOFT_CUDA_LAUNCH_CHECK("nms_compact");
   return LOFT_OK;
 }
 

@@ -21,7 +21,7 @@ from ...core import (build_anchor_generator, build_assigner, build_bbox_coder, b
 from ...engine import Packed, WeightRef
 from ...ops import dense as D
 from ...ops import losses as K
-from ...ops.nms import nms_sorted
+from ...ops.nms import nms_segmented
 
 i32 = ctypes.c_int
 _FUSED_W = 16      # 3 cls + 12 reg + 1 zero pad
@@ -295,12 +295,15 @@ class RPNHead(nn.Module):
             out3d = fused.permute(0, 2, 3, 1).reshape(n_img, fh * fw, _FUSED_W)
             scores = out3d[:, :, :A].reshape(n_img, -1).sigmoid()      # (h, w, a) order
             n = scores.shape[1]
+            # every level is sorted (the reference only sorts levels larger than nms_pre; a stable
+            # sort of the rest does not change the stable global order below) so that the NMS can
+            # work level by level on score-ordered segments
+            ranked, rank_inds = scores.sort(dim=1, descending=True, stable=True)
             if cfg.nms_pre > 0 and n > cfg.nms_pre:
-                ranked, rank_inds = scores.sort(dim=1, descending=True, stable=True)
                 topk = rank_inds[:, :cfg.nms_pre].contiguous()
                 scores = ranked[:, :cfg.nms_pre]
             else:
-                topk = torch.arange(n, device=dev).expand(n_img, n).contiguous()
+                topk, scores = rank_inds.contiguous(), ranked
             k = topk.shape[1]
             boxes = torch.empty((n_img, k, 4), device=dev, dtype=torch.float32)
             stride = self.anchor_generator.strides[l][0]
@@ -310,15 +313,14 @@ class RPNHead(nn.Module):
                    L.ll(fh * fw * _FUSED_W), L.ll(k), L.ll(k * 4), L.stream())
             boxes_l.append(boxes)
             scores_l.append(scores)
-            ids_l.append(torch.full((n_img, k), l, device=dev, dtype=torch.long))
-        bx = torch.cat(boxes_l, dim=1)
+        bx = torch.cat(boxes_l, dim=1)                 # level-major, score-sorted within a level
         sc = torch.cat(scores_l, dim=1)
-        ids = torch.cat(ids_l, dim=1)
-        order = sc.sort(dim=1, descending=True, stable=True)[1]
-        bx_s = torch.gather(bx, 1, order[:, :, None].expand(-1, -1, 4)).contiguous()
-        ids_s = torch.gather(ids, 1, order).contiguous()
-        sc_s = torch.gather(sc, 1, order)
-        keep, num = nms_sorted(bx_s, ids_s, float(cfg.nms_thr), int(cfg.nms_post))
+        sc_s, order = sc.sort(dim=1, descending=True, stable=True)
+        bx_s = torch.gather(bx, 1, order[:, :, None].expand(-1, -1, 4))
+        # batched_nms(boxes, scores, level ids): levels never suppress each other -> per-level
+        # pair masks + scans, then the first nms_post kept boxes in global score order
+        keep, num = nms_segmented(bx, [b.shape[1] for b in boxes_l], order, float(cfg.nms_thr),
+                                  int(cfg.nms_post))
         num_h = num.tolist()
         results = []
         for i in range(n_img):

@@ -5,7 +5,7 @@ kernels of libloft_b200.so.  RoI layers are looked up here by name, exactly like
 import torch.nn as nn
 
 from .roi import RoIAlign, roi_align, multilevel_roi_align, mask_target_sample
-from .nms import nms, batched_nms, nms_sorted, soft_nms
+from .nms import nms, batched_nms, nms_sorted, nms_segmented, soft_nms
 from .focal import sigmoid_focal_loss
 
 Conv2d = nn.Conv2d            # parameter containers; their math runs through ops.dense

@@ -25,6 +25,31 @@ def nms_sorted(boxes, idxs, iou_threshold, max_keep=-1):
     return keep, num
 
 
+def nms_segmented(boxes, seg_sizes, order, iou_threshold, max_keep=-1):
+    """Per-level form of batched NMS (the RPN's): boxes [B,n,4] segment-major, every segment sorted
+    by score; seg_sizes the segment lengths (segment index = the batched_nms idx); order [B,n]
+    int64 = segment-major indices in global score order.  Same (keep, num_keep) as
+    `nms_sorted(boxes.gather(order), idxs.gather(order), ...)`."""
+    B, n, _ = boxes.shape
+    keep = torch.empty((B, n), device=boxes.device, dtype=torch.long)
+    num = torch.zeros((B,), device=boxes.device, dtype=torch.int32)
+    if n == 0 or B == 0:
+        return keep, num
+    nseg = len(seg_sizes)
+    off = (ctypes.c_int * (nseg + 1))()
+    for i, k in enumerate(seg_sizes):
+        off[i + 1] = off[i] + int(k)
+    assert off[nseg] == n
+    fn = L.lib().loft_nms_segmented_workspace
+    fn.restype = ctypes.c_size_t
+    ws_bytes = B * fn(off, i32(nseg))
+    ws = torch.empty((ws_bytes,), device=boxes.device, dtype=torch.uint8)
+    L.call('nms_segmented', L.ptr(boxes.contiguous()), off, i32(nseg), L.ptr(order.contiguous()),
+           i32(B), i32(n), L.f32(iou_threshold), i32(max_keep), L.ptr(keep), L.ptr(num), L.ptr(ws),
+           ctypes.c_size_t(ws_bytes), L.stream())
+    return keep, num
+
+
 def nms(boxes, scores, iou_threshold, offset=0):
     """mmcv.ops.nms: returns (dets[k,5], inds[k]) with inds in score-descending order
     (ties keep input order)."""

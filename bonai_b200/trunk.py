@@ -533,6 +533,12 @@ class Trunk:
             prog.build_backward()
             if prog.use_graph:
                 prog.bwd.capture()
+            # The tapes pin thousands of small Python objects; move them (and everything else
+            # built so far) out of the cyclic GC's reach so a generation-2 sweep never stalls the
+            # launch thread in the middle of a step.
+            import gc
+            gc.collect()
+            gc.freeze()
         else:
             prog.bwd.launch()
         prog.rpn_done = False

@@ -167,6 +167,14 @@ size_t loft_nms_workspace(int n);
 int loft_nms_sorted(const float* boxes, const long long* idxs, int B, int n, float iou_thr,
                     int max_keep, long long* keep, int* num_keep, void* workspace, size_t ws_bytes,
                     cudaStream_t stream);
+/* per-level ("segmented") form of the same batched NMS for the RPN: boxes [B,n,4] are
+ * SEGMENT-MAJOR (level 0 first, ...; seg_off = L+1 host ints), each segment sorted by score;
+ * order [B,n] lists segment-major indices in global score order.  Identical keep / num_keep to
+ * loft_nms_sorted on the globally sorted boxes with idxs = level, at ~1/5 of the pair tests. */
+size_t loft_nms_segmented_workspace(const int* seg_off, int L);
+int loft_nms_segmented(const float* boxes, const int* seg_off, int L, const long long* order, int B,
+                       int n, float iou_thr, int max_keep, long long* keep, int* num_keep,
+                       void* workspace, size_t ws_bytes, cudaStream_t stream);
 /* test-time linear soft-NMS (mmcv.ops.soft_nms via core/post_processing/bbox_nms.py:63 with
  * bonai_loft_foa_r50_fpn_basic.py:138); CPU-only in mmcv 1.0.5, one-block kernel here */
 int loft_soft_nms_linear(const float* boxes, const float* scores, const long long* idxs, int n,

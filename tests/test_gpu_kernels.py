@@ -318,6 +318,38 @@ def test_nms_bit_exact(golden_units):
     assert torch.equal(dets.cpu(), torch.from_numpy(g['bnms_dets']))
 
 
+@pytest.mark.parametrize('sizes', [(3000, 3000, 3000, 3000, 768), (700, 1, 0, 65, 64), (129,)])
+def test_segmented_nms_equals_global_batched_nms(sizes, golden_units):
+    """The per-level NMS of the RPN path (loft_nms_segmented) must give exactly the keep list of
+    the global batched NMS (loft_nms_sorted with idxs = level, itself pinned to the reference's
+    mmcv batched_nms golden above): clustered boxes, many exact score ties, two images."""
+    from bonai_b200.ops import nms_sorted, nms_segmented
+    g = torch.Generator().manual_seed(sum(sizes))
+    B, n = 2, sum(sizes)
+    ctr = torch.rand(B, 40, 2, generator=g) * 900 + 60
+    boxes_l, scores_l, ids_l = [], [], []
+    for l, k in enumerate(sizes):
+        c = ctr[:, torch.randint(0, 40, (k,), generator=g)] + torch.randn(B, k, 2, generator=g) * 6
+        wh = torch.rand(B, k, 2, generator=g) * 60 + 8
+        bx = torch.cat([c - wh / 2, c + wh / 2], -1).clamp(0, 1024)
+        sc = (torch.rand(B, k, generator=g) * 50).round() / 50          # ties
+        sc, o = sc.sort(dim=1, descending=True, stable=True)
+        boxes_l.append(torch.gather(bx, 1, o[:, :, None].expand(-1, -1, 4)))
+        scores_l.append(sc)
+        ids_l.append(torch.full((B, k), l, dtype=torch.long))
+    bx, sc, ids = (torch.cat(t, 1).cuda() for t in (boxes_l, scores_l, ids_l))
+    sc_s, order = sc.sort(dim=1, descending=True, stable=True)
+    bx_s = torch.gather(bx, 1, order[:, :, None].expand(-1, -1, 4)).contiguous()
+    ids_s = torch.gather(ids, 1, order).contiguous()
+    for max_keep in (-1, 1000):
+        k0, n0 = nms_sorted(bx_s, ids_s, 0.7, max_keep)
+        k1, n1 = nms_segmented(bx, list(sizes), order, 0.7, max_keep)
+        assert torch.equal(n0, n1), (n0, n1)
+        for b in range(B):
+            assert torch.equal(k0[b, :int(n0[b])], k1[b, :int(n1[b])])
+        assert int(n0.min()) > 10
+
+
 def test_nms_large_vs_oracle():
     from bonai_b200.ops import batched_nms
     from oracle import ops_cpu
