@@ -84,6 +84,59 @@ class ClockSampler:
                     reasons=sorted(reasons), samples=len(self.rows))
 
 
+class NvmlClockSampler:
+    """Same record through NVML in a thread of this process (no nvidia-smi process: its queries
+    were measured to stall kernel launches for 20-170 ms now and then, which a 20 ms step cannot
+    hide).  Samples SM clock + clock-event reasons every `period` seconds during the timed region."""
+
+    def __init__(self, index=0, period=0.25):
+        self.index, self.period = index, period
+        self.sm, self.reasons, self.max_sm = [], set(), None
+        self.stop_flag = threading.Event()
+        self.t = None
+
+    def start(self):
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            idx = int(vis.split(',')[self.index]) if vis and vis.split(',')[0].isdigit() else self.index
+            self.h = N.nvmlDeviceGetHandleByIndex(idx)
+            self.N = N
+            self.max_sm = N.nvmlDeviceGetMaxClockInfo(self.h, N.NVML_CLOCK_SM)
+        except Exception:
+            self.N = None
+            return
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def _run(self):
+        N = self.N
+        names = {N.nvmlClocksEventReasonHwSlowdown: 'hw_slowdown',
+                 N.nvmlClocksEventReasonHwThermalSlowdown: 'hw_thermal_slowdown',
+                 N.nvmlClocksEventReasonSwThermalSlowdown: 'sw_thermal_slowdown',
+                 N.nvmlClocksEventReasonSwPowerCap: 'sw_power_cap'}
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(N.nvmlDeviceGetClockInfo(self.h, N.NVML_CLOCK_SM))
+                r = N.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self.stop_flag.wait(self.period)
+
+    def stop(self):
+        if getattr(self, 'N', None) is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvml unavailable'])
+        self.stop_flag.set()
+        self.t.join(timeout=2)
+        sm = sorted(self.sm)
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=self.max_sm,
+                    reasons=sorted(self.reasons), samples=len(sm), how='nvml')
+
+
 def make_batch(seed, device=None, pinned=False):
     from oracle import loft_cpu as O           # synthetic-input recipe shared with the oracle
     img, gb, gl, gm, go = O.make_inputs(seed, BATCH, IMG, NUM_GT)
@@ -242,7 +295,11 @@ def main():
                     help='GT boxes per tile: 80 = BONAI mean (init-like, P~100/img), 256 = '
                          'steady-state-like (P=256/img), SURVEY 8(d)')
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 10) if args.impl != 'reference' else args.warmup
+    # The first ~35 steps of a process see sporadic 50-350 ms stalls (allocator growth while the
+    # number of positives wanders, lazy initialisation in the driver / ATen; measured with
+    # LOFT_STEP_TIMES=1: none after step 40) -- warm up past them; the reported `warmup` is the
+    # number actually run.
+    args.warmup = max(args.warmup, 40) if args.impl != 'reference' else args.warmup
     globals()['NUM_GT'] = args.num_gt
     if args.impl == 'reference':
         return run_reference(args)
@@ -278,23 +335,32 @@ def main():
     for _ in range(args.warmup):
         trainer.train_step(data)
     sync_all()
-    clocks = ClockSampler(local)
-    if rank == 0:
+    how = os.environ.get('LOFT_CLOCKS', 'nvml')
+    clocks = ClockSampler(local) if how == 'smi' else NvmlClockSampler(local)
+    if rank == 0 and how != 'off':
         clocks.start()
     L.LAUNCHES[0] = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    marks = []
     for _ in range(args.steps):
         trainer.train_step(data)
+        if os.environ.get('LOFT_STEP_TIMES'):
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append(ev)
     e1.record()
     sync_all()
+    if marks and rank == 0:
+        ts = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
+        print('per-step ms: ' + ' '.join(f'{t:.1f}' for t in ts), file=sys.stderr)
     launches = L.LAUNCHES[0]
     ms = e0.elapsed_time(e1)
     if getattr(trainer, '_comm_events', None):
         ts = [a.elapsed_time(b) for a, b in trainer._comm_events[-args.steps:]]
         print(f'[rank {rank}] grad all-reduce ms/step: mean {sum(ts) / len(ts):.3f} min {min(ts):.3f} '
               f'max {max(ts):.3f}; step {ms / args.steps:.3f}', file=sys.stderr)
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop() if (rank == 0 and how != 'off') else None
     logs = trainer.read_logs()
     n_pos = sum(s.pos_bboxes.shape[0] for s in model.roi_head._last_sampling_results)
     t = torch.tensor([ms], device=device, dtype=torch.float64)
