@@ -381,20 +381,28 @@ def main():
     # ---- end to end: pinned host inputs copied every step (on the trainer's copy stream, the way
     # a prefetching loader feeds it) and the loss vector read back every step
     host_batch = to_model_inputs(make_batch(seed=rank, pinned=True))
-    for _ in range(2):
+    for _ in range(5):                          # first use of the staging path (pinned copies, events)
         trainer.train_step(trainer.stage(host_batch), read_logs=True)
     h2d_bytes = trainer.staged_bytes
     sync_all()
     cur = trainer.stage(host_batch)
     torch.cuda.synchronize()
     e0.record()
+    marks = []
     for _ in range(args.steps):
         nxt = trainer.stage(host_batch)          # next batch's copies overlap this step
         trainer.train_step(cur, read_logs='async')   # D2H of every step's loss vector, read one
         cur = nxt                                    # step late so the launch thread never stalls
+        if os.environ.get('LOFT_STEP_TIMES'):
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append(ev)
     out = trainer.flush_logs()                   # the last step's losses, inside the timed region
     e1.record()
     sync_all()
+    if marks and rank == 0:
+        ts = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
+        print('e2e per-step ms: ' + ' '.join(f'{t:.1f}' for t in ts), file=sys.stderr)
     t = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -27,8 +27,9 @@ class _MultiLevelRoIAlign(Function):
     """All FPN levels in one launch; the level of each RoI is computed in-kernel."""
 
     @staticmethod
-    def forward(ctx, rois, out_size, scales, finest_scale, *feats):
+    def forward(ctx, rois, out_size, scales, finest_scale, sinks, *feats):
         fn = [nhwc(f) for f in feats]
+        ctx.sinks = sinks
         K = rois.shape[0]
         C = fn[0].shape[-1]
         rois = rois.contiguous().float()
@@ -47,19 +48,30 @@ class _MultiLevelRoIAlign(Function):
         K = rois.shape[0]
         dn = nhwc(dout)
         C = dn.shape[-1]
+        if ctx.sinks is not None:
+            # the producer of the pyramid (bonai_b200.trunk) owns zeroed accumulation buffers:
+            # every RoIAlign of the step adds into them, nothing is allocated, zero-filled or
+            # summed by autograd, and no gradient tensor is returned for the feature maps
+            ptrs, Hs, Ws, sc = _pyramid_args(ctx.sinks, scales)
+            L.call('roi_align_bwd', ptrs, Hs, Ws, sc, i32(len(shapes)), L.ptr(rois), L.ll(K),
+                   i32(out_size), i32(C), L.f32(finest), L.ptr(dn), L.stream())
+            return (None,) * (5 + len(shapes))
         grads = [torch.zeros(s, device=dout.device, dtype=torch.float32) for s in shapes]
         ptrs, Hs, Ws, sc = _pyramid_args(grads, scales)
         L.call('roi_align_bwd', ptrs, Hs, Ws, sc, i32(len(grads)), L.ptr(rois), L.ll(K),
                i32(out_size), i32(C), L.f32(finest), L.ptr(dn), L.stream())
-        return (None, None, None, None) + tuple(g.permute(0, 3, 1, 2) for g in grads)
+        return (None, None, None, None, None) + tuple(g.permute(0, 3, 1, 2) for g in grads)
 
 
 def multilevel_roi_align(feats, rois, out_size, strides, finest_scale=56):
     C = feats[0].shape[1]
     if rois.shape[0] == 0:
         return feats[0].new_zeros((0, C, out_size, out_size))
+    sinks = [getattr(f, '_loft_grad_sink', None) for f in feats]
+    if any(s is None for s in sinks) or not torch.is_grad_enabled():
+        sinks = None
     return _MultiLevelRoIAlign.apply(rois, int(out_size), [1.0 / s for s in strides],
-                                     float(finest_scale), *feats)
+                                     float(finest_scale), sinks, *feats)
 
 
 def roi_align(input, rois, output_size, spatial_scale=1.0, sampling_ratio=0, pool_mode='avg',
@@ -71,7 +83,7 @@ def roi_align(input, rois, output_size, spatial_scale=1.0, sampling_ratio=0, poo
     oh, ow = _pair(output_size)
     assert oh == ow
     # a single level: finest_scale large enough that every RoI maps to level 0
-    return _MultiLevelRoIAlign.apply(rois, int(oh), [float(spatial_scale)], 1e30, input)
+    return _MultiLevelRoIAlign.apply(rois, int(oh), [float(spatial_scale)], 1e30, None, input)
 
 
 class RoIAlign(nn.Module):

@@ -242,6 +242,14 @@ class _Program:
                             round_out=False)
                 self.rpn_t.append(t)
                 self.rpn_out.append(o)
+            # gradient sinks of the FPN maps: RoIAlign backward (3 per step) accumulates straight
+            # into them; zeroed here, inside the forward graph
+            self.S = []
+            if self.train:
+                for f in outs:
+                    sbuf = self.buf(*f.shape)
+                    L.call('fill', L.ptr(sbuf), L.ll(sbuf.numel()), L.f32(0.0), L.stream())
+                    self.S.append(sbuf)
         self.fwd_ready = True
 
     # ---------------------------------------------------------------- backward program
@@ -329,6 +337,9 @@ class _Program:
         n = len(self.lat)
         with self.bwd:
             gtot = self.B
+            for l in range(len(self.S)):       # what the RoI heads sent (RoIAlign backward sinks)
+                L.call('add', L.ptr(gtot[l]), L.ptr(self.S[l]), L.ptr(gtot[l]),
+                       L.ll(gtot[l].numel()), i32(1), L.stream())
             # extra levels (P6 = P5-out subsampled): fold their gradient into the level below
             for l in range(nlev - 1, n - 1, -1):
                 Nf, Hf, Wf, Cf = self.P[l - 1].shape
@@ -573,4 +584,8 @@ class Trunk:
         outs = _TrunkFn.apply(img, self, *self.params)
         n = len(outs) // 2
         self.rpn_outs = list(outs[n:])
-        return tuple(outs[:n]), self.rpn_outs
+        feats = tuple(outs[:n])
+        if self.current is not None and self.current.S:
+            for f, sbuf in zip(feats, self.current.S):
+                f._loft_grad_sink = sbuf
+        return feats, self.rpn_outs
