@@ -381,8 +381,9 @@ def main():
     # ---- end to end: pinned host inputs copied every step (on the trainer's copy stream, the way
     # a prefetching loader feeds it) and the loss vector read back every step
     host_batch = to_model_inputs(make_batch(seed=rank, pinned=True))
-    for _ in range(5):                          # first use of the staging path (pinned copies, events)
-        trainer.train_step(trainer.stage(host_batch), read_logs=True)
+    for _ in range(5):                          # first use of the staging path (pinned copies,
+        trainer.train_step(trainer.stage(host_batch), read_logs='async')   # events, log buffers)
+    trainer.flush_logs()
     h2d_bytes = trainer.staged_bytes
     sync_all()
     cur = trainer.stage(host_batch)

@@ -150,7 +150,7 @@ class RPNHead(nn.Module):
             losses = after_loss(losses)
         if proposal_cfg is None:
             return losses
-        return losses, self.get_bboxes(*outs, img_metas, cfg=proposal_cfg)
+        return losses, self.get_bboxes(*outs, img_metas, cfg=proposal_cfg, fixed_size=True)
 
     # ------------------------------------------------------------------ targets + loss
     def get_anchors(self, featmap_sizes, img_metas, device='cuda'):
@@ -273,7 +273,8 @@ class RPNHead(nn.Module):
 
     # ------------------------------------------------------------------ proposals
     @torch.no_grad()
-    def get_bboxes(self, cls_scores, bbox_preds, img_metas, cfg=None, rescale=False):
+    def get_bboxes(self, cls_scores, bbox_preds, img_metas, cfg=None, rescale=False,
+                   fixed_size=False):
         """AnchorHead.get_bboxes -> RPNHead._get_bboxes_single (rpn_head.py:79-168), all images in
         one batched NMS.  Order within equal scores is (level, anchor index) = a stable sort."""
         if RPNHead.forced_proposals is not None:
@@ -321,6 +322,24 @@ class RPNHead(nn.Module):
         # pair masks + scans, then the first nms_post kept boxes in global score order
         keep, num = nms_segmented(bx, [b.shape[1] for b in boxes_l], order, float(cfg.nms_thr),
                                   int(cfg.nms_post))
+        if fixed_size:
+            # training: no host sync here.  Every image gets exactly K rows; rows past the number
+            # NMS kept are all-zero boxes (IoU 0 with everything) that the RoI sampler marks
+            # "ignore" through `_loft_num_valid`, so they are never drawn (same candidate sets
+            # and random draws as the reference's variable-length dets[:nms_post]).
+            n_tot = bx.shape[1]
+            K = min(int(cfg.nms_post), n_tot) if cfg.nms_post > 0 else n_tot
+            valid = torch.arange(K, device=dev)[None, :] < num[:, None]
+            kk = torch.where(valid, keep[:, :K], 0)
+            b = torch.gather(bx_s, 1, kk[:, :, None].expand(-1, -1, 4)) * valid[:, :, None]
+            s = torch.gather(sc_s, 1, kk) * valid
+            det = torch.cat([b, s[:, :, None]], dim=2)
+            results = []
+            for i in range(n_img):
+                r = det[i]
+                r._loft_num_valid = num[i]
+                results.append(r)
+            return results
         num_h = num.tolist()
         results = []
         for i in range(n_img):

@@ -101,6 +101,11 @@ class StandardRoIHead(BaseRoIHead):
         for i in range(n_img):
             ar = self.bbox_assigner.assign(proposal_list[i], gt_bboxes[i], gt_bboxes_ignore[i],
                                            gt_labels[i])
+            nv = getattr(proposal_list[i], '_loft_num_valid', None)
+            if nv is not None:     # fixed-size proposal block: rows >= nv are padding -> ignore
+                ar.gt_inds = torch.where(
+                    torch.arange(ar.gt_inds.numel(), device=ar.gt_inds.device) < nv, ar.gt_inds,
+                    torch.full_like(ar.gt_inds, -1))
             bboxes = proposal_list[i][:, :4]
             gt_flags = bboxes.new_zeros((bboxes.shape[0],), dtype=torch.uint8)
             if sampler.add_gt_as_proposals and len(gt_bboxes[i]) > 0:
@@ -113,16 +118,17 @@ class StandardRoIHead(BaseRoIHead):
             flags_l.append(gt_flags)
         sizes = [ar.gt_inds.numel() for ar in ars]
         allg = torch.cat([ar.gt_inds for ar in ars])
-        # code 0: positive, 1: negative candidates; one nonzero for everything
-        idx = torch.nonzero(torch.stack([allg > 0, allg == 0]), as_tuple=False)   # the only sync
-        kind, pos = idx[:, 0], idx[:, 1]
         offs = [0]
         for n in sizes:
             offs.append(offs[-1] + n)
-        ends = torch.tensor(offs[1:], device=allg.device)
-        img_of = torch.bucketize(pos, ends, right=True)
-        key = (kind * n_img + img_of)
-        counts = torch.bincount(key, minlength=2 * n_img).tolist()                 # rides the same sync
+        # code 0: positive, 1: negative candidates.  Per-image counts first (one read-back, the
+        # only host sync of the RoI sampling), then ONE size-known nonzero for everything: rows
+        # come out ordered by (code, position) = [pos img0, pos img1, ..., neg img0, neg img1, ...]
+        flags = torch.stack([allg > 0, allg == 0])
+        counts = torch.stack([flags[:, offs[i]:offs[i + 1]].sum(1) for i in range(n_img)], 1)
+        counts = counts.reshape(-1).tolist()                                       # the only sync
+        idx = torch.nonzero_static(flags, size=sum(counts))
+        pos = idx[:, 1]
         chunks = torch.split(pos, counts)
         results = []
         num_expected_pos = int(sampler.num * sampler.pos_fraction)
