@@ -25,7 +25,8 @@ constexpr int kKB = 32;                       // k elements per stage (128 B of 
 constexpr int kABytes = kBlockC * kKB * 4;    // 16 KB
 constexpr int kBBytes = kMaxN * kKB * 4;      // 32 KB
 constexpr int kStageBytes = kABytes + kBBytes;
-constexpr int kRowTabBytes = 2 * 2 * kMaxN * 4;  // 2 accumulator stages x (out row, residual row)
+constexpr int kRowTabBytes = 2 * 2 * kMaxN * 4 + 64;  // 2 accumulator stages x (out row, residual
+                                                      // row) + per-32-column validity masks
 constexpr int kSmemBytes =
     kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kRowTabBytes;
 constexpr int kThreads = 320;                 // warp0 TMA, warp1 MMA, warps2-9 epilogue
@@ -74,6 +75,7 @@ struct GemmParams {
   int relu;
   int out_map;    // 0 plain rows, 1 deconv 2x2/s2 pixel shuffle (out is [N,2H,2W,Cm/4])
   int round_out;  // round `out` to TF32 (RNA) so the next MMA's operand truncation is exact
+  int fast_epi;   // all element offsets of out / residual / mask fit in 31 bits
   float* colsum;  // per-channel sum over pixels of the value written to `out` (atomic accumulate):
   float* colsum2; //   the bias / BN-beta gradient of the layer that produced this dgrad's input
   long long colsum_gstride;  // stride of colsum between groups (floats)
@@ -287,6 +289,7 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const uint32_t as = lt & 1u, aph = (lt >> 1) & 1u;
       int* s_row = row_tab + as * (2 * kMaxN);
       int* s_rrow = s_row + kMaxN;
+      unsigned* s_vmask = reinterpret_cast<unsigned*>(row_tab + 4 * kMaxN) + as * 8;
       if (!is_wgrad) {
         const int col = et;
         int row = -1, rrow = 0;
@@ -327,6 +330,10 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
         s_row[col] = row;
         s_rrow[col] = rrow;
+        // validity of each 32-column chunk (= the columns one epilogue pass covers): a fully
+        // valid chunk takes the branch-free fast path below
+        const unsigned vm = __ballot_sync(0xffffffffu, row >= 0);
+        if (lane == 0) s_vmask[et >> 5] = vm;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&tfull_bar[as], aph);
@@ -379,6 +386,8 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const float* __restrict__ resb =
             res ? res + (p.res_mode == 1 ? (long long)row_add * ldr : 0) + ocol : nullptr;
         const int res_mode = p.res_mode, relu = p.relu, round_out = p.round_out;
+        const bool contig = (p.mode == FPROP_2D || p.mode == DGRAD_2D) && p.out_map == 0;
+        const bool do_colsum = p.colsum != nullptr;
         float csum = 0.f;
         for (int cc = half * kCh; cc < p.n_mma; cc += 2 * kCh) {
           float v[kCh];
@@ -386,6 +395,78 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if (!c_ok) continue;
           int rows[kCh];
           float rv[kCh];
+          if (p.fast_epi && s_vmask[cc >> 5] == 0xffffffffu) {
+            // ---- fast path: every column of the chunk is a valid pixel.  No per-element
+            // predicates or branches; in the 2-D modes the rows are consecutive, so addresses
+            // are base + j*pitch.  (The profiled epilogue spent ~30 instructions per stored
+            // value, issue-bound with two warps per scheduler: profiles/r01_ncu_epilogue.txt.)
+            // 32-bit element offsets (the host only enables the fast path when they fit): 2-D
+            // modes (r0 + j) * pitch, conv modes row-table lookups
+            const int ldo32 = (int)ldo, ldr32 = (int)ldr;
+            int* off = rows;
+            if (contig) {
+              const int r0 = s_row[cc];
+#pragma unroll
+              for (int j = 0; j < kCh; ++j) off[j] = (r0 + j) * ldo32;
+            } else {
+#pragma unroll
+              for (int j = 0; j < kCh; ++j) off[j] = s_row[cc + j] * ldo32;
+            }
+#define LOFT_OFF(j) off[j]
+            if (rawb != nullptr) {
+#pragma unroll
+              for (int j = 0; j < kCh; ++j) rawb[LOFT_OFF(j)] = v[j];
+            }
+#pragma unroll
+            for (int j = 0; j < kCh; ++j) v[j] = fmaf(v[j], sc, sh);
+            if (res_mode != 0) {
+              if (res_mode == 1) {
+                if (ldr == ldo) {
+#pragma unroll
+                  for (int j = 0; j < kCh; ++j) rv[j] = resb[LOFT_OFF(j)];
+                } else {
+#pragma unroll
+                  for (int j = 0; j < kCh; ++j) rv[j] = resb[s_row[cc + j] * ldr32];
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < kCh; ++j) {
+                  const int rr = s_rrow[cc + j];
+                  rv[j] = rr >= 0 ? resb[rr * ldr32] : 0.f;
+                }
+              }
+              asm volatile("" ::: "memory");
+#pragma unroll
+              for (int j = 0; j < kCh; ++j) v[j] += rv[j];
+            }
+            if (relu) {
+#pragma unroll
+              for (int j = 0; j < kCh; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (mskb != nullptr) {
+#pragma unroll
+              for (int j = 0; j < kCh; ++j) rv[j] = mskb[LOFT_OFF(j)];
+              asm volatile("" ::: "memory");
+#pragma unroll
+              for (int j = 0; j < kCh; ++j) v[j] = (rv[j] > 0.f) ? v[j] : 0.f;
+            }
+            if (round_out) {
+#pragma unroll
+              for (int j = 0; j < kCh; ++j) {
+                uint32_t rr;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(rr) : "f"(v[j]));
+                v[j] = __uint_as_float(rr);
+              }
+            }
+            if (do_colsum) {
+#pragma unroll
+              for (int j = 0; j < kCh; ++j) csum += v[j];
+            }
+#pragma unroll
+            for (int j = 0; j < kCh; ++j) outb[LOFT_OFF(j)] = v[j];
+#undef LOFT_OFF
+            continue;
+          }
 #pragma unroll
           for (int j = 0; j < kCh; ++j) rows[j] = s_row[cc + j];
           if (rawb != nullptr) {
@@ -550,7 +631,16 @@ void fill_descs(GemmParams& p, bool a_mn, bool b_mn) {
   if (g_dbg.idesc >= 0) p.idesc = (uint32_t)g_dbg.idesc;
 }
 
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p_in, cudaStream_t stream) {
+  GemmParams p = p_in;
+  {
+    // largest pixel-row index the epilogue can form, times the widest pitch
+    long long rows = (p.mode == FPROP_CONV || p.mode == DGRAD_CONV) ? (long long)p.N * p.H * p.W
+                                                                    : (long long)p.P;
+    if (p.out_map == 1) rows *= 4;
+    const long long ld = p.ldo > p.ldr ? p.ldo : p.ldr;
+    p.fast_epi = (rows + 1) * ld < (1ll << 31) ? 1 : 0;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(loft_gemm_tf32_kernel,

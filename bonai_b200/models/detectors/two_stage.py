@@ -102,12 +102,18 @@ class TwoStageDetector(BaseDetector):
             rpn_losses, proposal_list = self.rpn_head.forward_train(
                 x, img_metas, gt_bboxes, gt_labels=None, gt_bboxes_ignore=gt_bboxes_ignore,
                 proposal_cfg=proposal_cfg, rpn_outs=rpn_outs,
-                after_loss=trunk.early_rpn_backward if trunk is not None else None)
-            losses.update(rpn_losses)
+                after_loss=(lambda d: trunk.early_rpn_backward(d, 'side'))
+                if trunk is not None else None)
         else:
             proposal_list = proposals
+            rpn_losses = {}
         roi_losses = self.roi_head.forward_train(x, img_metas, proposal_list, gt_bboxes, gt_labels,
                                                  gt_bboxes_ignore, gt_masks, **kwargs)
+        if trunk is not None and rpn_losses:
+            # RPN part of the backward now: GEMM work for the GPU while the launch thread sums the
+            # losses and starts the autograd engine (bonai_b200.trunk.Trunk.early_rpn_backward)
+            rpn_losses = trunk.early_rpn_backward(rpn_losses, 'end')
+        losses.update(rpn_losses)
         losses.update(roi_losses)
         return losses
 

@@ -460,9 +460,15 @@ class Trunk:
         self.params = [p for mod in (model.backbone, model.neck, model.rpn_head)
                        for p in mod.parameters() if p.requires_grad]
         self.side = torch.cuda.Stream(device=store.device)
-        # measured on B200: no gain (the bubbles it should fill are spread over the whole RoI-head
-        # phase, the RPN backward is done 1.5 ms after it starts) -- off unless LOFT_EARLY_RPN=1
-        self.early_rpn = os.environ.get('LOFT_EARLY_RPN', '0') != '0'
+        # When the RPN losses are back-propagated ahead of loss.backward():
+        #   'end'  at the end of forward_train, on the main stream: its 1.3 ms of GEMMs
+        #          keep the GPU busy while the launch thread sums the losses, starts the autograd
+        #          engine and issues the first head-backward launches;
+        #   'side' right after the RPN loss, on a side stream under the proposal / sampling phase
+        #          (measured: no gain -- that phase's bubbles are many and short);
+        #          (measured: no gain either, 19.7 ms/step both ways);
+        #   '0'    (default) inside _TrunkFn.backward, like any other node.
+        self.early_rpn = os.environ.get('LOFT_EARLY_RPN', '0')
         self.current = None
         store.pre_finalize.append(self.flush)
 
@@ -554,13 +560,12 @@ class Trunk:
             prog.bwd.launch()
         prog.rpn_done = False
 
-    def early_rpn_backward(self, losses):
-        """Back-propagate the RPN losses right after they are computed: the RPN part of the trunk
-        backward then runs on a side stream underneath the host-bound proposal / sampling phase.
-        Returns the same dict with detached values (the outer loss.backward() must not visit
-        them again)."""
+    def early_rpn_backward(self, losses, when):
+        """Back-propagate the RPN losses ahead of the outer loss.backward() (see __init__).
+        Returns the same dict with detached values so the outer backward does not visit them
+        again."""
         prog = self.current
-        if prog is None or not self.early_rpn or not torch.is_grad_enabled():
+        if prog is None or self.early_rpn != when or not torch.is_grad_enabled():
             return losses
         terms = [t for v in losses.values() for t in (v if isinstance(v, (list, tuple)) else [v])]
         if not any(t.requires_grad for t in terms):
@@ -569,7 +574,7 @@ class Trunk:
         for t in terms[1:]:
             total = total + t
         grads = torch.autograd.grad(total, self.rpn_outs, allow_unused=True)
-        self.run_rpn_backward(prog, grads, side=True)
+        self.run_rpn_backward(prog, grads, side=(when == 'side'))
         return {k: ([t.detach() for t in v] if isinstance(v, (list, tuple)) else v.detach())
                 for k, v in losses.items()}
 
