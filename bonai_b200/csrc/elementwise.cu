@@ -263,33 +263,41 @@ __global__ void im2col_v4_kernel(const float4* __restrict__ x, float4* __restric
   }
 }
 
-// NCHW fp32 image (the 7x7/2 stem, C = 3): one thread per (row, tap) writes its C channels.
+// NCHW fp32 image (the 7x7/2 stem, C = 3): one thread per (output pixel, kernel row) gathers the
+// kw*C values of that kernel row (kw consecutive pixels of C image rows) and writes them as one
+// contiguous run of the im2col row; one extra "row" per pixel zero-fills the K padding.
 __global__ void im2col_nchw_kernel(const float* __restrict__ x, float* __restrict__ col, int N, int H,
                                    int W, int C, int kh, int kw, int stride, int pad, int Ho, int Wo,
                                    int Kpad) {
-  const int taps = kh * kw;
-  const int K = taps * C;
-  const int slots = taps + (Kpad > K ? 1 : 0);  // last slot zero-fills the padding columns
+  const int K = kh * kw * C;
+  const int slots = kh + (Kpad > K ? 1 : 0);
   const long long total = (long long)N * Ho * Wo * slots;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int tap = (int)(i % slots);
+    const int r = (int)(i % slots);
     const long long m = i / slots;
     float* dst = col + m * Kpad;
-    if (tap == taps) {
+    if (r == kh) {
       for (int k = K; k < Kpad; ++k) dst[k] = 0.f;
       continue;
     }
-    const int s = tap % kw, r = tap / kw;
     const int wo = (int)(m % Wo);
     const long long t = m / Wo;
     const int ho = (int)(t % Ho);
     const int n = (int)(t / Ho);
-    const int h = ho * stride - pad + r, w = wo * stride - pad + s;
-    const bool in = (h >= 0 && h < H && w >= 0 && w < W);
+    const int h = ho * stride - pad + r, w0 = wo * stride - pad;
+    dst += r * kw * C;
+    if (h < 0 || h >= H) {
+      for (int k = 0; k < kw * C; ++k) dst[k] = 0.f;
+      continue;
+    }
     for (int c = 0; c < C; ++c) {
-      const float v = in ? x[(((long long)n * C + c) * H + h) * W + w] : 0.f;
-      dst[tap * C + c] = tf32_rna(v);
+      const float* src = x + (((long long)n * C + c) * H + h) * W;
+      for (int s = 0; s < kw; ++s) {
+        const int w = w0 + s;
+        const float v = (w >= 0 && w < W) ? src[w] : 0.f;
+        dst[s * C + c] = tf32_rna(v);
+      }
     }
   }
 }
@@ -338,6 +346,37 @@ __global__ void col2im_v4_kernel(const float4* __restrict__ dcol, float4* __rest
 }
 
 // ---------------------------------------------------------------- pooling / sampling
+__global__ void maxpool3x3s2_v4_kernel(const float4* __restrict__ x, float4* __restrict__ y, int N,
+                                       int H, int W, int C4, int Ho, int Wo) {
+  const long long total = (long long)N * Ho * Wo * C4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4);
+    long long t = i / C4;
+    const int wo = (int)(t % Wo);
+    t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int h = ho * 2 - 1 + r;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int w = wo * 2 - 1 + s;
+        if (w < 0 || w >= W) continue;
+        const float4 v = x[(((long long)n * H + h) * W + w) * C4 + c];
+        m.x = fmaxf(m.x, v.x);
+        m.y = fmaxf(m.y, v.y);
+        m.z = fmaxf(m.z, v.z);
+        m.w = fmaxf(m.w, v.w);
+      }
+    }
+    y[i] = m;
+  }
+}
+
 __global__ void maxpool3x3s2_kernel(const float* __restrict__ x, float* __restrict__ y, int N,
                                     int H, int W, int C, int Ho, int Wo) {
   const long long total = (long long)N * Ho * Wo * C;
@@ -595,7 +634,7 @@ int loft_im2col(const float* x, float* col, int N, int H, int W, int C, int kh, 
   LOFT_CHECK_SHAPE(Kpad >= kh * kw * C && Kpad % 4 == 0, "im2col: bad Kpad %d", Kpad);
   if ((long long)N * Ho * Wo == 0) return LOFT_OK;
   if (nchw_input) {
-    const long long total = (long long)N * Ho * Wo * (kh * kw + 1);
+    const long long total = (long long)N * Ho * Wo * (kh + 1);
     im2col_nchw_kernel<<<grid_for(total, kT, 148 * 32), kT, 0, stream>>>(x, col, N, H, W, C, kh, kw,
                                                                         stride, pad, Ho, Wo, Kpad);
   } else {
@@ -628,7 +667,11 @@ int loft_maxpool3x3s2(const float* x, float* y, int N, int H, int W, int C, cuda
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const long long total = (long long)N * Ho * Wo * C;
   if (total == 0) return LOFT_OK;
-  maxpool3x3s2_kernel<<<grid_for(total, kT, 148 * 32), kT, 0, stream>>>(x, y, N, H, W, C, Ho, Wo);
+  if (C % 4 == 0)
+    maxpool3x3s2_v4_kernel<<<grid_for(total / 4, kT, 148 * 32), kT, 0, stream>>>(
+        reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), N, H, W, C / 4, Ho, Wo);
+  else
+    maxpool3x3s2_kernel<<<grid_for(total, kT, 148 * 32), kT, 0, stream>>>(x, y, N, H, W, C, Ho, Wo);
   LOFT_CUDA_LAUNCH_CHECK("maxpool3x3s2");
   return LOFT_OK;
 }

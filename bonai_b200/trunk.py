@@ -6,7 +6,7 @@ the frozen stem + layer1, the trainable ResNet stages (mmdet/models/backbones/re
 Instead of ~150 autograd nodes that each allocate, wrap and launch, this module writes that part
 as ONE autograd.Function whose forward and backward are fixed sequences of C-ABI launches over
 buffers allocated once: the sequence is *recorded* the first time it runs (`Tape`), then replayed
-as a CUDA graph -- one graph launch for the forward, one for the backward.
+as a CUDA graph -- one graph launch for the forward, two for the backward (RPN part, the rest).
 
 Because the whole backward is one hand-ordered program, ReLU / BN / residual backward never
 touches HBM on its own: every data-gradient launch applies, in its epilogue, the ReLU mask of
@@ -298,8 +298,9 @@ class _Program:
     def build_backward_rpn(self):
         """RPN part of the backward (needs only the RPN losses' gradient gR): fused-head and shared
         3x3 conv weight / bias gradients over all levels, and the gradient the RPN path sends into
-        each FPN map, written to self.B[l].  Runs early, on a side stream, while the launch thread
-        is busy with proposals / sampling (two_stage.forward_train)."""
+        each FPN map, written to self.B[l].  Its own program so that it can also be launched ahead
+        of loss.backward() (Trunk.early_rpn_backward); by default it runs first thing inside
+        _TrunkFn.backward."""
         rpn = self.model.rpn_head
         dev = self.dev
         with self.bwd_rpn:

@@ -138,6 +138,51 @@ def test_product_fails_loudly_without_cuda(model):
                             [torch.zeros(0, 4)], [torch.zeros(0, dtype=torch.long)])
 
 
+def test_trunk_eligibility_and_tape_replay(model, monkeypatch):
+    """Host logic of bonai_b200/trunk.py that needs no GPU: the LOFT R50-FPN-RPN composition is
+    recognised (and LOFT_TRUNK=0 turns the recorded path off); a Tape records what `_lib.call` is
+    asked to launch and replays it with the CURRENT stream substituted for the recorded one."""
+    from bonai_b200 import _lib as L
+    from bonai_b200 import trunk as T
+    assert T.Trunk.eligible(model)
+    monkeypatch.setenv('LOFT_TRUNK', '0')
+    assert not T.Trunk.eligible(model)
+    monkeypatch.delenv('LOFT_TRUNK')
+    model.backbone.style = 'caffe'
+    try:
+        assert not T.Trunk.eligible(model)
+    finally:
+        model.backbone.style = 'pytorch'
+
+    seen = []
+
+    class FakeLib:
+        def __getattr__(self, name):
+            def fn(*args):
+                seen.append((name, args))
+                return 0
+            return fn
+
+        def loft_last_error(self):
+            return b''
+
+    monkeypatch.setattr(L, '_lib', FakeLib())
+    monkeypatch.setattr(L, 'stream', lambda: 'STREAM-NOW')
+    tape = T.Tape('t')
+    with tape:
+        L.call('fill', 1, 2, 3.0, 'STREAM-AT-RECORD')
+        L.call('add', 'a', 'b', 'c', 4, 0, 'STREAM-AT-RECORD')
+    assert L.RECORD is None and [c[0] for c in tape.calls] == ['fill', 'add']
+    n0 = len(seen)
+    before = L.LAUNCHES[0]
+    tape.launch()
+    assert L.LAUNCHES[0] == before + 2
+    replayed = seen[n0:]
+    assert [r[0] for r in replayed] == ['loft_fill', 'loft_add']
+    assert all(r[1][-1] == 'STREAM-NOW' for r in replayed)
+    assert replayed[0][1][:-1] == (1, 2, 3.0)
+
+
 def test_abi_exports_every_declared_symbol():
     import __graft_entry__ as g
     g.build()
