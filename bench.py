@@ -336,7 +336,7 @@ def main():
         torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        trainer.train_step(data)
+        trainer.train_step(data, prefetch=data)
     sync_all()
     how = os.environ.get('LOFT_CLOCKS', 'nvml')
     clocks = ClockSampler(local) if how == 'smi' else NvmlClockSampler(local)
@@ -347,7 +347,7 @@ def main():
     e0.record()
     marks = []
     for _ in range(args.steps):
-        trainer.train_step(data)
+        trainer.train_step(data, prefetch=data)      # a training loop knows its next batch
         if os.environ.get('LOFT_STEP_TIMES'):
             ev = torch.cuda.Event(enable_timing=True)
             ev.record()
@@ -381,8 +381,11 @@ def main():
     # ---- end to end: pinned host inputs copied every step (on the trainer's copy stream, the way
     # a prefetching loader feeds it) and the loss vector read back every step
     host_batch = to_model_inputs(make_batch(seed=rank, pinned=True))
+    cur = trainer.stage(host_batch)
     for _ in range(5):                          # first use of the staging path (pinned copies,
-        trainer.train_step(trainer.stage(host_batch), read_logs='async')   # events, log buffers)
+        nxt = trainer.stage(host_batch)         # events, log buffers)
+        trainer.train_step(cur, read_logs='async', prefetch=nxt)
+        cur = nxt
     trainer.flush_logs()
     h2d_bytes = trainer.staged_bytes
     sync_all()
@@ -392,8 +395,8 @@ def main():
     marks = []
     for _ in range(args.steps):
         nxt = trainer.stage(host_batch)          # next batch's copies overlap this step
-        trainer.train_step(cur, read_logs='async')   # D2H of every step's loss vector, read one
-        cur = nxt                                    # step late so the launch thread never stalls
+        trainer.train_step(cur, read_logs='async', prefetch=nxt)   # D2H of every step's loss
+        cur = nxt                                # vector, read one step late
         if os.environ.get('LOFT_STEP_TIMES'):
             ev = torch.cuda.Event(enable_timing=True)
             ev.record()

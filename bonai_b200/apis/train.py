@@ -169,9 +169,12 @@ class Trainer:
         self.staged_bytes = nbytes
         return out
 
-    def train_step(self, data, read_logs=False):
+    def train_step(self, data, read_logs=False, prefetch=None):
         """forward + backward + gradient all-reduce + clip + SGD.  Returns the device-resident
-        packed log vector (and its key order); nothing synchronises the host unless read_logs."""
+        packed log vector (and its key order); nothing synchronises the host unless read_logs.
+        `prefetch`: the NEXT batch (device-resident or from `stage`) -- its input-only work (RPN
+        targets) is issued right after this step's optimizer launch, when the launch thread would
+        otherwise wait for the GPU to finish the backward."""
         model = self.model
         losses = model(**data)
         log_vars = OrderedDict()
@@ -198,6 +201,8 @@ class Trainer:
         self.store.sgd_step(self.current_lr(), self.momentum, self.weight_decay, self.max_norm,
                             grad_scale=1.0 / self.world)
         self.iter += 1
+        if prefetch is not None and hasattr(model, 'prefetch'):
+            model.prefetch(prefetch)
         packed = torch.stack([v.detach().reshape(()) for v in log_vars.values()])
         self._last_logs = (list(log_vars.keys()), packed)
         if read_logs == 'async':

@@ -139,7 +139,8 @@ class RPNHead(nn.Module):
         return cls, reg
 
     def forward_train(self, x, img_metas, gt_bboxes, gt_labels=None, gt_bboxes_ignore=None,
-                      proposal_cfg=None, rpn_outs=None, after_loss=None, **kwargs):
+                      proposal_cfg=None, rpn_outs=None, after_loss=None, proposals=None,
+                      **kwargs):
         outs = rpn_outs if rpn_outs is not None else self(x)
         if gt_labels is None:
             loss_inputs = outs + (gt_bboxes, img_metas)
@@ -150,6 +151,8 @@ class RPNHead(nn.Module):
             losses = after_loss(losses)
         if proposal_cfg is None:
             return losses
+        if proposals is not None:         # already produced inside the trunk's forward graph
+            return losses, proposals
         return losses, self.get_bboxes(*outs, img_metas, cfg=proposal_cfg, fixed_size=True)
 
     # ------------------------------------------------------------------ targets + loss
@@ -240,15 +243,27 @@ class RPNHead(nn.Module):
         for tup in per_level:
             for t in tup:
                 t.record_stream(main)
-        self._prefetched = (tuple(sizes), per_level, num_total, ev)
+        self._prefetched = (tuple(sizes), per_level, num_total, ev, ident)
+
+    @staticmethod
+    def _gt_ident(gt_bboxes):
+        return tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in gt_bboxes)
+
+    def has_prefetched(self, gt_bboxes):
+        """True if targets for exactly these GT tensors were already prefetched (by the previous
+        step's Trainer.train_step(..., prefetch=next_batch))."""
+        pre = self.__dict__.get('_prefetched')
+        return pre is not None and len(gt_bboxes) > 0 and gt_bboxes[0].is_cuda and \
+            pre[4] == self._gt_ident(gt_bboxes)
 
     def loss(self, cls_scores, bbox_preds, gt_bboxes, img_metas, gt_bboxes_ignore=None):
         """AnchorHead.loss / RPNHead.loss (anchor_head.py:429-497, rpn_head.py:46-77)."""
         featmap_sizes = [tuple(int(v) for v in f.size()[-2:]) for f in cls_scores]
         device = cls_scores[0].device
         pre = self.__dict__.pop('_prefetched', None)
-        if pre is not None and pre[0] == tuple(featmap_sizes):
-            _, per_level, num_total_samples, ev = pre
+        if pre is not None and pre[0] == tuple(featmap_sizes) and \
+                pre[4] == self._gt_ident(gt_bboxes):
+            _, per_level, num_total_samples, ev, _ = pre
             torch.cuda.current_stream(device).wait_event(ev)
         else:
             per_level, num_total_samples = self._build_targets(featmap_sizes, gt_bboxes, img_metas,

@@ -58,6 +58,20 @@ class TwoStageDetector(BaseDetector):
             t = self.__dict__['_trunk'] = Trunk(self, store) if ok else None
         return t
 
+    def prefetch(self, data):
+        """Start the input-only work of the NEXT step (RPN anchor targets: assignment + sampling,
+        ~3 ms of launch-thread time with a dozen host syncs) on the side stream now, while the GPU
+        is still busy with this step's backward.  `data` is the next batch as it will be passed
+        to forward_train (device-resident or staged by Trainer.stage)."""
+        if not (self.with_rpn and hasattr(self.rpn_head, 'prefetch_targets')):
+            return
+        gt = data.get('gt_bboxes')
+        img = data.get('img')
+        if not gt or img is None or not all(t.is_cuda for t in gt):
+            return
+        self.rpn_head.prefetch_targets(gt, data['img_metas'], img.shape[-2:],
+                                       data.get('ready_event'))
+
     def extract_feat(self, img):
         x = self.backbone(img)
         if self.with_neck:
@@ -86,10 +100,14 @@ class TwoStageDetector(BaseDetector):
         rpn_outs = None
         trunk = self._loft_trunk(store) if torch.is_grad_enabled() else None
         prefetch = self.with_rpn and hasattr(self.rpn_head, 'prefetch_targets') and \
-            len(gt_bboxes) > 0
+            len(gt_bboxes) > 0 and not self.rpn_head.has_prefetched(gt_bboxes)
+        proposal_cfg = self.train_cfg.get('rpn_proposal', self.test_cfg.rpn) if self.with_rpn \
+            else None
+        pre_proposals = None
         if trunk is not None:
-            x, fused = trunk(img)
+            x, fused = trunk(img, img_metas, proposal_cfg)
             rpn_outs = self.rpn_head.outs_from_fused(fused)
+            pre_proposals = trunk.proposals()
             if prefetch:
                 self.rpn_head.prefetch_targets(gt_bboxes, img_metas, img.shape[-2:], ready_event)
         else:
@@ -98,10 +116,9 @@ class TwoStageDetector(BaseDetector):
             x = self.extract_feat(img)
         losses = dict()
         if self.with_rpn:
-            proposal_cfg = self.train_cfg.get('rpn_proposal', self.test_cfg.rpn)
             rpn_losses, proposal_list = self.rpn_head.forward_train(
                 x, img_metas, gt_bboxes, gt_labels=None, gt_bboxes_ignore=gt_bboxes_ignore,
-                proposal_cfg=proposal_cfg, rpn_outs=rpn_outs,
+                proposal_cfg=proposal_cfg, rpn_outs=rpn_outs, proposals=pre_proposals,
                 after_loss=(lambda d: trunk.early_rpn_backward(d, 'side'))
                 if trunk is not None else None)
         else:

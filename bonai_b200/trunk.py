@@ -462,15 +462,15 @@ class Trunk:
                        for p in mod.parameters() if p.requires_grad]
         self.side = torch.cuda.Stream(device=store.device)
         # When the RPN losses are back-propagated ahead of loss.backward():
-        #   'end'  at the end of forward_train, on the main stream: its 1.3 ms of GEMMs
-        #          keep the GPU busy while the launch thread sums the losses, starts the autograd
-        #          engine and issues the first head-backward launches;
+        #   'end'  (default) at the end of forward_train, on the main stream: its 1.3 ms of GEMMs
+        #          keep the GPU busy while the launch thread sums the losses and starts the
+        #          autograd engine (measured 18.4 -> 18.2 ms/step);
         #   'side' right after the RPN loss, on a side stream under the proposal / sampling phase
         #          (measured: no gain -- that phase's bubbles are many and short);
-        #          (measured: no gain either, 19.7 ms/step both ways);
-        #   '0'    (default) inside _TrunkFn.backward, like any other node.
-        self.early_rpn = os.environ.get('LOFT_EARLY_RPN', '0')
+        #   '0'    inside _TrunkFn.backward, like any other node.
+        self.early_rpn = os.environ.get('LOFT_EARLY_RPN', 'end')
         self.current = None
+        self.step_ctx = (None, None)
         store.pre_finalize.append(self.flush)
 
     @staticmethod
@@ -492,7 +492,9 @@ class Trunk:
 
     def run_forward(self, img):
         N, _, H, W = img.shape
-        key = (N, H, W)
+        metas, pcfg = self.step_ctx
+        shapes = tuple(tuple(m['img_shape'][:2]) for m in metas) if metas else None
+        key = (N, H, W, shapes)
         prog = self.progs.get(key)
         if prog is None:
             if len(self.progs) >= 2:
@@ -503,13 +505,51 @@ class Trunk:
             prog.build_forward()
             prog.B = [torch.zeros_like(f) for f in prog.P]          # total gradient of FPN map l
             prog.gR = [torch.zeros_like(o) for o in prog.rpn_out]   # gradient of fused RPN map l
+            prog.proposals, prog.proposals_fresh = None, False
             if prog.use_graph:
-                prog.fwd.capture()
+                self._capture_forward(prog, metas, pcfg)
         else:
             prog.fwd.launch()
+            prog.proposals_fresh = prog.proposals is not None and prog.fwd.graph is not None
         prog.rpn_done = False
         self.current = prog
         return prog
+
+    def _capture_forward(self, prog, metas, pcfg):
+        """Forward graph = the recorded launches + (when the caller gave the proposal config) the
+        whole RPN proposal generation: per-level sigmoid / sort / top-k decode, the global sort,
+        per-level NMS and the fixed-size [N, nms_post, 5] proposal block all have static shapes,
+        so ~80 small kernels of RPNHead.get_bboxes ride in the same graph launch instead of
+        being issued one by one by the (forward-phase-bound) launch thread."""
+        from .models.dense_heads.rpn_head import RPNHead
+        rpn = self.model.rpn_head
+        want = pcfg is not None and metas is not None and RPNHead.forced_proposals is None and \
+            os.environ.get('LOFT_GRAPH_PROPOSALS', '1') != '0'
+        for with_props in ([True, False] if want else [False]):
+            g = torch.cuda.CUDAGraph()
+            try:
+                with torch.no_grad(), torch.cuda.graph(g, capture_error_mode='thread_local'):
+                    prog.fwd.replay()
+                    if with_props:
+                        outs = rpn.outs_from_fused([t.permute(0, 3, 1, 2) for t in prog.rpn_out])
+                        prog.proposals = rpn.get_bboxes(*outs, metas, cfg=pcfg, fixed_size=True)
+                prog.fwd.graph = g
+                return
+            except Exception as e:      # an op in get_bboxes that cannot be captured
+                prog.proposals = None
+                if not with_props:
+                    raise
+                import warnings
+                warnings.warn(f'proposal generation not captured into the forward graph: {e}')
+
+    def proposals(self):
+        """The proposal block the forward graph produced for the current step (None on the
+        recording step, when proposals are forced by a test, or when not captured)."""
+        from .models.dense_heads.rpn_head import RPNHead
+        prog = self.current
+        if prog is None or not prog.proposals_fresh or RPNHead.forced_proposals is not None:
+            return None
+        return prog.proposals
 
     def run_rpn_backward(self, prog, grads, side):
         for buf, g in zip(prog.gR, grads):
@@ -586,7 +626,8 @@ class Trunk:
         if prog is not None and prog.rpn_done:
             self.run_main_backward(prog, [None] * len(prog.P))
 
-    def __call__(self, img):
+    def __call__(self, img, img_metas=None, proposal_cfg=None):
+        self.step_ctx = (img_metas, proposal_cfg)
         outs = _TrunkFn.apply(img, self, *self.params)
         n = len(outs) // 2
         self.rpn_outs = list(outs[n:])

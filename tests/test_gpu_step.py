@@ -338,3 +338,26 @@ def test_recorded_trunk_graph_matches_module_path(monkeypatch):
     for k in wb:
         d = float((wa[k] - wb[k]).norm())
         assert d <= 2e-2 * float(wb[k].norm()) + 1e-6, (k, d)
+
+
+def test_graph_captured_proposals_equal_eager(full_size):
+    """From the second step on, the RPN proposals come out of the trunk's forward CUDA graph
+    (sigmoid / sort / decode / per-level NMS captured with it).  They must equal, bit for bit, what
+    RPNHead.get_bboxes computes eagerly from the same head outputs."""
+    model, trainer, data = full_size
+    for _ in range(2):
+        trainer.train_step(data)
+    trunk = model._trunk
+    assert trunk is not None
+    pre = trunk.proposals()
+    assert pre is not None, 'proposal generation was not captured into the forward graph'
+    prog = trunk.current
+    outs = model.rpn_head.outs_from_fused([t.permute(0, 3, 1, 2) for t in prog.rpn_out])
+    cfg = model.train_cfg.get('rpn_proposal', model.test_cfg.rpn)
+    with torch.no_grad():
+        eager = model.rpn_head.get_bboxes(*outs, data['img_metas'], cfg=cfg, fixed_size=True)
+        ragged = model.rpn_head.get_bboxes(*outs, data['img_metas'], cfg=cfg)
+    for a, b, c in zip(pre, eager, ragged):
+        assert torch.equal(a, b)
+        assert int(a._loft_num_valid) == int(b._loft_num_valid) == c.shape[0]
+        assert torch.equal(a[:c.shape[0]], c)

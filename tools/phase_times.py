@@ -16,7 +16,7 @@ dev = torch.device('cuda:0')
 trainer = Trainer(model, cfg, dev)
 data = bench.to_model_inputs(bench.make_batch(0, device=dev))
 for _ in range(5):
-    trainer.train_step(data)
+    trainer.train_step(data, prefetch=data)
 torch.cuda.synchronize()
 
 marks = []
@@ -41,7 +41,7 @@ for it in range(3):
     marks.clear()
     torch.cuda.synchronize()
     mark('step:begin')
-    trainer.train_step(data)
+    trainer.train_step(data, prefetch=data)
     mark('step:end')
     torch.cuda.synchronize()
     d = {n: (e, t) for n, e, t in marks}

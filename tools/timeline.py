@@ -17,11 +17,11 @@ dev = torch.device('cuda:0')
 trainer = Trainer(model, cfg, dev)
 data = bench.to_model_inputs(bench.make_batch(0, device=dev))
 for _ in range(6):
-    trainer.train_step(data)
+    trainer.train_step(data, prefetch=data)
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     for _ in range(3):
-        trainer.train_step(data)
+        trainer.train_step(data, prefetch=data)
     torch.cuda.synchronize()
 ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
 ks = sorted([(e.time_range.start, e.time_range.end, e.name) for e in ev], key=lambda t: t[0])

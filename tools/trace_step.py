@@ -19,7 +19,7 @@ dev = torch.device('cuda:0')
 trainer = Trainer(model, cfg, dev)
 data = bench.to_model_inputs(bench.make_batch(0, device=dev))
 for _ in range(3):
-    trainer.train_step(data)
+    trainer.train_step(data, prefetch=data)
 torch.cuda.synchronize()
 L.TRACE = []
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
