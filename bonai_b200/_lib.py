@@ -103,6 +103,8 @@ def call(name, *args):
         return
     if name == 'nms_sorted':
         LAUNCHES[0] += 3 * int(args[2].value) + 1      # per image: fill+max+mask; one scan
+    elif name == 'nms_segmented':
+        LAUNCHES[0] += 2 * int(args[4].value) + 3      # per image: fill+max; mask, scan, compact
     else:
         LAUNCHES[0] += _KERNELS_PER_CALL.get(name, 1)
     rc = fn(*args)
