@@ -18,7 +18,8 @@
 
 namespace {
 
-constexpr int kStages = 4;
+constexpr int kStages = 4;                    // stages of the largest (256-pixel) tile
+constexpr int kMaxStages = 8;                 // narrower tiles split the same arena into more
 constexpr int kBlockC = 128;                  // UMMA M: channels per tile
 constexpr int kMaxN = 256;                    // UMMA N max: pixels per tile
 constexpr int kKB = 32;                       // k elements per stage (128 B of fp32)
@@ -49,6 +50,8 @@ struct GemmParams {
   int num_kb;     // k-blocks per tile (FPROP/DGRAD); total k-blocks (WGRAD)
   int kb_per_split;
   int n_mma;  // UMMA N
+  int stages;            // operand pipeline depth (4..8) and bytes per stage, set by launch()
+  uint32_t stage_bytes;
   uint32_t tx_bytes;
   uint64_t a_desc, b_desc;  // smem descriptor templates (address field zero)
   uint32_t a_kstep, b_kstep;
@@ -114,11 +117,17 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
-  uint64_t* full_bar = bars;                    // [kStages]
-  uint64_t* empty_bar = bars + kStages;         // [kStages]
-  uint64_t* tfull_bar = bars + 2 * kStages;     // [2]
-  uint64_t* tempty_bar = bars + 2 * kStages + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint64_t* full_bar = bars;                       // [kMaxStages]
+  uint64_t* empty_bar = bars + kMaxStages;         // [kMaxStages]
+  uint64_t* tfull_bar = bars + 2 * kMaxStages;     // [2]
+  uint64_t* tempty_bar = bars + 2 * kMaxStages + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  // The 192 KB operand arena holds p.stages stages of p.stage_bytes each (16 KB of A + 128 B per
+  // pixel column of B): 4 for 256-column tiles, up to 8 for 64-column ones.  Small tiles are
+  // bound by the TMA round trip per stage, not by bytes, so depth is what they need (measured:
+  // layer4's 3x3 took 51 us whatever the tile width with 4 stages).
+  const int n_stages = p.stages;
+  const uint32_t stage_bytes = p.stage_bytes;
   int* row_tab = reinterpret_cast<int*>(smem + kStages * kStageBytes + 256);
 
   const int warp = threadIdx.x >> 5;
@@ -127,7 +136,7 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < kMaxStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
@@ -153,7 +162,8 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      uint32_t it = 0;
+      int s = 0;
+      uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         int t = tile;
         const int ct = t % p.nct;
@@ -180,12 +190,10 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
           n0 += gn0;
         }
         const int tdh = tap / 3 - 1, tdw = tap % 3 - 1;  // WGRAD_CONV tap shift
-        for (int kbi = 0; kbi < kb_count; ++kbi, ++it) {
+        for (int kbi = 0; kbi < kb_count; ++kbi) {
           const int kb = kb_begin + kbi;
-          const int s = it % kStages;
-          const uint32_t ph = (it / kStages) & 1u;
           mbar_wait(&empty_bar[s], ph ^ 1u);
-          uint8_t* sa = smem + s * kStageBytes;
+          uint8_t* sa = smem + s * stage_bytes;
           uint8_t* sb = sa + kABytes;
           mbar_expect_tx(&full_bar[s], p.tx_bytes);
           switch (p.mode) {
@@ -228,13 +236,19 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
               break;
             }
           }
+          if (++s == n_stages) {
+            s = 0;
+            ph ^= 1u;
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      uint32_t it = 0, lt = 0;
+      uint32_t lt = 0;
+      int s = 0;
+      uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
         int kb_count = p.num_kb;
         if (is_wgrad) {
@@ -245,12 +259,10 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
         mbar_wait(&tempty_bar[as], aph ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * kMaxN;
-        for (int kbi = 0; kbi < kb_count; ++kbi, ++it) {
-          const int s = it % kStages;
-          const uint32_t ph = (it / kStages) & 1u;
+        for (int kbi = 0; kbi < kb_count; ++kbi) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * kStageBytes);
+          const uint32_t sa = smem_u32(smem + s * stage_bytes);
           const uint32_t sb = sa + kABytes;
           const uint64_t ad = p.a_desc + (uint64_t)((sa >> 4) & 0x3FFFu);
           const uint64_t bd = p.b_desc + (uint64_t)((sb >> 4) & 0x3FFFu);
@@ -260,6 +272,10 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
                       p.idesc, (kbi | ks) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[s]);
+          if (++s == n_stages) {
+            s = 0;
+            ph ^= 1u;
+          }
         }
         umma_commit(&tfull_bar[as]);
       }
@@ -640,6 +656,17 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p_in,
     if (p.out_map == 1) rows *= 4;
     const long long ld = p.ldo > p.ldr ? p.ldo : p.ldr;
     p.fast_epi = (rows + 1) * ld < (1ll << 31) ? 1 : 0;
+    // operand arena: as many stages as fit (n_mma is a multiple of 16 -> stages stay 1 KB aligned)
+    p.stage_bytes = (uint32_t)(kABytes + p.n_mma * kKB * 4);
+    int st = (kStages * kStageBytes) / (int)p.stage_bytes;
+    static int max_st = -1;
+    if (max_st < 0) {
+      const char* e = getenv("LOFT_MAX_STAGES");
+      max_st = e ? atoi(e) : kMaxStages;
+      if (max_st < 2) max_st = 2;
+      if (max_st > kMaxStages) max_st = kMaxStages;
+    }
+    p.stages = st < max_st ? st : max_st;
   }
   static bool attr_set = false;
   if (!attr_set) {
@@ -686,8 +713,18 @@ long long wave_cost(long long tiles, int n) {
   return waves * (n + 48);
 }
 
+int forced_tile_n() {   // bring-up / tuning only: LOFT_TILE_N=256|128|64 overrides the pickers
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LOFT_TILE_N");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
 int pick_n_2d(long long P, int nct) {
   if (P < 256) return round16((int)P);
+  if (forced_tile_n() > 0) return forced_tile_n();
   int best = 256;
   long long bc = wave_cost((long long)nct * loft_cdiv(P, 256), 256);
   for (int n : {128, 64}) {
@@ -723,6 +760,10 @@ void pick_pixel_tile(int N, int H, int W, int nct, int& tn, int& th, int& tw) {
       tw = c;
     }
   };
+  if (forced_tile_n() > 0) {
+    pixel_tile_for(forced_tile_n(), N, H, W, tn, th, tw);
+    return;
+  }
   for (int target : {256, 128, 64}) {
     int a, b, c;
     pixel_tile_for(target, N, H, W, a, b, c);
