@@ -453,7 +453,9 @@ class _TrunkFn(Function):
 
 
 class Trunk:
-    """Per-model manager: one recorded program set per input shape (at most two shapes cached)."""
+    """Per-model manager: one recorded program set per input shape (at most four shapes cached,
+    oldest evicted).  A program owns its activations, so only ONE step per program may be in
+    flight: forward, then backward, then the next forward."""
 
     def __init__(self, model, store):
         self.model, self.store = model, store
@@ -497,7 +499,7 @@ class Trunk:
         key = (N, H, W, shapes)
         prog = self.progs.get(key)
         if prog is None:
-            if len(self.progs) >= 2:
+            if len(self.progs) >= 4:          # ~3 GB of static buffers per 2x1024^2 program
                 self.progs.pop(next(iter(self.progs)))
             prog = self.progs[key] = _Program(self.model, N, H, W, self.store.device, True)
         prog.img.copy_(img)
