@@ -319,6 +319,9 @@ def main():
         local = int(os.environ.get('LOCAL_RANK', rank))
     torch.cuda.set_device(local)
     device = torch.device('cuda', local)
+    # the GPU arm does no CPU math worth a thread pool; N ranks x os.cpu_count() spinning OpenMP
+    # workers only compete with the launch threads for the box's cores
+    torch.set_num_threads(max(1, min(4, (os.cpu_count() or 4) // max(world, 1))))
     torch.manual_seed(1234)                          # identical initial weights on every rank
     cfg = Config.fromfile(CFG)
     model = build_detector(cfg.model, train_cfg=cfg.train_cfg, test_cfg=cfg.test_cfg)
@@ -344,16 +347,48 @@ def main():
         clocks.start()
     L.LAUNCHES[0] = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wd = None
+    if os.environ.get('LOFT_WATCHDOG'):
+        # debugging aid: sample every Python thread's stack each 5 ms; after the loop print what
+        # the launch threads were doing during any step that took more than twice the median
+        import collections, traceback
+        wd = dict(samples=[], stop=threading.Event(), host=[])
+
+        def _sample():
+            me = threading.get_ident()
+            while not wd['stop'].is_set():
+                t = time.perf_counter()
+                for tid, fr in sys._current_frames().items():
+                    if tid != me:
+                        st = traceback.extract_stack(fr)[-4:]
+                        wd['samples'].append((t, tid, ' < '.join(
+                            f'{os.path.basename(f.filename)}:{f.lineno}:{f.name}' for f in reversed(st))))
+                time.sleep(0.005)
+        threading.Thread(target=_sample, daemon=True).start()
     e0.record()
     marks = []
     for _ in range(args.steps):
         trainer.train_step(data, prefetch=data)      # a training loop knows its next batch
+        if wd is not None:
+            wd['host'].append(time.perf_counter())
         if os.environ.get('LOFT_STEP_TIMES'):
             ev = torch.cuda.Event(enable_timing=True)
             ev.record()
             marks.append(ev)
     e1.record()
     sync_all()
+    if wd is not None:
+        wd['stop'].set()
+        hs = wd['host']
+        d = [b - a for a, b in zip(hs[:-1], hs[1:])]
+        med = sorted(d)[len(d) // 2] if d else 0
+        for i, dt in enumerate(d):
+            if dt > 2 * med:
+                c = collections.Counter(s for t, tid, s in wd['samples'] if hs[i] <= t <= hs[i + 1])
+                print(f'[rank {rank}] slow step {i + 1}: host {dt * 1e3:.1f} ms (median {med * 1e3:.1f}); '
+                      f'top stacks:', file=sys.stderr)
+                for s, n in c.most_common(6):
+                    print(f'    {n:4d}  {s}', file=sys.stderr)
     if marks and rank == 0:
         ts = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
         print('per-step ms: ' + ' '.join(f'{t:.1f}' for t in ts), file=sys.stderr)

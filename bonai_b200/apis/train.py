@@ -201,7 +201,8 @@ class Trainer:
         self.store.sgd_step(self.current_lr(), self.momentum, self.weight_decay, self.max_norm,
                             grad_scale=1.0 / self.world)
         self.iter += 1
-        if prefetch is not None and hasattr(model, 'prefetch'):
+        if prefetch is not None and hasattr(model, 'prefetch') and \
+                os.environ.get('LOFT_PREFETCH', '1') != '0':
             model.prefetch(prefetch)
         packed = torch.stack([v.detach().reshape(()) for v in log_vars.values()])
         self._last_logs = (list(log_vars.keys()), packed)
