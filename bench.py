@@ -89,7 +89,7 @@ class NvmlClockSampler:
     were measured to stall kernel launches for 20-170 ms now and then, which a 20 ms step cannot
     hide).  Samples SM clock + clock-event reasons every `period` seconds during the timed region."""
 
-    def __init__(self, index=0, period=0.25):
+    def __init__(self, index=0, period=0.05):
         self.index, self.period = index, period
         self.sm, self.reasons, self.max_sm = [], set(), None
         self.stop_flag = threading.Event()
