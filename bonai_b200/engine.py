@@ -226,7 +226,6 @@ class ParamStore:
         ver = self.P._version
         if not force and self._seen_version == ver:
             return
-        n0 = 0 if not self._frozen_ready else 0
         end = self.total
         L.call('copy2d', L.ptr(self.P), L.ll(end), L.ptr(self.T), L.ll(end), L.ll(1),
                ctypes.c_int(end), ctypes.c_int(0), ctypes.c_int(1), L.stream())

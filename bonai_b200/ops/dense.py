@@ -2,9 +2,11 @@
 
 Activations are logically NCHW (the reference's module protocol) but physically NHWC
 (torch.channels_last); every Function allocates its outputs that way so no layout conversion
-happens between layers.  Weight / bias / BN-affine gradients are accumulated by the kernels
-directly into the ParamStore's flat gradient buffer; the Functions return ``None`` for those
-inputs (they are passed as tensors only so autograd schedules the node).
+happens between layers.  Weight / bias / BN-beta gradients are accumulated by the kernels
+directly into the ParamStore's flat gradient buffer (BN-gamma gradients are derived from the
+weight gradients afterwards, engine._bn_finalize); the Functions return ``None`` for those inputs
+(they are passed as tensors only so autograd schedules the node).  The static trunk of the LOFT
+model does not go through these Functions in training -- see bonai_b200/trunk.py.
 """
 import ctypes
 
@@ -120,7 +122,7 @@ def link_chain(specs):
 
 
 def _fprop(spec, x, residual):
-    """Returns (y, z_raw_or_None, saved_input_for_wgrad)."""
+    """Returns (y, saved_input_for_wgrad)."""
     w = spec.wref.w
     dev = x.device
     N, Cin, H, W = x.shape
@@ -131,7 +133,6 @@ def _fprop(spec, x, residual):
     xn = nhwc(x)
     y = new_nhwc(N, Cout, Ho, Wo, dev)
     yn = y.permute(0, 2, 3, 1)
-    z = None
     rn = nhwc(residual) if residual is not None else None
     e = L.make_epilogue(shift=spec.bias, residual=rn,
                         ldr=(rn.shape[-1] if rn is not None else 0),
@@ -162,7 +163,7 @@ def _fprop(spec, x, residual):
         L.call('gemm_fprop', L.ptr(col), L.ptr(w), L.ptr(yn), L.ll(N * Ho * Wo), i32(Kp), i32(Cout),
                L.ll(Kp), L.ll(Kp), L.ll(Cout), i32(Ho), i32(Wo), ctypes.byref(e), st)
         saved = col
-    return y, z, saved
+    return y, saved
 
 
 class _ConvFn(Function):
@@ -170,20 +171,20 @@ class _ConvFn(Function):
 
     @staticmethod
     def forward(ctx, x, residual, spec, *triggers):
-        y, z, saved = _fprop(spec, x, residual)
+        y, saved = _fprop(spec, x, residual)
         ctx.spec = spec
         ctx.x_shape = tuple(x.shape)
         ctx.has_res = residual is not None
         ctx.res_shape = tuple(residual.shape) if residual is not None else None
         relu_eff = spec.relu and not spec.grad_premasked
         xin = nhwc(x) if spec.premask_in else None
-        ctx.save_for_backward(saved, y if relu_eff else None, z, xin)
+        ctx.save_for_backward(saved, y if relu_eff else None, xin)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         spec = ctx.spec
-        saved, y, z, xin = ctx.saved_tensors
+        saved, y, xin = ctx.saved_tensors
         relu_eff = spec.relu and not spec.grad_premasked
         _queue_finalize(spec.store)
         st = L.stream()
