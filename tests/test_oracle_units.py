@@ -154,3 +154,69 @@ def test_cross_entropy_known_answer():
     # class_weight; here the plain values the path relies on: CE([[100,-100]],[1]) = 200
     import torch.nn.functional as F
     assert float(F.cross_entropy(torch.Tensor([[100., -100.]]), torch.LongTensor([1]))) == 200.
+
+
+def test_level_by_level_nms_equals_batched_nms():
+    """The product runs the RPN's batched NMS level by level (loft_nms_segmented): boxes of
+    different levels are pushed (max+1) apart by batched_nms, so they never suppress each other.
+    Restated with the oracle on CPU: per-level NMS on the SAME offset coordinates, kept boxes merged
+    back in global score order and cut to max_keep, equals the oracle's batched_nms (itself pinned
+    to the reference's golden vectors above), ties included."""
+    import torch
+    from oracle import ops_cpu as O
+    g = torch.Generator().manual_seed(11)
+    sizes = (300, 300, 120, 33, 1)
+    ctr = torch.rand(12, 2, generator=g) * 400 + 50
+    boxes, scores, ids = [], [], []
+    for l, k in enumerate(sizes):
+        c = ctr[torch.randint(0, 12, (k,), generator=g)] + torch.randn(k, 2, generator=g) * 5
+        wh = torch.rand(k, 2, generator=g) * 50 + 6
+        boxes.append(torch.cat([c - wh / 2, c + wh / 2], 1).clamp(0, 512))
+        scores.append((torch.rand(k, generator=g) * 40).round() / 40)        # many exact ties
+        ids.append(torch.full((k,), l, dtype=torch.long))
+    boxes, scores, ids = torch.cat(boxes), torch.cat(scores), torch.cat(ids)
+    _, keep_ref = O.batched_nms(boxes, scores, ids, 0.7)
+    # level by level, with batched_nms's fp32 offsets
+    off = ids.to(boxes) * (boxes.max() + 1)
+    shifted = boxes + off[:, None]
+    kept = torch.zeros(boxes.shape[0], dtype=torch.bool)
+    for l in range(len(sizes)):
+        sel = torch.nonzero(ids == l)[:, 0]
+        _, k = O.nms(shifted[sel], scores[sel], 0.7)
+        kept[sel[k]] = True
+    order = torch.sort(scores, descending=True, stable=True)[1]
+    merged = order[kept[order]]
+    assert torch.equal(merged, keep_ref)
+    assert torch.equal(merged[:100], keep_ref[:100])                          # max_keep cut
+
+
+def test_bn_fold_identities():
+    """The product folds eval-mode BN into the conv weights and recovers the BN gradients from the
+    weight gradient (loft_bn_fold_weights / loft_bn_finalize).  The algebra, checked
+    against torch autograd in float64: with W' = s*W, shift = beta - mean*s, s = gamma*rstd,
+      dW = s * dW',   dbeta = sum_p dY,   dgamma = rstd * (sum_k W*dW' - mean*dbeta)."""
+    import torch
+    import torch.nn.functional as F
+    torch.manual_seed(3)
+    x = torch.randn(3, 8, 9, 9, dtype=torch.float64)
+    w = torch.randn(12, 8, 3, 3, dtype=torch.float64, requires_grad=True)
+    gamma = (torch.rand(12, dtype=torch.float64) + 0.3).requires_grad_(True)
+    gamma.data[5] = 0.0                                   # zero_init_residual corner
+    beta = torch.randn(12, dtype=torch.float64, requires_grad=True)
+    mean, var = torch.randn(12, dtype=torch.float64), torch.rand(12, dtype=torch.float64) + 0.5
+    y = F.relu(F.batch_norm(F.conv2d(x, w, padding=1), mean, var, gamma, beta, False, 0.0, 1e-5))
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    rstd = 1.0 / torch.sqrt(var + 1e-5)
+    s = (gamma * rstd).detach()
+    wf = (w.detach() * s[:, None, None, None]).requires_grad_(True)       # folded weights
+    shift = (beta - mean * gamma * rstd).detach().requires_grad_(True)
+    y2 = F.relu(F.conv2d(x, wf, padding=1) + shift[None, :, None, None])
+    assert torch.allclose(y2, y.detach(), atol=1e-12)
+    y2.backward(dy)
+    dwf, dbeta = wf.grad, shift.grad
+    assert torch.allclose(dbeta, beta.grad, atol=1e-10)
+    assert torch.allclose(dwf * s[:, None, None, None], w.grad, atol=1e-10)
+    dgamma = rstd * ((w.detach() * dwf).sum((1, 2, 3)) - mean * dbeta)
+    assert torch.allclose(dgamma, gamma.grad, atol=1e-9)
+    assert gamma.grad[5].abs() > 0 and w.grad[5].abs().max() == 0       # gamma=0: dW=0, dgamma!=0
