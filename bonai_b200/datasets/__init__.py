@@ -1,0 +1,1 @@
+from .gpu_pipeline import GpuTrainPipeline, image_prep, mask_flip_pad  # noqa: F401

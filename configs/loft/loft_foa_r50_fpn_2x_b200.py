@@ -81,3 +81,19 @@ log_level = 'INFO'
 load_from = None
 resume_from = None
 workflow = [('train', 1)]
+
+# post-load training pipeline (same values as the reference's
+# configs/_base_/datasets/bonai_instance.py:3-17); bonai_b200.datasets.GpuTrainPipeline.from_cfg
+# runs RandomFlip / Normalize / Pad / formatting on the device
+img_norm_cfg = dict(mean=[123.675, 116.28, 103.53], std=[58.395, 57.12, 57.375], to_rgb=True)
+train_pipeline = [
+    dict(type='LoadImageFromFile'),
+    dict(type='LoadAnnotations', with_bbox=True, with_mask=True, with_offset=True),
+    dict(type='Resize', img_scale=(1024, 1024), keep_ratio=True),
+    dict(type='RandomFlip', flip_ratio=0.5, direction=['horizontal', 'vertical']),
+    dict(type='Normalize', **img_norm_cfg),
+    dict(type='Pad', size_divisor=32),
+    dict(type='DefaultFormatBundle'),
+    dict(type='Collect', keys=['img', 'gt_bboxes', 'gt_labels', 'gt_masks', 'gt_offsets']),
+]
+data = dict(samples_per_gpu=2, workers_per_gpu=2, train=dict(type='BONAI', pipeline=train_pipeline))

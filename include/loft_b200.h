@@ -185,6 +185,19 @@ int loft_bbox_encode(const float* props, const float* gts, long long n, float s0
 int loft_offset_target(const float* props, const float* gt_offsets, const long long* gt_inds,
                        long long P, float std_x, float std_y, float* out, cudaStream_t stream);
 
+/* ---- device side of the post-load training pipeline (pipeline.cu) -----------------------------
+ * configs/_base_/datasets/bonai_instance.py:5-17 on a 1024^2 BONAI tile (Resize is the identity):
+ * RandomFlip (transforms.py:484-488, mmcv.imflip) -> Normalize (:655-676, mmcv.imnormalize: BGR->RGB,
+ * subtract mean in fp32, multiply by 1/std as a double scalar) -> Pad to a multiple of 32 with 0
+ * (:571-600) -> HWC->CHW (formating.py:191-230) in one pass over the uint8 image;
+ * BitmapMasks.flip + pad (core/mask/structures.py:218-240) in one pass over the uint8 bitmaps.
+ * flip: 0 none, 1 horizontal, 2 vertical.  mean3 / std3 are HOST pointers to 3 floats (RGB order). */
+int loft_image_prep(const uint8_t* img_hwc, float* out_chw, int H, int W, int Hp, int Wp,
+                    const float* mean3, const float* std3, int to_rgb, int flip,
+                    cudaStream_t stream);
+int loft_mask_flip_pad(const uint8_t* in, uint8_t* out, long long G, int H, int W, int Hp, int Wp,
+                       int flip, cudaStream_t stream);
+
 /* ---- losses (loss.cu) ----------------------------------------------------------------------------
  * mode 0 = BCE-with-logits (cross_entropy_loss.py:58-125), 1 = L1, 2 = SmoothL1
  * (smooth_l1_loss.py:8-42); sums are accumulated into device scalars (weight_reduce_loss,
