@@ -55,7 +55,8 @@ __global__ void image_prep_kernel(const uint8_t* __restrict__ img, float* __rest
 
 // one thread per 16 consecutive output bytes of one mask row
 __global__ void mask_flip_pad_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
-                                     long long G, int H, int W, int Hp, int Wp, int flip) {
+                                     long long G, int H, int W, int Hp, int Wp, int flip,
+                                     int aligned16) {
   const int Wq = Wp >> 4;
   const long long total = G * Hp * Wq;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -68,12 +69,32 @@ __global__ void mask_flip_pad_kernel(const uint8_t* __restrict__ in, uint8_t* __
     if (y < H) {
       const int ys = (flip == 2) ? H - 1 - y : y;
       const uint8_t* row = in + (g * H + ys) * (long long)W;
+      if (aligned16) {
+        // rows are 16-byte aligned and W % 16 == 0: one 16-byte load per thread; a horizontal
+        // flip reads the mirrored chunk and reverses its bytes in registers
+        if (x0 < W) {
+          if (flip == 1) {
+            const uint4 v = *reinterpret_cast<const uint4*>(row + (W - 16 - x0));
+            w[0] = __byte_perm(v.w, 0, 0x0123);
+            w[1] = __byte_perm(v.z, 0, 0x0123);
+            w[2] = __byte_perm(v.y, 0, 0x0123);
+            w[3] = __byte_perm(v.x, 0, 0x0123);
+          } else {
+            const uint4 v = *reinterpret_cast<const uint4*>(row + x0);
+            w[0] = v.x;
+            w[1] = v.y;
+            w[2] = v.z;
+            w[3] = v.w;
+          }
+        }
+      } else {
 #pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        const int x = x0 + k;
-        if (x < W) {
-          const int xs = (flip == 1) ? W - 1 - x : x;
-          w[k >> 2] |= (uint32_t)row[xs] << (8 * (k & 3));
+        for (int k = 0; k < 16; ++k) {
+          const int x = x0 + k;
+          if (x < W) {
+            const int xs = (flip == 1) ? W - 1 - x : x;
+            w[k >> 2] |= (uint32_t)row[xs] << (8 * (k & 3));
+          }
         }
       }
     }
@@ -122,7 +143,9 @@ int loft_mask_flip_pad(const uint8_t* in, uint8_t* out, long long G, int H, int 
   LOFT_CHECK_ARG(flip >= 0 && flip <= 2, "mask_flip_pad: flip must be 0, 1 or 2");
   if (G == 0) return LOFT_OK;
   const long long total = G * Hp * (Wp / 16);
-  mask_flip_pad_kernel<<<grid_for(total), 256, 0, stream>>>(in, out, G, H, W, Hp, Wp, flip);
+  const int aligned16 = (W % 16 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
+  mask_flip_pad_kernel<<<grid_for(total), 256, 0, stream>>>(in, out, G, H, W, Hp, Wp, flip,
+                                                            aligned16);
   LOFT_CUDA_LAUNCH_CHECK("mask_flip_pad");
   return LOFT_OK;
 }
