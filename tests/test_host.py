@@ -286,3 +286,26 @@ def test_gradient_exchange_world2_gloo(tmp_path):
                                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     outs = [p.communicate(timeout=180)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+def test_bench_reference_arm_schema(monkeypatch, capsys):
+    """`bench.py --impl reference` prints one JSON line with the contract's keys, the product arm's
+    metric / unit / workload name, and only on rank 0 (the CPU step itself is mocked here; it is
+    exercised for real by `python bench.py --impl reference`)."""
+    import argparse
+    import json
+    import bench
+    monkeypatch.setattr(bench, 'cpu_oracle_step', lambda n_img, threads: (lambda: 0.01))
+    args = argparse.Namespace(gpus=1, steps=3, warmup=1)
+    monkeypatch.setenv('RANK', '0')
+    bench.run_reference(args)
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert line['impl'] == 'reference' and line['metric'] == bench.METRIC and line['unit'] == 'img/s'
+    assert line['higher_is_better'] is True and line['steps'] == 3 and line['gpu_launches'] == 0
+    assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
+    assert line['e2e'] == {'value': line['value'], 'unit': 'img/s', 'h2d_bytes_per_step': 0,
+                           'd2h_bytes_per_step': 0}
+    assert line['config']['workload'].startswith('LOFT offset_rcnn R50-FPN 2x, 1024x1024')
+    monkeypatch.setenv('RANK', '1')                     # other ranks exit without work or output
+    bench.run_reference(args)
+    assert capsys.readouterr().out.strip() == ''
