@@ -1,3 +1,2 @@
-from .train import Trainer, set_random_seed, step_lr, init_dist, build_optimizer_args
-
-__all__ = ['Trainer', 'set_random_seed', 'step_lr', 'init_dist', 'build_optimizer_args']
+from .train import (Trainer, set_random_seed, step_lr, init_dist, build_optimizer_args,
+                    launcher_env)

@@ -45,6 +45,36 @@ def init_dist(backend='nccl', **kwargs):
     return rank, world
 
 
+def launcher_env(launcher):
+    """Translate a `--launcher slurm|mpi` environment into the RANK / WORLD_SIZE / LOCAL_RANK /
+    MASTER_* variables `init_dist` reads (mmcv.runner.init_dist as called from tools/train.py:94-98:
+    `_init_dist_slurm` derives them from SLURM_PROCID / SLURM_NTASKS / SLURM_NODELIST,
+    `_init_dist_mpi` from OMPI_COMM_WORLD_*).  'pytorch' / 'none' leave the environment alone."""
+    e = os.environ
+    if launcher == 'slurm':
+        e['RANK'] = e['SLURM_PROCID']
+        e['WORLD_SIZE'] = e['SLURM_NTASKS']
+        e['LOCAL_RANK'] = e.get('SLURM_LOCALID', str(int(e['SLURM_PROCID']) %
+                                                     max(torch.cuda.device_count(), 1)))
+        if 'MASTER_ADDR' not in e:
+            nodes = e.get('SLURM_STEP_NODELIST', e.get('SLURM_NODELIST', '127.0.0.1'))
+            # first host of a "prefix[a-b,c],other" list
+            head = nodes.split(',')[0]
+            if '[' in head:
+                pre, rng = head.split('[', 1)
+                head = pre + rng.rstrip(']').split(',')[0].split('-')[0]
+            e['MASTER_ADDR'] = head
+        e.setdefault('MASTER_PORT', '29500')
+    elif launcher == 'mpi':
+        e['RANK'] = e['OMPI_COMM_WORLD_RANK']
+        e['WORLD_SIZE'] = e['OMPI_COMM_WORLD_SIZE']
+        e['LOCAL_RANK'] = e.get('OMPI_COMM_WORLD_LOCAL_RANK', '0')
+        e.setdefault('MASTER_ADDR', '127.0.0.1')
+        e.setdefault('MASTER_PORT', '29500')
+    elif launcher not in ('pytorch', 'none', None):
+        raise ValueError(f'Invalid launcher type: {launcher}')
+
+
 def step_lr(base_lr, it, epoch, step=(16, 22), gamma=0.1, warmup='linear', warmup_iters=300,
             warmup_ratio=0.001):
     """mmcv StepLrUpdaterHook + linear warm-up as configured by
@@ -101,8 +131,12 @@ def allreduce_flat(flat, group=None, bucket_bytes=64 << 20, async_op=False):
 
 
 class Trainer:
+    """`iters_per_epoch`: length of one epoch in iterations (len(data_loader) of the reference's
+    EpochBasedRunner); with it `epoch` advances by itself and the step LR policy / per-epoch
+    checkpoints behave as in the reference.  Without it the caller drives `set_epoch`."""
+
     def __init__(self, model, cfg=None, device=None, lr=0.005, momentum=0.9, weight_decay=1e-4,
-                 max_norm=35.0, bucket_bytes=64 << 20):
+                 max_norm=35.0, bucket_bytes=64 << 20, iters_per_epoch=None):
         self.model = model
         if cfg is not None:
             a = build_optimizer_args(cfg)
@@ -120,7 +154,35 @@ class Trainer:
         self.world = dist.get_world_size() if self.distributed else 1
         self.iter = 0
         self.epoch = 0
+        self.iters_per_epoch = iters_per_epoch
+        self.max_epochs = cfg.get('total_epochs') if cfg is not None else None
         self._last_logs = None
+        if self.distributed:
+            self.sync_replicas()
+
+    # ------------------------------------------------------------------ replicas / epochs
+    def sync_replicas(self, src=0):
+        """Make every rank's master weights, momentum and BN statistics those of rank `src` --
+        what MMDistributedDataParallel does at construction (mmdet/apis/train.py:75-79): without it
+        replicas seeded differently (or a checkpoint loaded on one rank) diverge silently."""
+        if not self.distributed:
+            return
+        st = self.store
+        dist.broadcast(st.P, src)
+        dist.broadcast(st.M, src)
+        for g in st._bn_groups:
+            if g is not None:
+                dist.broadcast(g['mean'], src)
+                dist.broadcast(g['var'], src)
+        st.refresh_weights(force=True)
+
+    def set_epoch(self, epoch):
+        self.epoch = int(epoch)
+
+    def end_epoch(self):
+        """Advance the epoch counter (EpochBasedRunner.train: `self._epoch += 1`)."""
+        self.epoch += 1
+        return self.epoch
 
     def current_lr(self):
         c = self.lr_cfg
@@ -201,6 +263,8 @@ class Trainer:
         self.store.sgd_step(self.current_lr(), self.momentum, self.weight_decay, self.max_norm,
                             grad_scale=1.0 / self.world)
         self.iter += 1
+        if self.iters_per_epoch and self.iter % self.iters_per_epoch == 0:
+            self.end_epoch()
         if prefetch is not None and hasattr(model, 'prefetch') and \
                 os.environ.get('LOFT_PREFETCH', '1') != '0':
             model.prefetch(prefetch)
@@ -213,27 +277,96 @@ class Trainer:
         return packed
 
     # ------------------------------------------------------------------ checkpoints
+    def _sgd_state_dict(self):
+        """torch.optim.SGD.state_dict() layout, which is what mmcv's save_checkpoint stores under
+        'optimizer' for the reference: one param group over ALL of model.parameters() in order
+        (mmcv DefaultOptimizerConstructor without paramwise_cfg passes `model.parameters()`, frozen
+        ones included; they simply never acquire state)."""
+        mom = self.store.momentum_state()
+        state, idx = {}, []
+        for i, (name, p) in enumerate(self.model.named_parameters()):
+            idx.append(i)
+            if name in mom and self.iter > 0:
+                state[i] = {'momentum_buffer': mom[name].cpu()}
+        group = dict(lr=self.current_lr(), momentum=self.momentum, dampening=0,
+                     weight_decay=self.weight_decay, nesterov=False, initial_lr=self.base_lr,
+                     params=idx)
+        return {'state': state, 'param_groups': [group]}
+
+    def _load_sgd_state_dict(self, opt):
+        import warnings
+        names = [n for n, _ in self.model.named_parameters()]
+        if 'state' in opt and 'param_groups' in opt:
+            order = [i for g in opt['param_groups'] for i in g['params']]
+            if len(order) != len(names):
+                warnings.warn(f'optimizer state covers {len(order)} parameters, the model has '
+                              f'{len(names)}: momentum not restored')
+                return False
+            mom = {names[k]: opt['state'][i]['momentum_buffer']
+                   for k, i in enumerate(order) if i in opt['state'] and
+                   opt['state'][i].get('momentum_buffer') is not None}
+        elif 'momentum_buffer' in opt:          # round-1 layout of this repo
+            mom = opt['momentum_buffer']
+        else:
+            warnings.warn('unrecognised optimizer state in checkpoint: momentum not restored')
+            return False
+        self.store.load_momentum_state(mom)
+        return True
+
     def save_checkpoint(self, path, meta=None):
         """Reference checkpoint layout (mmcv save_checkpoint as used by CheckpointHook,
         default_runtime.py:1): {'meta', 'state_dict', 'optimizer'}; state_dict keys / shapes are
-        the reference's, tensors are saved contiguous in the reference (OIHW) order."""
+        the reference's, tensors are saved contiguous in the reference (OIHW) order; 'optimizer'
+        is torch.optim.SGD.state_dict() so the reference's runner.resume accepts the file."""
         sd = {k: v.detach().cpu().contiguous() for k, v in self.model.state_dict().items()}
-        opt = {k: v.cpu() for k, v in self.store.momentum_state().items()}
         m = dict(iter=self.iter, epoch=self.epoch, lr=self.current_lr())
         m.update(meta or {})
-        torch.save({'meta': m, 'state_dict': sd, 'optimizer': {'momentum_buffer': opt}}, path)
+        torch.save({'meta': m, 'state_dict': sd, 'optimizer': self._sgd_state_dict()}, path)
 
     def load_checkpoint(self, path, resume=True):
         ck = torch.load(path, map_location='cpu')
         sd = ck['state_dict'] if 'state_dict' in ck else ck
+        # checkpoints written from a (MM)DistributedDataParallel wrapper carry a 'module.' prefix
+        # (mmcv load_checkpoint strips it)
+        if sd and all(k.startswith('module.') for k in sd):
+            sd = {k[len('module.'):]: v for k, v in sd.items()}
         self.model.load_state_dict(sd)
         self.store.refresh_weights(force=True)
         if resume:
-            if 'optimizer' in ck and 'momentum_buffer' in ck['optimizer']:
-                self.store.load_momentum_state(ck['optimizer']['momentum_buffer'])
+            if 'optimizer' in ck:
+                self._load_sgd_state_dict(ck['optimizer'])
             self.iter = ck.get('meta', {}).get('iter', 0)
             self.epoch = ck.get('meta', {}).get('epoch', 0)
+        if self.distributed:
+            self.sync_replicas()
         return ck.get('meta', {})
+
+    # ------------------------------------------------------------------ epoch-based run
+    def run(self, batches, max_epochs=None, work_dir=None, checkpoint_interval=1, log_interval=50,
+            rank=0, log=print):
+        """EpochBasedRunner.run for workflow [('train', 1)] (mmdet/apis/train.py:143, mmcv
+        EpochBasedRunner.train): `iters_per_epoch` steps per epoch, LR stepped by epoch, a
+        checkpoint `epoch_{n}.pth` every `checkpoint_interval` epochs (CheckpointHook,
+        default_runtime.py:1).  `batches`: iterator of host input dicts."""
+        import time
+        assert self.iters_per_epoch, 'Trainer.run needs iters_per_epoch'
+        max_epochs = max_epochs or self.max_epochs or 1
+        nxt = self.stage(next(batches))
+        while self.epoch < max_epochs:
+            ep, t0 = self.epoch, time.time()
+            for i in range(self.iter % self.iters_per_epoch, self.iters_per_epoch):
+                last = (i + 1 == self.iters_per_epoch) and (ep + 1 == max_epochs)
+                cur, nxt = nxt, (None if last else self.stage(next(batches)))
+                want = (i + 1) % log_interval == 0 or i + 1 == self.iters_per_epoch
+                lr = self.current_lr()
+                out = self.train_step(cur, read_logs=want, prefetch=nxt)
+                if want and rank == 0:
+                    items = ', '.join(f'{k}: {v:.4f}' for k, v in out.items())
+                    log(f'Epoch [{ep + 1}][{i + 1}/{self.iters_per_epoch}]\tlr: {lr:.3e}, '
+                        f'time: {(time.time() - t0) / (i + 1):.3f}, {items}')
+            if work_dir and rank == 0 and checkpoint_interval and \
+                    self.epoch % checkpoint_interval == 0:
+                self.save_checkpoint(os.path.join(work_dir, f'epoch_{self.epoch}.pth'))
 
     def read_logs_async(self):
         """Non-blocking variant: enqueue the device->host copy of THIS step's packed log vector

@@ -166,10 +166,9 @@ class SamplingResult:
 @BBOX_SAMPLERS.register_module()
 class RandomSampler:
     """BaseSampler.sample + RandomSampler (samplers/base_sampler.py:34-101,
-    random_sampler.py:31-75).  `forced_choices` (a list consumed front-to-back) lets the parity
-    tests inject the oracle's random draws (CUDA and CPU Philox streams differ)."""
-
-    forced_choices = None
+    random_sampler.py:31-75).  All random draws go through `random_choice` (parity tests replace
+    that method on a sampler INSTANCE to inject the oracle's draws: CUDA and CPU Philox streams
+    differ)."""
 
     def __init__(self, num, pos_fraction, neg_pos_ub=-1, add_gt_as_proposals=True, **kwargs):
         self.num = num
@@ -181,9 +180,6 @@ class RandomSampler:
 
     def random_choice(self, gallery, num):
         assert len(gallery) >= num
-        forced = RandomSampler.forced_choices
-        if forced is not None:
-            return forced.pop(0).to(gallery.device)
         is_tensor = isinstance(gallery, torch.Tensor)
         if not is_tensor:
             gallery = torch.tensor(gallery, dtype=torch.long,

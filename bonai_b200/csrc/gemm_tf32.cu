@@ -50,6 +50,7 @@ struct GemmParams {
   int num_kb;     // k-blocks per tile (FPROP/DGRAD); total k-blocks (WGRAD)
   int kb_per_split;
   int n_mma;  // UMMA N
+  int n_half; // B rows (pixels / cin) one CTA stages per k-block: n_mma, or n_mma/2 in pair mode
   int stages;            // operand pipeline depth (4..8) and bytes per stage, set by launch()
   uint32_t stage_bytes;
   uint32_t tx_bytes;
@@ -88,6 +89,8 @@ struct GemmParams {
   int groups;               // >= 1
   int group_n;              // images (RoIs) per group along the N axis of the activations
   int splits;               // WGRAD: split-K factor per (group, tap, tile)
+  int pair;                 // host only: launch the cta_group::2 form (clusters of 2 CTAs)
+  unsigned long long* trace;  // debug (loft_debug_set_trace): 8 globaltimer stamps per CTA
   long long vec_gstride;    // scale / shift stride between groups (floats)
   long long out_gstride;    // WGRAD: dW stride between groups (floats)
 };
@@ -98,6 +101,13 @@ struct DebugOverrides {
   long long idesc = -1;
 };
 DebugOverrides g_dbg;
+unsigned long long* g_trace = nullptr;   // device buffer, 8 x u64 per CTA (tools/gemm_timeline.py)
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 __device__ __forceinline__ void tile_pixel_origin(const GemmParams& p, int ptile, int& n0, int& h0,
                                                   int& w0) {
@@ -110,6 +120,13 @@ __device__ __forceinline__ void tile_pixel_origin(const GemmParams& p, int ptile
   w0 = twi * p.tw;
 }
 
+// kPair = true: the kernel runs as clusters of two CTAs (one TPC) that share each tile with
+// tcgen05.mma.cta_group::2 -- the pair covers 256 channels x n_mma pixels, each CTA stages its own
+// 128 channel rows of A and HALF of the pixel rows of B per k-block (32 KB instead of 48 KB for
+// the same 128 x 256 x 32 block of MMA work per SM), the leader CTA issues the MMAs for both, and
+// each CTA drains its own 128 TMEM lanes.  Operand delivery (L2 -> SM), not the tensor pipe, is
+// what bounds the 1-CTA form (profiles/r01_ncu_layer4_conv.txt: 33x operand re-fetch).
+template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
                       const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
@@ -132,6 +149,13 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  unsigned long long* trace = p.trace ? p.trace + 8ull * blockIdx.x : nullptr;
+  if (trace && threadIdx.x == 0) trace[0] = gtime();
+  // pair mode: rank 0 is the leader (owns the full / tmem-empty barriers, issues the MMAs)
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0u;
+  const int tile0 = kPair ? (int)cluster_id_x() : (int)blockIdx.x;
+  const int tile_step = kPair ? (int)cluster_nctaid_x() : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -142,13 +166,19 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 8);
+      mbar_init(&tempty_bar[i], kPair ? 16 : 8);   // epilogue warps of both CTAs drain a pair tile
     }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  if (warp == 1) {
+    if constexpr (kPair) tmem_alloc_pair(tmem_slot, kTmemCols);
+    else tmem_alloc(tmem_slot, kTmemCols);
+  }
   tc_fence_before();
   __syncthreads();
+  // the peer's barriers must exist before anything of ours signals them (TMA complete_tx on the
+  // leader's full barriers, multicast commits, remote tmem-empty arrivals)
+  if constexpr (kPair) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor
@@ -156,6 +186,7 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
   // touched after the previous grid has completed and flushed.
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (trace && threadIdx.x == 0) trace[1] = gtime();
 
   const bool is_wgrad = p.mode >= WGRAD_2D;
 
@@ -164,11 +195,13 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
         int t = tile;
-        const int ct = t % p.nct;
+        // pair mode: (ct, pt) of the tile index name a PAIR of 128-channel tiles and a pair of
+        // B half-tiles; this CTA stages the members with its rank
+        const int ct = kPair ? (t % p.nct) * 2 + (int)rank : t % p.nct;
         t /= p.nct;
-        int pt = t % p.npt, tap = 0, split = 0, grp;
+        int pt = kPair ? (t % p.npt) * 2 + (int)rank : t % p.npt, tap = 0, split = 0, grp;
         t /= p.npt;
         if (is_wgrad) {
           tap = t % p.ntaps;
@@ -195,44 +228,48 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
           mbar_wait(&empty_bar[s], ph ^ 1u);
           uint8_t* sa = smem + s * stage_bytes;
           uint8_t* sb = sa + kABytes;
-          mbar_expect_tx(&full_bar[s], p.tx_bytes);
+          // pair mode: both CTAs' loads complete on the LEADER's full barrier, which expects the
+          // bytes of both (a peer complete_tx that lands before the leader's expect_tx only drives
+          // the tx-count negative; the phase cannot complete before the leader's arrival)
+          if (!kPair || leader) mbar_expect_tx(&full_bar[s], p.tx_bytes);
+          const uint32_t fb = kPair ? mapa_shared(smem_u32(&full_bar[s]), 0u) : smem_u32(&full_bar[s]);
           switch (p.mode) {
             case FPROP_2D:
-              tma_load_2d(sa, &tmap_a, &full_bar[s], kb * kKB, ct * kBlockC);
-              tma_load_2d(sb, &tmap_b, &full_bar[s], kb * kKB, pt * p.n_mma);
+              tma_load_2d<kPair>(sa, &tmap_a, fb, kb * kKB, ct * kBlockC);
+              tma_load_2d<kPair>(sb, &tmap_b, fb, kb * kKB, pt * p.n_half);
               break;
             case FPROP_CONV: {
               const int tp = kb / p.cchunks, ch = kb % p.cchunks;
               const int dh = (p.ntaps == 9) ? tp / 3 - 1 : 0, dw = (p.ntaps == 9) ? tp % 3 - 1 : 0;
-              tma_load_3d(sa, &tmap_a, &full_bar[s], kb * kKB, ct * kBlockC, grp);
-              tma_load_4d(sb, &tmap_b, &full_bar[s], ch * kKB, w0 + dw, h0 + dh, n0);
+              tma_load_3d<kPair>(sa, &tmap_a, fb, kb * kKB, ct * kBlockC, grp);
+              tma_load_4d<kPair>(sb, &tmap_b, fb, ch * kKB, w0 + dw, h0 + dh, n0);
               break;
             }
             case DGRAD_2D:
               // A view: (32 cin, Cout rows, Cin/32 chunks); k-block = 32 cout rows
-              tma_load_3d(sa, &tmap_a, &full_bar[s], 0, kb * kKB, ct * (kBlockC / 32));
-              tma_load_2d(sb, &tmap_b, &full_bar[s], kb * kKB, pt * p.n_mma);
+              tma_load_3d<kPair>(sa, &tmap_a, fb, 0, kb * kKB, ct * (kBlockC / 32));
+              tma_load_2d<kPair>(sb, &tmap_b, fb, kb * kKB, pt * p.n_half);
               break;
             case DGRAD_CONV: {
               const int tp = kb / p.cchunks, ch = kb % p.cchunks;
               const int dh = (p.ntaps == 9) ? tp / 3 - 1 : 0, dw = (p.ntaps == 9) ? tp % 3 - 1 : 0;
               // A view of W[Cout][ntaps*Cin]: chunk index = (tap*Cin + cin0)/32
-              tma_load_4d(sa, &tmap_a, &full_bar[s], 0, ch * kKB,
-                          tp * (p.tap_stride / 32) + ct * (kBlockC / 32), grp);
-              tma_load_4d(sb, &tmap_b, &full_bar[s], ch * kKB, w0 - dw, h0 - dh, n0);
+              tma_load_4d<kPair>(sa, &tmap_a, fb, 0, ch * kKB,
+                                 tp * (p.tap_stride / 32) + ct * (kBlockC / 32), grp);
+              tma_load_4d<kPair>(sb, &tmap_b, fb, ch * kKB, w0 - dw, h0 - dh, n0);
               break;
             }
             case WGRAD_2D:
-              tma_load_3d(sa, &tmap_a, &full_bar[s], 0, kb * kKB, ct * (kBlockC / 32));
-              tma_load_3d(sb, &tmap_b, &full_bar[s], 0, kb * kKB, pt * (p.n_mma / 32));
+              tma_load_3d<kPair>(sa, &tmap_a, fb, 0, kb * kKB, ct * (kBlockC / 32));
+              tma_load_3d<kPair>(sb, &tmap_b, fb, 0, kb * kKB, pt * (p.n_half / 32));
               break;
             case WGRAD_CONV: {
               int kn0, kh0, kw0;
               tile_pixel_origin(p, kb, kn0, kh0, kw0);
               kn0 += gn0;
-              tma_load_5d(sa, &tmap_a, &full_bar[s], 0, kw0, kh0, kn0, ct * (kBlockC / 32));
-              tma_load_5d(sb, &tmap_b, &full_bar[s], 0, kw0 + tdw, kh0 + tdh, kn0,
-                          pt * (p.n_mma / 32));
+              tma_load_5d<kPair>(sa, &tmap_a, fb, 0, kw0, kh0, kn0, ct * (kBlockC / 32));
+              tma_load_5d<kPair>(sb, &tmap_b, fb, 0, kw0 + tdw, kh0 + tdh, kn0,
+                                 pt * (p.n_half / 32));
               break;
             }
           }
@@ -245,11 +282,11 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (lane == 0 && (!kPair || leader)) {
       uint32_t lt = 0;
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+      for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++lt) {
         int kb_count = p.num_kb;
         if (is_wgrad) {
           const int split = (tile / (p.nct * p.npt * p.ntaps)) % p.splits;
@@ -262,22 +299,31 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
         for (int kbi = 0; kbi < kb_count; ++kbi) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
+          if (trace && lt == 0 && kbi == 0) trace[2] = gtime();
           const uint32_t sa = smem_u32(smem + s * stage_bytes);
           const uint32_t sb = sa + kABytes;
           const uint64_t ad = p.a_desc + (uint64_t)((sa >> 4) & 0x3FFFu);
           const uint64_t bd = p.b_desc + (uint64_t)((sb >> 4) & 0x3FFFu);
 #pragma unroll
           for (int ks = 0; ks < kKB / 8; ++ks) {
-            umma_tf32(tmem_d, ad + (uint64_t)(ks * p.a_kstep), bd + (uint64_t)(ks * p.b_kstep),
-                      p.idesc, (kbi | ks) != 0 ? 1u : 0u);
+            if constexpr (kPair)
+              umma_tf32_pair(tmem_d, ad + (uint64_t)(ks * p.a_kstep),
+                             bd + (uint64_t)(ks * p.b_kstep), p.idesc, (kbi | ks) != 0 ? 1u : 0u);
+            else
+              umma_tf32(tmem_d, ad + (uint64_t)(ks * p.a_kstep), bd + (uint64_t)(ks * p.b_kstep),
+                        p.idesc, (kbi | ks) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[s]);
+          // frees the stage in BOTH CTAs of a pair (the MMA read both shared memories)
+          if constexpr (kPair) umma_commit_pair(&empty_bar[s], 3);
+          else umma_commit(&empty_bar[s]);
           if (++s == n_stages) {
             s = 0;
             ph ^= 1u;
           }
         }
-        umma_commit(&tfull_bar[as]);
+        if constexpr (kPair) umma_commit_pair(&tfull_bar[as], 3);
+        else umma_commit(&tfull_bar[as]);
+        if (trace && lt == 0) trace[3] = gtime();
       }
     }
   } else {
@@ -289,10 +335,14 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const int half = (warp - 2) >> 2;
     const int et = (int)threadIdx.x - 64;  // 0..255
     uint32_t lt = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+    const uint32_t tempty_remote =
+        kPair ? mapa_shared(smem_u32(&tempty_bar[0]), 0u) : 0u;   // leader's tempty_bar[0]
+    for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++lt) {
       int t = tile;
-      const int ct = t % p.nct;
+      const int ct = kPair ? (t % p.nct) * 2 + (int)rank : t % p.nct;
       t /= p.nct;
+      // pt here is the index of the (pair) tile: its columns are the half-tiles 2*pt, 2*pt+1 side
+      // by side (n_half columns each) in pair mode
       int pt = t % p.npt, tap = 0, grp;
       t /= p.npt;
       if (is_wgrad) {
@@ -315,10 +365,12 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
           bool ok;
           if (p.mode == FPROP_CONV || p.mode == DGRAD_CONV) {
             int n0, h0, w0;
-            tile_pixel_origin(p, pt, n0, h0, w0);
+            const int hf = kPair ? (col >= p.n_half ? 1 : 0) : 0;
+            const int lc = col - hf * p.n_half;             // column within the half-tile's box
+            tile_pixel_origin(p, kPair ? 2 * pt + hf : pt, n0, h0, w0);
             n0 += grp * p.group_n;
             const int thw = p.th * p.tw;
-            const int jn = col / thw, r = col - jn * thw;
+            const int jn = lc / thw, r = lc - jn * thw;
             const int jh = r / p.tw, jw = r - jh * p.tw;
             pn = n0 + jn;
             ph_ = h0 + jh;
@@ -354,6 +406,7 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
+      if (trace && lt == 0 && et == 0) trace[4] = gtime();
       const int c = ct * kBlockC + q * 32 + lane;
       const bool c_ok = c < p.Cm;
       const uint32_t taddr = tmem_base + as * kMaxN + ((uint32_t)(q * 32) << 16);
@@ -540,15 +593,27 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) {
+        if (!kPair || leader) mbar_arrive(&tempty_bar[as]);
+        else mbar_arrive_cluster(tempty_remote + as * 8u);
+      }
+      if (trace && et == 0) {
+        if (lt == 0) trace[5] = gtime();
+        trace[6] = gtime();
+        trace[7] = lt + 1;
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  // neither CTA of a pair may retire (or free tensor memory) while the other can still read its
+  // shared memory through an in-flight MMA or signal one of its barriers
+  if constexpr (kPair) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if constexpr (kPair) tmem_dealloc_pair(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -616,6 +681,8 @@ int make_tmap(CUtensorMap* m, int rank, const void* ptr, const uint64_t* dims,
   return LOFT_OK;
 }
 
+int pair_slots() { return loft_num_sms() / 2; }   // CTA pairs resident at once (one per TPC)
+
 constexpr uint64_t desc_template(uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
   // SmemDescriptor (sm_100): [0,14) addr>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1,
   // [61,64) layout type (2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B)
@@ -623,11 +690,11 @@ constexpr uint64_t desc_template(uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_
          (1ull << 46) | ((uint64_t)layout_type << 61);
 }
 
-constexpr uint32_t make_idesc(int n_mma, bool a_mn, bool b_mn) {
+constexpr uint32_t make_idesc(int n_mma, bool a_mn, bool b_mn, bool pair) {
   // InstrDescriptor: c_format F32 (1) @4, a_format TF32 (2) @7, b_format TF32 (2) @10,
-  // a_major @15, b_major @16, N>>3 @17, M>>4 @24
+  // a_major @15, b_major @16, N>>3 @17, M>>4 @24 (M = 256 across the two CTAs of a pair)
   return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
-         ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(kBlockC >> 4) << 24);
+         ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)((pair ? 2 * kBlockC : kBlockC) >> 4) << 24);
 }
 
 void fill_descs(GemmParams& p, bool a_mn, bool b_mn) {
@@ -639,7 +706,8 @@ void fill_descs(GemmParams& p, bool a_mn, bool b_mn) {
   p.b_desc = b_mn ? desc_template(kKB * 128, 512, 1) : desc_template(16, 1024, 2);
   p.a_kstep = a_mn ? (1024 >> 4) : (32 >> 4);
   p.b_kstep = b_mn ? (1024 >> 4) : (32 >> 4);
-  p.idesc = make_idesc(p.n_mma, a_mn, b_mn);
+  p.idesc = make_idesc(p.n_mma, a_mn, b_mn, p.pair != 0);
+  p.n_half = p.pair ? p.n_mma / 2 : p.n_mma;
   if (g_dbg.a_desc >= 0) p.a_desc = (uint64_t)g_dbg.a_desc;
   if (g_dbg.b_desc >= 0) p.b_desc = (uint64_t)g_dbg.b_desc;
   if (g_dbg.a_kstep >= 0) p.a_kstep = (uint32_t)g_dbg.a_kstep;
@@ -649,6 +717,7 @@ void fill_descs(GemmParams& p, bool a_mn, bool b_mn) {
 
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p_in, cudaStream_t stream) {
   GemmParams p = p_in;
+  p.trace = g_trace;
   {
     // largest pixel-row index the epilogue can form, times the widest pitch
     long long rows = (p.mode == FPROP_CONV || p.mode == DGRAD_CONV) ? (long long)p.N * p.H * p.W
@@ -657,7 +726,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p_in,
     const long long ld = p.ldo > p.ldr ? p.ldo : p.ldr;
     p.fast_epi = (rows + 1) * ld < (1ll << 31) ? 1 : 0;
     // operand arena: as many stages as fit (n_mma is a multiple of 16 -> stages stay 1 KB aligned)
-    p.stage_bytes = (uint32_t)(kABytes + p.n_mma * kKB * 4);
+    p.stage_bytes = (uint32_t)(kABytes + p.n_half * kKB * 4);
     int st = (kStages * kStageBytes) / (int)p.stage_bytes;
     static int max_st = -1;
     if (max_st < 0) {
@@ -670,8 +739,11 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p_in,
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(loft_gemm_tf32_kernel,
+    cudaError_t e = cudaFuncSetAttribute(loft_gemm_tf32_kernel<false>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(loft_gemm_tf32_kernel<true>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) {
       loft_set_error("gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return LOFT_ERR_CUDA;
@@ -680,6 +752,10 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p_in,
   }
   if (p.num_tiles <= 0) return LOFT_OK;
   int grid = p.num_tiles < loft_num_sms() ? p.num_tiles : loft_num_sms();
+  if (p.pair) {   // one cluster (CTA pair) per pair tile, at most one per TPC
+    const int slots = pair_slots();
+    grid = 2 * (p.num_tiles < slots ? p.num_tiles : slots);
+  }
   static int use_pdl = -1;
   if (use_pdl < 0) {
     const char* e = getenv("LOFT_PDL");
@@ -690,12 +766,24 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p_in,
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (use_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (p.pair) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = use_pdl ? 1 : 0;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, loft_gemm_tf32_kernel, ta, tb, p);
+  cfg.numAttrs = na;
+  cudaError_t le = p.pair ? cudaLaunchKernelEx(&cfg, loft_gemm_tf32_kernel<true>, ta, tb, p)
+                          : cudaLaunchKernelEx(&cfg, loft_gemm_tf32_kernel<false>, ta, tb, p);
   if (le != cudaSuccess) {
     loft_set_error("loft_gemm_tf32_kernel: launch failed: %s", cudaGetErrorString(le));
     return LOFT_ERR_CUDA;
@@ -704,6 +792,30 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p_in,
 }
 
 int round16(int x) { return (x + 15) & ~15; }
+int round8(int x) { return (x + 7) & ~7; }
+
+// ---- pair (cta_group::2) policy -----------------------------------------------------------
+// LOFT_2CTA=0 never, 1 (default) when the cost model below prefers it, 2 whenever eligible.
+int pair_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LOFT_2CTA");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+// Per-k-block time of one tile in units of "MMA columns" (a 128 x n x 32 TF32 block of MMAs takes
+// 2n cycles): the MMA needs n, staging the operands needs bytes/128 at the ~64 B/cycle one SM
+// ingests from L2 -- 128 + n for a 1-CTA tile (16 KB of A + 128 B per column), 128 + n/2 for a
+// CTA of a pair.  +48: fixed per-tile overhead (pipeline fill, epilogue tail), as in wave_cost.
+long long tile_time(int n, bool pair) {
+  const int fill = pair ? 128 + n / 2 : 128 + n;
+  return (n > fill ? n : fill) + 48;
+}
+long long fill_cost(long long tiles, int n, bool pair) {
+  const long long slots = pair ? pair_slots() : loft_num_sms();
+  return ((tiles + slots - 1) / slots) * tile_time(n, pair);
+}
 
 // Relative cost of covering `tiles` tiles of n columns on the machine: full waves x (n + fixed
 // per-tile overhead).  Used to pick the UMMA N (pixels per tile) for small problems so that the
@@ -730,6 +842,28 @@ int pick_n_2d(long long P, int nct) {
   for (int n : {128, 64}) {
     const long long c = wave_cost((long long)nct * loft_cdiv(P, n), n);
     if (c < bc) {
+      bc = c;
+      best = n;
+    }
+  }
+  return best;
+}
+
+// Pair form: UMMA N in {256,128,64} (halves of 128/64/32 rows per CTA); returns 0 if the 1-CTA
+// choice n1 is predicted to be at least as fast.  nct = number of 128-channel tiles (even).
+int pick_n_2d_pair(long long P, int nct, int n1) {
+  if (pair_mode() == 0 || nct < 2 || (nct & 1)) return 0;
+  if (P < 32) return 0;
+  int best = 0;
+  long long bc = pair_mode() >= 2 ? -1 : fill_cost((long long)nct * loft_cdiv(P, n1), n1, false);
+  if (P < 256) {
+    const int n = round16((int)P);
+    const long long c = fill_cost(nct / 2, n, true);
+    return (bc < 0 || c < bc) ? n : 0;
+  }
+  for (int n : {256, 128, 64}) {
+    const long long c = fill_cost((long long)(nct / 2) * loft_cdiv(P, n), n, true);
+    if (bc < 0 || c < bc) {
       bc = c;
       best = n;
     }
@@ -775,6 +909,40 @@ void pick_pixel_tile(int N, int H, int W, int nct, int& tn, int& th, int& tw) {
     for (int a = 1; a <= N && a * H * W <= kMaxN; ++a) consider(a, H, W);
 }
 
+// Pair form of the conv-mode tile choice: the box (tn, th, tw) is what ONE CTA stages (<= 128
+// pixels, rounded up to 8 rows of B); a pair tile is two consecutive boxes.  Returns false if
+// the 1-CTA tile (t1 columns, tiles1 tiles) is predicted to be at least as fast.
+bool pick_pixel_tile_pair(int N, int H, int W, int nct, int G, long long tiles1, int n1, int& tn,
+                          int& th, int& tw) {
+  if (pair_mode() == 0 || nct < 2 || (nct & 1)) return false;
+  long long bc = pair_mode() >= 2 ? -1 : fill_cost(tiles1, n1, false);
+  bool found = false;
+  auto consider = [&](int a, int b, int c) {
+    if (a * b * c > 128 || a * b * c < 8) return;
+    const long long halves = (long long)loft_cdiv(W, c) * loft_cdiv(H, b) * loft_cdiv(N, a);
+    const long long tiles = (long long)(nct / 2) * G * ((halves + 1) / 2);
+    const long long cost = fill_cost(tiles, 2 * round8(a * b * c), true);
+    if (bc < 0 || cost < bc) {
+      bc = cost;
+      tn = a;
+      th = b;
+      tw = c;
+      found = true;
+    }
+  };
+  for (int target : {128, 64, 32}) {
+    int a, b, c;
+    pixel_tile_for(target, N, H, W, a, b, c);
+    consider(a, b, c);
+  }
+  if (W <= 16) {
+    // small maps (RoI heads): whole maps per CTA, or an even split of the rows of one map
+    for (int a = 1; a <= N && a * H * W <= 128; ++a) consider(a, H, W);
+    for (int k = 2; k <= H; ++k) consider(1, loft_cdiv(H, k), W);
+  }
+  return found;
+}
+
 // Pixel patch of exactly kKB (=32) positions for the K side of WGRAD_CONV (OOB -> zero fill).
 void pick_k_patch(int H, int W, int& tn, int& th, int& tw) {
   tw = W > 8 ? 16 : (W > 4 ? 8 : 4);
@@ -782,6 +950,33 @@ void pick_k_patch(int H, int W, int& tn, int& th, int& tw) {
   th = 1;
   while (th < hmax && th < H) th <<= 1;
   tn = kKB / (tw * th);
+}
+
+// Pixel tiling of FPROP_CONV / DGRAD_CONV (p.nct = number of 128-channel tiles on entry): picks the
+// 1-CTA tile, then the pair form if eligible and predicted faster.
+void set_conv_tiles(GemmParams& p, int Ng, int H, int W, int G) {
+  pick_pixel_tile(Ng, H, W, p.nct * G, p.tn, p.th, p.tw);
+  const int n1 = round16(p.tn * p.th * p.tw);
+  const long long tiles1 = (long long)p.nct * G * loft_cdiv(W, p.tw) * loft_cdiv(H, p.th) *
+                           loft_cdiv(Ng, p.tn);
+  int a, b, c;
+  if (pick_pixel_tile_pair(Ng, H, W, p.nct, G, tiles1, n1, a, b, c)) {
+    p.pair = 1;
+    p.nct /= 2;
+    p.tn = a;
+    p.th = b;
+    p.tw = c;
+    p.n_mma = 2 * round8(a * b * c);
+  } else {
+    p.n_mma = n1;
+  }
+  p.tiles_w = loft_cdiv(W, p.tw);
+  p.tiles_h = loft_cdiv(H, p.th);
+  const int boxes = p.tiles_w * p.tiles_h * loft_cdiv(Ng, p.tn);   // per group
+  p.npt = p.pair ? (boxes + 1) / 2 : boxes;
+  p.num_tiles = p.nct * p.npt * G;
+  const int box_bytes = p.tn * p.th * p.tw * kKB * 4;
+  p.tx_bytes = p.pair ? 2 * (kABytes + box_bytes) : kABytes + box_bytes;
 }
 
 void set_epilogue(GemmParams& p, const loft_epilogue_t* e, float* out, long long ldo) {
@@ -805,6 +1000,12 @@ void set_epilogue(GemmParams& p, const loft_epilogue_t* e, float* out, long long
 }  // namespace
 
 extern "C" {
+
+// Debug: every later GEMM launch writes 8 globaltimer stamps per CTA into `buf` (device memory,
+// >= 8 * 8 * num_SMs bytes; NULL turns it off): kernel entry, operands may be read (after the
+// programmatic-dependency wait), first stage landed, last MMA of the first tile issued, first
+// accumulator complete, first tile stored, last tile stored, tiles done by the CTA.
+void loft_debug_set_trace(unsigned long long* buf) { g_trace = buf; }
 
 void loft_debug_set_desc(long long a_desc, long long b_desc, long long a_kstep, long long b_kstep,
                          long long idesc) {
@@ -830,12 +1031,17 @@ int loft_gemm_fprop(const float* x, const float* w, float* y, long long P, int K
   p.splits = 1;
   p.nct = loft_cdiv(Cout, kBlockC);
   p.n_mma = pick_n_2d(P, p.nct);
+  if (const int n2 = pick_n_2d_pair(P, p.nct, p.n_mma)) {
+    p.pair = 1;
+    p.n_mma = n2;
+    p.nct /= 2;
+  }
   p.npt = loft_cdiv(P, p.n_mma);
   p.num_tiles = p.nct * p.npt;
   p.num_kb = loft_cdiv(K, kKB);
   p.kb_per_split = p.num_kb;
   p.ntaps = 1;
-  p.tx_bytes = kABytes + p.n_mma * kKB * 4;
+  p.tx_bytes = p.pair ? 2 * (kABytes + (p.n_mma / 2) * kKB * 4) : kABytes + p.n_mma * kKB * 4;
   p.P = (int)P;
   p.Cm = Cout;
   p.N = 1;
@@ -854,7 +1060,7 @@ int loft_gemm_fprop(const float* x, const float* w, float* y, long long P, int K
   {
     uint64_t d[2] = {(uint64_t)K, (uint64_t)P};
     uint64_t s[1] = {(uint64_t)ldx * 4};
-    uint32_t b[2] = {kKB, (uint32_t)p.n_mma};
+    uint32_t b[2] = {kKB, (uint32_t)p.n_half};
     int r = make_tmap(&tb, 2, x, d, s, b);
     if (r) return r;
   }
@@ -875,12 +1081,17 @@ int loft_gemm_dgrad_hw(const float* dy, const float* w, float* dx, long long P, 
   p.splits = 1;
   p.nct = loft_cdiv(Cin, kBlockC);
   p.n_mma = pick_n_2d(P, p.nct);
+  if (const int n2 = pick_n_2d_pair(P, p.nct, p.n_mma)) {
+    p.pair = 1;
+    p.n_mma = n2;
+    p.nct /= 2;
+  }
   p.npt = loft_cdiv(P, p.n_mma);
   p.num_tiles = p.nct * p.npt;
   p.num_kb = loft_cdiv(Cout, kKB);
   p.kb_per_split = p.num_kb;
   p.ntaps = 1;
-  p.tx_bytes = kABytes + p.n_mma * kKB * 4;
+  p.tx_bytes = p.pair ? 2 * (kABytes + (p.n_mma / 2) * kKB * 4) : kABytes + p.n_mma * kKB * 4;
   p.P = (int)P;
   p.Cm = Cin;
   p.N = 1;
@@ -899,7 +1110,7 @@ int loft_gemm_dgrad_hw(const float* dy, const float* w, float* dx, long long P, 
   {
     uint64_t d[2] = {(uint64_t)Cout, (uint64_t)P};
     uint64_t s[1] = {(uint64_t)lddy * 4};
-    uint32_t b[2] = {kKB, (uint32_t)p.n_mma};
+    uint32_t b[2] = {kKB, (uint32_t)p.n_half};
     int r = make_tmap(&tb, 2, dy, d, s, b);
     if (r) return r;
   }
@@ -924,11 +1135,16 @@ int loft_gemm_wgrad(const float* dy, const float* x, float* dw, long long P, int
   p.mode = WGRAD_2D;
   p.n_mma = Cin >= 256 ? 256 : Cin;  // multiple of 32
   p.nct = loft_cdiv(Cout, kBlockC);
+  // pair form: 256 output channels per CTA pair, each CTA stages half of the Cin columns
+  if (pair_mode() != 0 && p.nct >= 2 && (p.nct & 1) == 0 && p.n_mma % 64 == 0) {
+    p.pair = 1;
+    p.nct /= 2;
+  }
   p.npt = loft_cdiv(Cin, p.n_mma);
   p.ntaps = 1;
   p.num_kb = loft_cdiv(P, kKB);
   int base = p.nct * p.npt;
-  int splits = loft_num_sms() / base;
+  int splits = (p.pair ? pair_slots() : loft_num_sms()) / base;
   if (splits < 1) splits = 1;
   if (splits > p.num_kb) splits = p.num_kb;
   p.kb_per_split = loft_cdiv(p.num_kb, splits);
@@ -936,7 +1152,7 @@ int loft_gemm_wgrad(const float* dy, const float* x, float* dw, long long P, int
   p.num_tiles = base * splits;
   p.groups = 1;
   p.splits = splits;
-  p.tx_bytes = kABytes + p.n_mma * kKB * 4;
+  p.tx_bytes = p.pair ? 2 * (kABytes + (p.n_mma / 2) * kKB * 4) : kABytes + p.n_mma * kKB * 4;
   p.Cm = Cout;
   p.Cn = Cin;
   p.ldw = lddw;
@@ -954,7 +1170,7 @@ int loft_gemm_wgrad(const float* dy, const float* x, float* dw, long long P, int
   {
     uint64_t d[3] = {32, (uint64_t)P, (uint64_t)(Cin / 32)};
     uint64_t s[2] = {(uint64_t)ldx * 4, 128};
-    uint32_t b[3] = {32, kKB, (uint32_t)(p.n_mma / 32)};
+    uint32_t b[3] = {32, kKB, (uint32_t)(p.n_half / 32)};
     int r = make_tmap(&tb, 3, x, d, s, b, true);
     if (r) return r;
   }
@@ -981,17 +1197,11 @@ int loft_conv3x3_fprop_grouped(const float* x, const float* w, float* y, int N, 
   p.splits = 1;
   p.vec_gstride = vec_gstride;
   p.nct = loft_cdiv(Cout, kBlockC);
-  pick_pixel_tile(Ng, H, W, p.nct * G, p.tn, p.th, p.tw);
-  p.n_mma = round16(p.tn * p.th * p.tw);
-  p.tiles_w = loft_cdiv(W, p.tw);
-  p.tiles_h = loft_cdiv(H, p.th);
-  p.npt = p.tiles_w * p.tiles_h * loft_cdiv(Ng, p.tn);
-  p.num_tiles = p.nct * p.npt * G;
+  set_conv_tiles(p, Ng, H, W, G);
   p.cchunks = Cin / 32;
   p.ntaps = 9;
   p.num_kb = 9 * p.cchunks;
   p.kb_per_split = p.num_kb;
-  p.tx_bytes = kABytes + p.tn * p.th * p.tw * kKB * 4;
   p.N = N;
   p.H = H;
   p.W = W;
@@ -1038,17 +1248,11 @@ int loft_conv3x3_dgrad_grouped(const float* dy, const float* w, float* dx, int N
   p.group_n = Ng;
   p.splits = 1;
   p.nct = loft_cdiv(Cin, kBlockC);
-  pick_pixel_tile(Ng, H, W, p.nct * G, p.tn, p.th, p.tw);
-  p.n_mma = round16(p.tn * p.th * p.tw);
-  p.tiles_w = loft_cdiv(W, p.tw);
-  p.tiles_h = loft_cdiv(H, p.th);
-  p.npt = p.tiles_w * p.tiles_h * loft_cdiv(Ng, p.tn);
-  p.num_tiles = p.nct * p.npt * G;
+  set_conv_tiles(p, Ng, H, W, G);
   p.cchunks = loft_cdiv(Cout, 32);
   p.ntaps = 9;
   p.num_kb = 9 * p.cchunks;
   p.kb_per_split = p.num_kb;
-  p.tx_bytes = kABytes + p.tn * p.th * p.tw * kKB * 4;
   p.N = N;
   p.H = H;
   p.W = W;
@@ -1101,18 +1305,23 @@ int loft_conv3x3_wgrad_grouped(const float* dy, const float* x, float* dw, int N
   p.tiles_h = loft_cdiv(H, p.th);
   p.n_mma = Cin >= 256 ? 256 : Cin;
   p.nct = loft_cdiv(Cout, kBlockC);
+  if (pair_mode() != 0 && p.nct >= 2 && (p.nct & 1) == 0 && p.n_mma % 64 == 0) {
+    p.pair = 1;
+    p.nct /= 2;
+  }
   p.npt = loft_cdiv(Cin, p.n_mma);
   p.ntaps = 9;
   p.num_kb = p.tiles_w * p.tiles_h * loft_cdiv(Ng, p.tn);  // k-blocks per group
   int base = p.nct * p.npt * 9 * G;
-  int splits = loft_num_sms() / base;  // floor: one full wave, never a ragged second one
+  // floor: one full wave, never a ragged second one
+  int splits = (p.pair ? pair_slots() : loft_num_sms()) / base;
   if (splits < 1) splits = 1;
   if (splits > p.num_kb) splits = p.num_kb;
   p.kb_per_split = loft_cdiv(p.num_kb, splits);
   splits = loft_cdiv(p.num_kb, p.kb_per_split);
   p.splits = splits;
   p.num_tiles = base * splits;
-  p.tx_bytes = kABytes + p.n_mma * kKB * 4;
+  p.tx_bytes = p.pair ? 2 * (kABytes + (p.n_mma / 2) * kKB * 4) : kABytes + p.n_mma * kKB * 4;
   p.N = N;
   p.H = H;
   p.W = W;
@@ -1133,7 +1342,7 @@ int loft_conv3x3_wgrad_grouped(const float* dy, const float* x, float* dw, int N
   {
     uint64_t d[5] = {32, (uint64_t)W, (uint64_t)H, (uint64_t)N, (uint64_t)(Cin / 32)};
     uint64_t s[4] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4, 128};
-    uint32_t b[5] = {32, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.tn, (uint32_t)(p.n_mma / 32)};
+    uint32_t b[5] = {32, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.tn, (uint32_t)(p.n_half / 32)};
     int r = make_tmap(&tb, 5, x, d, s, b, true);
     if (r) return r;
   }

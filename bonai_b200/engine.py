@@ -153,6 +153,14 @@ class ParamStore:
             if hasattr(m, 'loft_prepare'):
                 m.loft_prepare(self)
         self._build_fold_tables()
+        # everything whose in-place modification (load_state_dict, init_weights, an external torch
+        # optimizer) must trigger a rebuild of the derived copies: the parameters themselves --
+        # `p.data = view` keeps each parameter's OWN version counter, self.P._version never moves
+        # when a parameter is written through -- and the BN running statistics
+        self._versioned = [p for p, _ in self._grad_views]
+        for m in bns:
+            self._versioned += [m.running_mean, m.running_var]
+        self._dirty = False
         self._seen_version = None
         self._frozen_ready = False
         self._callback_queued = False
@@ -220,12 +228,24 @@ class ParamStore:
         return packed
 
     # ------------------------------------------------------------------ per-step protocol
+    def _version_sig(self):
+        return self.P._version + sum(t._version for t in self._versioned)
+
+    def mark_dirty(self):
+        """Tell the store that master weights / BN statistics were modified behind autograd's
+        back (through `.data`, a raw pointer, a custom kernel): the next step rebuilds the TF32
+        copy, the folded-BN weights and the packed weights.  In-place tensor ops on the
+        parameters (load_state_dict, optimizer.step of a torch optimizer, init_weights) are
+        detected without this."""
+        self._dirty = True
+
     def refresh_weights(self, force=False):
-        """TF32-round the master weights into T, fold BN, rebuild packed weights (only when the
-        master copy changed since the last call)."""
-        ver = self.P._version
-        if not force and self._seen_version == ver:
+        """TF32-round the master weights into T, fold BN, rebuild packed weights (only when a
+        parameter or a BN statistic changed since the last call)."""
+        ver = self._version_sig()
+        if not force and not self._dirty and self._seen_version == ver:
             return
+        self._dirty = False
         end = self.total
         L.call('copy2d', L.ptr(self.P), L.ll(end), L.ptr(self.T), L.ll(end), L.ll(1),
                ctypes.c_int(end), ctypes.c_int(0), ctypes.c_int(1), L.stream())
@@ -303,7 +323,8 @@ class ParamStore:
                L.f32(lr), L.f32(momentum), L.f32(weight_decay), L.f32(max_norm if use_clip else 0.0),
                L.f32(grad_scale), L.ptr(self.sqnorm) if use_clip else None, L.stream())
         self._after_weight_update()
-        self._seen_version = self.P._version
+        # the kernels write P / T through raw pointers: no version counter moved, the signature
+        # taken in begin_step still describes what T was derived from
 
     def momentum_state(self):
         """{parameter name: momentum buffer (reference layout)} for checkpoints."""

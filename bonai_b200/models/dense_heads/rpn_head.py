@@ -29,8 +29,6 @@ _FUSED_W = 16      # 3 cls + 12 reg + 1 zero pad
 
 @HEADS.register_module()
 class RPNHead(nn.Module):
-    forced_proposals = None       # test hook: list[Tensor[k,5]] injected instead of get_bboxes
-
     def __init__(self, in_channels, num_classes=1, feat_channels=256,
                  anchor_generator=dict(type='AnchorGenerator', scales=[8, 16, 32],
                                        ratios=[0.5, 1.0, 2.0], strides=[4, 8, 16, 32, 64]),
@@ -227,15 +225,16 @@ class RPNHead(nn.Module):
             self._tstream = torch.cuda.Stream(device=dev)
         main = torch.cuda.current_stream(dev)
         # The side stream must not read GT boxes before they exist.  If the caller staged them
-        # with an event, wait for that; if they are the very tensors of the previous step they
-        # are long since resident; otherwise fall back to ordering after the main stream (which
-        # serialises behind the previous step's backward).
-        ident = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in gt_bboxes)
+        # with an event, wait for that; if they are the very tensor OBJECTS of the previous call
+        # (held alive here, so the allocator cannot have recycled their memory for another batch)
+        # with unchanged version counters they are long since resident; otherwise order after the
+        # main stream (which serialises behind the previous step's backward).
         if ready_event is not None:
             self._tstream.wait_event(ready_event)
-        elif ident != getattr(self, '_last_gt_ident', None):
+        elif not self._same_gt(getattr(self, '_last_gt_token', None), gt_bboxes):
             self._tstream.wait_stream(main)
-        self._last_gt_ident = ident
+        ident = self._gt_token(gt_bboxes)
+        self._last_gt_token = ident
         sizes = self.featmap_sizes_for(img_hw)
         with torch.cuda.stream(self._tstream):
             per_level, num_total = self._build_targets(sizes, gt_bboxes, img_metas, dev)
@@ -246,15 +245,23 @@ class RPNHead(nn.Module):
         self._prefetched = (tuple(sizes), per_level, num_total, ev, ident)
 
     @staticmethod
-    def _gt_ident(gt_bboxes):
-        return tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in gt_bboxes)
+    def _gt_token(gt_bboxes):
+        """Identity of a batch's GT boxes: the tensor objects themselves (strong references -- a
+        recycled device address can never alias a live tensor) and their version counters."""
+        return (list(gt_bboxes), tuple(t._version for t in gt_bboxes))
+
+    @staticmethod
+    def _same_gt(token, gt_bboxes):
+        if token is None or len(token[0]) != len(gt_bboxes):
+            return False
+        return all(a is b and v == b._version for a, v, b in zip(token[0], token[1], gt_bboxes))
 
     def has_prefetched(self, gt_bboxes):
         """True if targets for exactly these GT tensors were already prefetched (by the previous
         step's Trainer.train_step(..., prefetch=next_batch))."""
         pre = self.__dict__.get('_prefetched')
         return pre is not None and len(gt_bboxes) > 0 and gt_bboxes[0].is_cuda and \
-            pre[4] == self._gt_ident(gt_bboxes)
+            self._same_gt(pre[4], gt_bboxes)
 
     def loss(self, cls_scores, bbox_preds, gt_bboxes, img_metas, gt_bboxes_ignore=None):
         """AnchorHead.loss / RPNHead.loss (anchor_head.py:429-497, rpn_head.py:46-77)."""
@@ -262,7 +269,7 @@ class RPNHead(nn.Module):
         device = cls_scores[0].device
         pre = self.__dict__.pop('_prefetched', None)
         if pre is not None and pre[0] == tuple(featmap_sizes) and \
-                pre[4] == self._gt_ident(gt_bboxes):
+                self._same_gt(pre[4], gt_bboxes):
             _, per_level, num_total_samples, ev, _ = pre
             torch.cuda.current_stream(device).wait_event(ev)
         else:
@@ -292,8 +299,6 @@ class RPNHead(nn.Module):
                    fixed_size=False):
         """AnchorHead.get_bboxes -> RPNHead._get_bboxes_single (rpn_head.py:79-168), all images in
         one batched NMS.  Order within equal scores is (level, anchor index) = a stable sort."""
-        if RPNHead.forced_proposals is not None:
-            return [p.to(cls_scores[0].device) for p in RPNHead.forced_proposals]
         cfg = self.test_cfg if cfg is None else cfg
         if cfg.get('nms_across_levels', False) or cfg.min_bbox_size > 0:
             raise NotImplementedError('LOFT config: per-level NMS, min_bbox_size=0')

@@ -523,9 +523,8 @@ class Trunk:
         per-level NMS and the fixed-size [N, nms_post, 5] proposal block all have static shapes,
         so ~80 small kernels of RPNHead.get_bboxes ride in the same graph launch instead of
         being issued one by one by the (forward-phase-bound) launch thread."""
-        from .models.dense_heads.rpn_head import RPNHead
         rpn = self.model.rpn_head
-        want = pcfg is not None and metas is not None and RPNHead.forced_proposals is None and \
+        want = pcfg is not None and metas is not None and \
             os.environ.get('LOFT_GRAPH_PROPOSALS', '1') != '0'
         for with_props in ([True, False] if want else [False]):
             g = torch.cuda.CUDAGraph()
@@ -546,10 +545,9 @@ class Trunk:
 
     def proposals(self):
         """The proposal block the forward graph produced for the current step (None on the
-        recording step, when proposals are forced by a test, or when not captured)."""
-        from .models.dense_heads.rpn_head import RPNHead
+        recording step or when not captured: LOFT_GRAPH_PROPOSALS=0)."""
         prog = self.current
-        if prog is None or not prog.proposals_fresh or RPNHead.forced_proposals is not None:
+        if prog is None or not prog.proposals_fresh:
             return None
         return prog.proposals
 

@@ -47,7 +47,7 @@ def run(case, variant):
     out = {}
     if case.startswith('fprop2d'):
         P, K, Co = {'fprop2d': (1000, 256, 256), 'fprop2d_small': (4096, 64, 64),
-                    'fprop2d_big': (131072, 256, 256), 'fprop2d_tiny': (50, 1024, 8)}[case]
+                    'fprop2d_big': (131072, 256, 256), 'fprop2d_tiny': (50, 1024, 8), 'fprop2d_wide': (2048, 1024, 1024)}[case]
         x, w, b = rnd(P, K), rnd(Co, K) * 0.1, rnd(Co)
         res = rnd(P, Co)
         y = torch.empty(P, Co, device=dev)

@@ -13,10 +13,47 @@ from oracle import loft_cpu as O  # noqa: E402
 from bonai_b200 import Config  # noqa: E402
 from bonai_b200.models import build_detector  # noqa: E402
 from bonai_b200.core import BitmapMasks  # noqa: E402
-from bonai_b200.core.bbox import RandomSampler  # noqa: E402
-from bonai_b200.models.dense_heads import RPNHead  # noqa: E402
 
 CFG = os.path.join(ROOT, 'configs', 'loft', 'loft_foa_r50_fpn_2x_b200.py')
+
+
+class teacher_force:
+    """Context: make `model` draw the oracle's random samples and (optionally) use the oracle's
+    proposals.  Nothing in the product knows about this: the sampler INSTANCES' `random_choice`
+    and the RPN head INSTANCE's `get_bboxes` are replaced for the duration, and the proposal
+    generation is kept out of the trunk's forward graph (LOFT_GRAPH_PROPOSALS=0) so that
+    `get_bboxes` is what the step calls."""
+
+    def __init__(self, model, draws, proposals=None):
+        self.model, self.draws, self.proposals = model, list(draws), proposals
+        self.samplers = [s for s in (getattr(model.rpn_head, 'sampler', None),
+                                     getattr(model.roi_head, 'bbox_sampler', None))
+                         if s is not None]
+
+    def __enter__(self):
+        draws = self.draws
+
+        def forced_choice(gallery, num):
+            return draws.pop(0).to(gallery.device)
+        for s in self.samplers:
+            s.random_choice = forced_choice
+        self._env = os.environ.get('LOFT_GRAPH_PROPOSALS')
+        if self.proposals is not None:
+            props = self.proposals
+            os.environ['LOFT_GRAPH_PROPOSALS'] = '0'
+            self.model.rpn_head.get_bboxes = \
+                lambda cls_scores, *a, **k: [p.to(cls_scores[0].device) for p in props]
+        return self
+
+    def __exit__(self, *a):
+        for s in self.samplers:
+            s.__dict__.pop('random_choice', None)
+        self.model.rpn_head.__dict__.pop('get_bboxes', None)
+        if self._env is None:
+            os.environ.pop('LOFT_GRAPH_PROPOSALS', None)
+        else:
+            os.environ['LOFT_GRAPH_PROPOSALS'] = self._env
+        return False
 
 
 def run(size=256, n_img=1, num_gt=10, seed=0, force_proposals=True, verbose=True, diag=False):
@@ -38,8 +75,6 @@ def run(size=256, n_img=1, num_gt=10, seed=0, force_proposals=True, verbose=True
     model.load_state_dict(p)
     model.train()
     dev = torch.device('cuda:0')
-    RandomSampler.forced_choices = [r.clone() for r in rec]
-    RPNHead.forced_proposals = [q.clone() for q in aux['proposals']] if force_proposals else None
     metas = [dict(img_shape=(H, W, 3), pad_shape=(H, W, 3), ori_shape=(H, W, 3),
                   scale_factor=1.0, flip=False) for _ in range(n_img)]
     caps = {}
@@ -54,13 +89,13 @@ def run(size=256, n_img=1, num_gt=10, seed=0, force_proposals=True, verbose=True
         model.roi_head.mask_head.register_forward_hook(cap('mask_pred'))
         model.roi_head.offset_head.register_forward_hook(cap('offset_pred'))
         model.roi_head.bbox_head.register_forward_hook(cap('bbox_out'))
-    losses = model.forward_train(img.to(dev), metas, gb, gl,
-                                 gt_masks=[BitmapMasks(m, H, W) for m in gm], gt_offsets=go)
-    loss, logs = model._parse_losses(losses)
-    loss.backward()
-    torch.cuda.synchronize()
-    RandomSampler.forced_choices = None
-    RPNHead.forced_proposals = None
+    with teacher_force(model, [r.clone() for r in rec],
+                       [q.clone() for q in aux['proposals']] if force_proposals else None):
+        losses = model.forward_train(img.to(dev), metas, gb, gl,
+                                     gt_masks=[BitmapMasks(m, H, W) for m in gm], gt_offsets=go)
+        loss, logs = model._parse_losses(losses)
+        loss.backward()
+        torch.cuda.synchronize()
     rep = {'losses': {}, 'grads': {}}
     if diag:
         import torch.nn.functional as F

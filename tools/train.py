@@ -17,7 +17,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from bonai_b200 import Config, DictAction  # noqa: E402
-from bonai_b200.apis import Trainer, init_dist, set_random_seed  # noqa: E402
+from bonai_b200.apis import Trainer, init_dist, launcher_env, set_random_seed  # noqa: E402
 from bonai_b200.core import BitmapMasks  # noqa: E402
 from bonai_b200.models import build_detector  # noqa: E402
 
@@ -59,10 +59,16 @@ def main():
     ap.add_argument('config')
     ap.add_argument('--work-dir', default=None)
     ap.add_argument('--resume-from', default=None)
-    ap.add_argument('--launcher', choices=['none', 'pytorch'], default='none')
+    ap.add_argument('--launcher', choices=['none', 'pytorch', 'slurm', 'mpi'], default='none')
     ap.add_argument('--seed', type=int, default=None)
     ap.add_argument('--options', nargs='+', action=DictAction)
-    ap.add_argument('--iters', type=int, default=50, help='iterations to run')
+    ap.add_argument('--iters', type=int, default=None,
+                    help='iteration-based smoke run: stop after this many iterations')
+    ap.add_argument('--iters-per-epoch', type=int, default=None,
+                    help='epoch length (len(data_loader) in the reference); default: '
+                         '3300 BONAI training tiles / global batch, or the data module\'s '
+                         '`iters_per_epoch(cfg, world)`')
+    ap.add_argument('--epochs', type=int, default=None, help='default: cfg.total_epochs')
     ap.add_argument('--size', type=int, default=1024)
     ap.add_argument('--num-gt', type=int, default=80)
     ap.add_argument('--data-module', default=None)
@@ -73,8 +79,9 @@ def main():
     if args.options:
         cfg.merge_from_dict(args.options)
     cfg.model.pretrained = None
+    launcher_env(args.launcher)
     rank, world = (init_dist(cfg.get('dist_params', {}).get('backend', 'nccl'))
-                   if args.launcher == 'pytorch' else (0, 1))
+                   if args.launcher != 'none' else (0, 1))
     if args.seed is not None:
         set_random_seed(args.seed)
     torch.manual_seed(args.seed if args.seed is not None else 0)
@@ -83,7 +90,14 @@ def main():
     device = torch.device('cuda', local)
     model = build_detector(cfg.model, train_cfg=cfg.train_cfg, test_cfg=cfg.test_cfg)
     model.train()
-    trainer = Trainer(model, cfg, device)
+    data_mod = importlib.import_module(args.data_module) if args.data_module else None
+    per_gpu = cfg.get('data', {}).get('samples_per_gpu', 2) if 'data' in cfg else 2
+    ipe = args.iters_per_epoch
+    if ipe is None and data_mod is not None and hasattr(data_mod, 'iters_per_epoch'):
+        ipe = data_mod.iters_per_epoch(cfg, world)
+    if ipe is None:
+        ipe = max(1, 3300 // (per_gpu * world))      # BONAI: 3 300 training tiles (README.md:13)
+    trainer = Trainer(model, cfg, device, iters_per_epoch=ipe)
     work_dir = args.work_dir or os.path.join('work_dirs', os.path.splitext(
         os.path.basename(args.config))[0])
     if rank == 0:
@@ -92,24 +106,32 @@ def main():
     if resume:
         meta = trainer.load_checkpoint(resume, resume=True)
         if rank == 0:
-            print(f'resumed from {resume} at iter {meta.get("iter", 0)}')
-    if args.data_module:
-        batches = importlib.import_module(args.data_module).iter_batches(cfg, rank, world)
+            print(f'resumed from {resume} at epoch {trainer.epoch}, iter {meta.get("iter", 0)}')
+    elif cfg.get('load_from'):
+        trainer.load_checkpoint(cfg.load_from, resume=False)
+    if data_mod is not None:
+        batches = data_mod.iter_batches(cfg, rank, world)
     else:
         batches = synthetic_batches(cfg, rank, world, args.size, args.num_gt, device)
     interval = cfg.get('log_config', {}).get('interval', 10)
+    if args.iters is None:
+        # the reference's schedule: total_epochs epochs, LR stepped by epoch, epoch_{n}.pth
+        ck = cfg.get('checkpoint_config', {}).get('interval', 1)
+        trainer.run(batches, max_epochs=args.epochs, work_dir=work_dir, checkpoint_interval=ck,
+                    log_interval=interval, rank=rank, log=lambda m: print(m, flush=True))
+        return
     nxt = trainer.stage(next(batches))
     t0, n_img = time.time(), 0
     for it in range(args.iters):
         cur, nxt = nxt, trainer.stage(next(batches))
         log = (it + 1) % interval == 0 or it + 1 == args.iters
-        out = trainer.train_step(cur, read_logs=log)
+        out = trainer.train_step(cur, read_logs=log, prefetch=nxt)
         n_img += len(cur['img_metas']) * world
         if log and rank == 0:
             dt = time.time() - t0
             items = ', '.join(f'{k}: {v:.4f}' for k, v in out.items())
-            print(f'Iter [{trainer.iter}]\tlr: {trainer.current_lr():.3e}, {n_img / dt:.1f} img/s, '
-                  f'{items}', flush=True)
+            print(f'Epoch [{trainer.epoch + 1}] Iter [{trainer.iter}]\tlr: {trainer.current_lr():.3e}, '
+                  f'{n_img / dt:.1f} img/s, {items}', flush=True)
     if rank == 0:
         path = os.path.join(work_dir, f'iter_{trainer.iter}.pth')
         trainer.save_checkpoint(path, meta=dict(config=cfg.filename))
