@@ -190,102 +190,134 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
   const bool is_wgrad = p.mode >= WGRAD_2D;
 
+  // The producer and MMA roles are executed by WHOLE warps in convergent control flow; only the
+  // asynchronous instructions themselves are issued by one elected lane.  Everything they consume
+  // (stage addresses, coordinates, descriptors) is then warp-uniform and lives in uniform
+  // registers.  With the loops inside `if (lane == 0)` the compiler could not prove uniformity and
+  // wrapped every UTMALDG / UTCHMMA / UTCBAR in an ELECT + R2UR.BROADCAST waterfall: measured
+  // (LOFT_GEMM_SKIP runs, gpurun_out/gemm_timeline_c/d.txt) ~125 ns + 45 ns per MMA on the issue
+  // side and ~400 ns per k-block on the load side whatever the tile width -- the k-loop of every
+  // tile narrower than 256 columns ran at that floor instead of at its MMA time.
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
-        int t = tile;
-        // pair mode: (ct, pt) of the tile index name a PAIR of 128-channel tiles and a pair of
-        // B half-tiles; this CTA stages the members with its rank
-        const int ct = kPair ? (t % p.nct) * 2 + (int)rank : t % p.nct;
-        t /= p.nct;
-        int pt = kPair ? (t % p.npt) * 2 + (int)rank : t % p.npt, tap = 0, split = 0, grp;
-        t /= p.npt;
-        if (is_wgrad) {
-          tap = t % p.ntaps;
-          t /= p.ntaps;
-          split = t % p.splits;
-          grp = t / p.splits;
-        } else {
-          grp = t;
-        }
-        const int gn0 = grp * p.group_n;  // first image of this group
-        int kb_begin = 0, kb_count = p.num_kb;
-        if (is_wgrad) {
-          kb_begin = split * p.kb_per_split;
-          kb_count = min(p.kb_per_split, p.num_kb - kb_begin);
-        }
-        int n0 = 0, h0 = 0, w0 = 0;
-        if (p.mode == FPROP_CONV || p.mode == DGRAD_CONV) {
-          tile_pixel_origin(p, pt, n0, h0, w0);
-          n0 += gn0;
-        }
-        const int tdh = tap / 3 - 1, tdw = tap % 3 - 1;  // WGRAD_CONV tap shift
-        for (int kbi = 0; kbi < kb_count; ++kbi) {
-          const int kb = kb_begin + kbi;
-          mbar_wait(&empty_bar[s], ph ^ 1u);
-          uint8_t* sa = smem + s * stage_bytes;
-          uint8_t* sb = sa + kABytes;
-          // pair mode: both CTAs' loads complete on the LEADER's full barrier, which expects the
-          // bytes of both (a peer complete_tx that lands before the leader's expect_tx only drives
-          // the tx-count negative; the phase cannot complete before the leader's arrival)
+    const bool elected = elect_one_sync();
+    int s = 0;
+    uint32_t ph = 0;
+    const bool conv_b = p.mode == FPROP_CONV || p.mode == DGRAD_CONV;
+    for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
+      int t = tile;
+      // pair mode: (ct, pt) of the tile index name a PAIR of 128-channel tiles and a pair of
+      // B half-tiles; this CTA stages the members with its rank
+      const int ct = kPair ? (t % p.nct) * 2 + (int)rank : t % p.nct;
+      t /= p.nct;
+      int pt = kPair ? (t % p.npt) * 2 + (int)rank : t % p.npt, tap = 0, split = 0, grp;
+      t /= p.npt;
+      if (is_wgrad) {
+        tap = t % p.ntaps;
+        t /= p.ntaps;
+        split = t % p.splits;
+        grp = t / p.splits;
+      } else {
+        grp = t;
+      }
+      const int gn0 = grp * p.group_n;  // first image of this group
+      int kb_begin = 0, kb_count = p.num_kb;
+      if (is_wgrad) {
+        kb_begin = split * p.kb_per_split;
+        kb_count = min(p.kb_per_split, p.num_kb - kb_begin);
+      }
+      int n0 = 0, h0 = 0, w0 = 0;
+      if (conv_b) {
+        tile_pixel_origin(p, pt, n0, h0, w0);
+        n0 += gn0;
+      }
+      const int tdh = tap / 3 - 1, tdw = tap % 3 - 1;  // WGRAD_CONV tap shift
+      // running coordinates of the k-block (no division in the loop):
+      //   conv fprop / dgrad: k-block = (filter tap (dh, dw), 32-channel chunk ch)
+      //   conv wgrad:         k-block = 32-pixel patch (kwi, khi, kni) of the group's images
+      int ch = 0, tp = 0, dh = p.ntaps == 9 ? -1 : 0, dw = p.ntaps == 9 ? -1 : 0;
+      int kwi = 0, khi = 0, kni = 0;
+      if (p.mode == WGRAD_CONV) {
+        kwi = kb_begin % p.tiles_w;
+        const int r = kb_begin / p.tiles_w;
+        khi = r % p.tiles_h;
+        kni = r / p.tiles_h;
+      }
+      for (int kbi = 0; kbi < kb_count; ++kbi) {
+        const int kb = kb_begin + kbi;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        uint8_t* sa = smem + s * stage_bytes;
+        uint8_t* sb = sa + kABytes;
+        // pair mode: both CTAs' loads complete on the LEADER's full barrier, which expects the
+        // bytes of both (a peer complete_tx that lands before the leader's expect_tx only drives
+        // the tx-count negative; the phase cannot complete before the leader's arrival)
+        const uint32_t fb = kPair ? mapa_shared(smem_u32(&full_bar[s]), 0u) : smem_u32(&full_bar[s]);
+        if (elected) {
           if (!kPair || leader) mbar_expect_tx(&full_bar[s], p.tx_bytes);
-          const uint32_t fb = kPair ? mapa_shared(smem_u32(&full_bar[s]), 0u) : smem_u32(&full_bar[s]);
           switch (p.mode) {
             case FPROP_2D:
               tma_load_2d<kPair>(sa, &tmap_a, fb, kb * kKB, ct * kBlockC);
               tma_load_2d<kPair>(sb, &tmap_b, fb, kb * kKB, pt * p.n_half);
               break;
-            case FPROP_CONV: {
-              const int tp = kb / p.cchunks, ch = kb % p.cchunks;
-              const int dh = (p.ntaps == 9) ? tp / 3 - 1 : 0, dw = (p.ntaps == 9) ? tp % 3 - 1 : 0;
+            case FPROP_CONV:
               tma_load_3d<kPair>(sa, &tmap_a, fb, kb * kKB, ct * kBlockC, grp);
               tma_load_4d<kPair>(sb, &tmap_b, fb, ch * kKB, w0 + dw, h0 + dh, n0);
               break;
-            }
             case DGRAD_2D:
               // A view: (32 cin, Cout rows, Cin/32 chunks); k-block = 32 cout rows
               tma_load_3d<kPair>(sa, &tmap_a, fb, 0, kb * kKB, ct * (kBlockC / 32));
               tma_load_2d<kPair>(sb, &tmap_b, fb, kb * kKB, pt * p.n_half);
               break;
-            case DGRAD_CONV: {
-              const int tp = kb / p.cchunks, ch = kb % p.cchunks;
-              const int dh = (p.ntaps == 9) ? tp / 3 - 1 : 0, dw = (p.ntaps == 9) ? tp % 3 - 1 : 0;
+            case DGRAD_CONV:
               // A view of W[Cout][ntaps*Cin]: chunk index = (tap*Cin + cin0)/32
               tma_load_4d<kPair>(sa, &tmap_a, fb, 0, ch * kKB,
                                  tp * (p.tap_stride / 32) + ct * (kBlockC / 32), grp);
               tma_load_4d<kPair>(sb, &tmap_b, fb, ch * kKB, w0 - dw, h0 - dh, n0);
               break;
-            }
             case WGRAD_2D:
               tma_load_3d<kPair>(sa, &tmap_a, fb, 0, kb * kKB, ct * (kBlockC / 32));
               tma_load_3d<kPair>(sb, &tmap_b, fb, 0, kb * kKB, pt * (p.n_half / 32));
               break;
             case WGRAD_CONV: {
-              int kn0, kh0, kw0;
-              tile_pixel_origin(p, kb, kn0, kh0, kw0);
-              kn0 += gn0;
+              const int kw0 = kwi * p.tw, kh0 = khi * p.th, kn0 = kni * p.tn + gn0;
               tma_load_5d<kPair>(sa, &tmap_a, fb, 0, kw0, kh0, kn0, ct * (kBlockC / 32));
               tma_load_5d<kPair>(sb, &tmap_b, fb, 0, kw0 + tdw, kh0 + tdh, kn0,
                                  pt * (p.n_half / 32));
               break;
             }
           }
-          if (++s == n_stages) {
-            s = 0;
-            ph ^= 1u;
+        }
+        if (++ch == p.cchunks) {          // next filter tap (conv fprop / dgrad)
+          ch = 0;
+          ++tp;
+          if (++dw == 2) {
+            dw = -1;
+            ++dh;
           }
+        }
+        if (++kwi == p.tiles_w) {         // next pixel patch (conv wgrad)
+          kwi = 0;
+          if (++khi == p.tiles_h) {
+            khi = 0;
+            ++kni;
+          }
+        }
+        if (++s == n_stages) {
+          s = 0;
+          ph ^= 1u;
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0 && (!kPair || leader)) {
+    if (!kPair || leader) {
+      const bool elected = elect_one_sync();
       uint32_t lt = 0;
       int s = 0;
       uint32_t ph = 0;
+      const uint32_t smem_base = smem_u32(smem);
+      const uint64_t a_desc = p.a_desc, b_desc = p.b_desc;
+      const uint32_t a_kstep = p.a_kstep, b_kstep = p.b_kstep, idesc = p.idesc;
       for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++lt) {
         int kb_count = p.num_kb;
         if (is_wgrad) {
@@ -299,31 +331,35 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
         for (int kbi = 0; kbi < kb_count; ++kbi) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          if (trace && lt == 0 && kbi == 0) trace[2] = gtime();
-          const uint32_t sa = smem_u32(smem + s * stage_bytes);
+          if (trace && lt == 0 && kbi == 0 && elected) trace[2] = gtime();
+          const uint32_t sa = smem_base + s * stage_bytes;
           const uint32_t sb = sa + kABytes;
-          const uint64_t ad = p.a_desc + (uint64_t)((sa >> 4) & 0x3FFFu);
-          const uint64_t bd = p.b_desc + (uint64_t)((sb >> 4) & 0x3FFFu);
+          const uint64_t ad = a_desc + (uint64_t)((sa >> 4) & 0x3FFFu);
+          const uint64_t bd = b_desc + (uint64_t)((sb >> 4) & 0x3FFFu);
+          if (elected) {
 #pragma unroll
-          for (int ks = 0; ks < kKB / 8; ++ks) {
-            if constexpr (kPair)
-              umma_tf32_pair(tmem_d, ad + (uint64_t)(ks * p.a_kstep),
-                             bd + (uint64_t)(ks * p.b_kstep), p.idesc, (kbi | ks) != 0 ? 1u : 0u);
-            else
-              umma_tf32(tmem_d, ad + (uint64_t)(ks * p.a_kstep), bd + (uint64_t)(ks * p.b_kstep),
-                        p.idesc, (kbi | ks) != 0 ? 1u : 0u);
+            for (int ks = 0; ks < kKB / 8; ++ks) {
+              if constexpr (kPair)
+                umma_tf32_pair(tmem_d, ad + (uint64_t)(ks * a_kstep), bd + (uint64_t)(ks * b_kstep),
+                               idesc, (kbi | ks) != 0 ? 1u : 0u);
+              else
+                umma_tf32(tmem_d, ad + (uint64_t)(ks * a_kstep), bd + (uint64_t)(ks * b_kstep),
+                          idesc, (kbi | ks) != 0 ? 1u : 0u);
+            }
+            // frees the stage in BOTH CTAs of a pair (the MMA read both shared memories)
+            if constexpr (kPair) umma_commit_pair(&empty_bar[s], 3);
+            else umma_commit(&empty_bar[s]);
           }
-          // frees the stage in BOTH CTAs of a pair (the MMA read both shared memories)
-          if constexpr (kPair) umma_commit_pair(&empty_bar[s], 3);
-          else umma_commit(&empty_bar[s]);
           if (++s == n_stages) {
             s = 0;
             ph ^= 1u;
           }
         }
-        if constexpr (kPair) umma_commit_pair(&tfull_bar[as], 3);
-        else umma_commit(&tfull_bar[as]);
-        if (trace && lt == 0) trace[3] = gtime();
+        if (elected) {
+          if constexpr (kPair) umma_commit_pair(&tfull_bar[as], 3);
+          else umma_commit(&tfull_bar[as]);
+          if (trace && lt == 0) trace[3] = gtime();
+        }
       }
     }
   } else {
@@ -795,7 +831,15 @@ int round16(int x) { return (x + 15) & ~15; }
 int round8(int x) { return (x + 7) & ~7; }
 
 // ---- pair (cta_group::2) policy -----------------------------------------------------------
-// LOFT_2CTA=0 never, 1 (default) when the cost model below prefers it, 2 whenever eligible.
+// LOFT_2CTA=0 never, 1 (default) by the rules below, 2 whenever eligible.
+// Measured per shape (gpurun_out/gemm_shapes_v2_2cta{0,2}.txt): a pair launch costs ~1.5 us more
+// to start and drain (cluster barrier, paired TMEM allocation) and, for the same tile width, has
+// half as many independent CTAs; it wins 6-12 % where the launch runs for more than ~1.7 waves of
+// 1-CTA tiles with a k-loop long enough to be operand-delivery bound (FPN/RPN P2-P3 convs, the
+// mask head, the grouped FOA convs, the 12544-wide fc layers' dgrad / wgrad, wgrads over >= 32 K
+// pixels), and loses 5-15 % on single-wave launches (layer3/4, P4-P6, the 1024-wide fc layers).
+constexpr long long kPairMinTiles = 256;   // 1-CTA work items (148 SMs -> 1.7 waves)
+constexpr int kPairMinKb = 16;             // k-blocks per tile (K >= 512)
 int pair_mode() {
   static int v = -1;
   if (v < 0) {
@@ -851,11 +895,14 @@ int pick_n_2d(long long P, int nct) {
 
 // Pair form: UMMA N in {256,128,64} (halves of 128/64/32 rows per CTA); returns 0 if the 1-CTA
 // choice n1 is predicted to be at least as fast.  nct = number of 128-channel tiles (even).
-int pick_n_2d_pair(long long P, int nct, int n1) {
+int pick_n_2d_pair(long long P, int nct, int n1, int num_kb) {
   if (pair_mode() == 0 || nct < 2 || (nct & 1)) return 0;
   if (P < 32) return 0;
+  if (pair_mode() == 1 &&
+      (num_kb < kPairMinKb || (long long)nct * loft_cdiv(P, n1) < kPairMinTiles))
+    return 0;
   int best = 0;
-  long long bc = pair_mode() >= 2 ? -1 : fill_cost((long long)nct * loft_cdiv(P, n1), n1, false);
+  long long bc = -1;
   if (P < 256) {
     const int n = round16((int)P);
     const long long c = fill_cost(nct / 2, n, true);
@@ -915,7 +962,8 @@ void pick_pixel_tile(int N, int H, int W, int nct, int& tn, int& th, int& tw) {
 bool pick_pixel_tile_pair(int N, int H, int W, int nct, int G, long long tiles1, int n1, int& tn,
                           int& th, int& tw) {
   if (pair_mode() == 0 || nct < 2 || (nct & 1)) return false;
-  long long bc = pair_mode() >= 2 ? -1 : fill_cost(tiles1, n1, false);
+  if (pair_mode() == 1 && tiles1 < kPairMinTiles) return false;
+  long long bc = -1;    // eligible and worthwhile: the cheapest pair tiling
   bool found = false;
   auto consider = [&](int a, int b, int c) {
     if (a * b * c > 128 || a * b * c < 8) return;
@@ -1031,7 +1079,7 @@ int loft_gemm_fprop(const float* x, const float* w, float* y, long long P, int K
   p.splits = 1;
   p.nct = loft_cdiv(Cout, kBlockC);
   p.n_mma = pick_n_2d(P, p.nct);
-  if (const int n2 = pick_n_2d_pair(P, p.nct, p.n_mma)) {
+  if (const int n2 = pick_n_2d_pair(P, p.nct, p.n_mma, loft_cdiv(K, kKB))) {
     p.pair = 1;
     p.n_mma = n2;
     p.nct /= 2;
@@ -1081,7 +1129,7 @@ int loft_gemm_dgrad_hw(const float* dy, const float* w, float* dx, long long P, 
   p.splits = 1;
   p.nct = loft_cdiv(Cin, kBlockC);
   p.n_mma = pick_n_2d(P, p.nct);
-  if (const int n2 = pick_n_2d_pair(P, p.nct, p.n_mma)) {
+  if (const int n2 = pick_n_2d_pair(P, p.nct, p.n_mma, loft_cdiv(Cout, kKB))) {
     p.pair = 1;
     p.n_mma = n2;
     p.nct /= 2;
@@ -1136,7 +1184,9 @@ int loft_gemm_wgrad(const float* dy, const float* x, float* dw, long long P, int
   p.n_mma = Cin >= 256 ? 256 : Cin;  // multiple of 32
   p.nct = loft_cdiv(Cout, kBlockC);
   // pair form: 256 output channels per CTA pair, each CTA stages half of the Cin columns
-  if (pair_mode() != 0 && p.nct >= 2 && (p.nct & 1) == 0 && p.n_mma % 64 == 0) {
+  if (pair_mode() != 0 && p.nct >= 2 && (p.nct & 1) == 0 && p.n_mma % 64 == 0 &&
+      (pair_mode() >= 2 || P >= 32768 ||
+       (long long)p.nct * loft_cdiv(Cin, p.n_mma) >= kPairMinTiles)) {
     p.pair = 1;
     p.nct /= 2;
   }
@@ -1305,7 +1355,8 @@ int loft_conv3x3_wgrad_grouped(const float* dy, const float* x, float* dw, int N
   p.tiles_h = loft_cdiv(H, p.th);
   p.n_mma = Cin >= 256 ? 256 : Cin;
   p.nct = loft_cdiv(Cout, kBlockC);
-  if (pair_mode() != 0 && p.nct >= 2 && (p.nct & 1) == 0 && p.n_mma % 64 == 0) {
+  if (pair_mode() != 0 && p.nct >= 2 && (p.nct & 1) == 0 && p.n_mma % 64 == 0 &&
+      (pair_mode() >= 2 || (long long)N * H * W >= 32768)) {
     p.pair = 1;
     p.nct /= 2;
   }

@@ -296,7 +296,7 @@ def test_recorded_trunk_graph_matches_module_path(monkeypatch):
 
     # fixed proposals (jittered GT + random boxes): without them tiny score differences reorder
     # the NMS output and the two runs sample different RoIs -- chaos, not error
-    from bonai_b200.models.dense_heads import RPNHead
+    import e2e_check
     g = torch.Generator().manual_seed(5)
     props = []
     for b in gb:
@@ -305,7 +305,6 @@ def test_recorded_trunk_graph_matches_module_path(monkeypatch):
         wh = torch.rand(150, 2, generator=g) * 50 + 4
         box = torch.cat([jit, torch.cat([xy, xy + wh], 1)]).clamp(0, 256)
         props.append(torch.cat([box, torch.rand(box.shape[0], 1, generator=g)], 1))
-    monkeypatch.setattr(RPNHead, 'forced_proposals', props)
 
     def run(trunk):
         monkeypatch.setenv('LOFT_TRUNK', '1' if trunk else '0')
@@ -316,10 +315,11 @@ def test_recorded_trunk_graph_matches_module_path(monkeypatch):
         data = dict(img=img.cuda(), img_metas=metas, gt_bboxes=gb, gt_labels=gl,
                     gt_masks=[BitmapMasks(m, 256, 256) for m in gm], gt_offsets=go)
         out = []
-        for it in range(3):
-            torch.manual_seed(100 + it)
-            logs = trainer.train_step(data, read_logs=True)
-            out.append((logs, float(trainer.store.grad_norm())))
+        with e2e_check.teacher_force(model, proposals=props):
+            for it in range(3):
+                torch.manual_seed(100 + it)
+                logs = trainer.train_step(data, read_logs=True)
+                out.append((logs, float(trainer.store.grad_norm())))
         assert (model.__dict__.get('_trunk') is not None) == trunk
         if trunk:
             prog = next(iter(model._trunk.progs.values()))

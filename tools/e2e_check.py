@@ -24,19 +24,20 @@ class teacher_force:
     generation is kept out of the trunk's forward graph (LOFT_GRAPH_PROPOSALS=0) so that
     `get_bboxes` is what the step calls."""
 
-    def __init__(self, model, draws, proposals=None):
-        self.model, self.draws, self.proposals = model, list(draws), proposals
+    def __init__(self, model, draws=None, proposals=None):
+        self.model, self.draws, self.proposals = model, draws, proposals
         self.samplers = [s for s in (getattr(model.rpn_head, 'sampler', None),
                                      getattr(model.roi_head, 'bbox_sampler', None))
                          if s is not None]
 
     def __enter__(self):
-        draws = self.draws
+        if self.draws is not None:
+            draws = list(self.draws)
 
-        def forced_choice(gallery, num):
-            return draws.pop(0).to(gallery.device)
-        for s in self.samplers:
-            s.random_choice = forced_choice
+            def forced_choice(gallery, num):
+                return draws.pop(0).to(gallery.device)
+            for s in self.samplers:
+                s.random_choice = forced_choice
         self._env = os.environ.get('LOFT_GRAPH_PROPOSALS')
         if self.proposals is not None:
             props = self.proposals

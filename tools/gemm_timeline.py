@@ -37,7 +37,7 @@ def main():
     names = sys.argv[1:] or list(SHAPES)
     lib = L.lib()
     nsm = torch.cuda.get_device_properties(0).multi_processor_count
-    buf = torch.zeros(8 * (nsm + 8), dtype=torch.int64, device=dev)
+    buf = torch.zeros(8 * 1024 + 4 * 64, dtype=torch.int64, device=dev)
     print(f'{"shape":12s} {"ctas":>4s} {"tiles":>5s} | {"wait":>6s} {"1st_ld":>6s} {"mma_t0":>6s} '
           f'{"drain":>6s} {"epi_t0":>6s} {"rest":>7s} | {"total":>7s} {"event":>7s}  (us, median CTA; '
           f'total = first entry -> last store)')
@@ -83,7 +83,8 @@ def main():
         launch()
         torch.cuda.synchronize()
         lib.loft_debug_set_trace(ctypes.c_void_p(0))
-        t = buf.view(-1, 8).cpu()
+        kt = buf[8 * 1024:].view(64, 4).cpu().double()
+        t = buf[:8 * 1024].view(-1, 8).cpu()
         t = t[t[:, 0] > 0].double()
         n_cta = t.shape[0]
         lead = t[t[:, 2] > 0]                   # CTAs that issued MMAs (all, or the pair leaders)
@@ -95,6 +96,13 @@ def main():
               f'{med(t[:, 4] - t[:, 1]) - med(lead[:, 3] - lead[:, 1]):6.2f} '
               f'{med(t[:, 5] - t[:, 4]):6.2f} {med(t[:, 6] - t[:, 5]):7.2f} | {total:7.2f} '
               f'{ev_us:7.2f}  {flops / ev_us / 1e6:6.0f} TF/s')
+        if os.environ.get('LOFT_KTRACE'):
+            t0 = float(t[0, 1])
+            rows = [(k, *((kt[k] - t0) / 1e3).tolist()) for k in range(64) if kt[k, 0] > 0]
+            print('   CTA 0, us since start: k-block | empty acquired | TMA issued | full acquired | '
+                  'MMAs issued')
+            for r in rows[:40]:
+                print('   %3d  %7.2f %7.2f %7.2f %7.2f' % r)
 
 
 if __name__ == '__main__':
