@@ -205,6 +205,23 @@ int loft_mask_flip_pad(const uint8_t* in, uint8_t* out, long long G, int H, int 
  * mode 0 = BCE-with-logits (cross_entropy_loss.py:58-125), 1 = L1, 2 = SmoothL1
  * (smooth_l1_loss.py:8-42); sums are accumulated into device scalars (weight_reduce_loss,
  * losses/utils.py:26-52); gscale is the device-resident upstream gradient (NULL = 1). */
+/* AnchorHead.loss over all pyramid levels in one launch (anchor_head.py:382-497): sums[0..n) =
+ * per-level sigmoid-BCE * cls_scale, sums[n..2n) = per-level L1 (mode 1) / SmoothL1 (mode 2) *
+ * bbox_scale; if `grad` of a level is set, d(total)/d(fused head output) is written there in full
+ * ([rows, ld], padding columns zero).  Fused head output row = (image, y, x), columns [0,A) cls,
+ * [A,5A) deltas; labels / label_w are [rows*A], bbox_t / bbox_w [rows*4A]. */
+typedef struct {
+  const float* out;
+  const float* labels;
+  const float* label_w;
+  const float* bbox_t;
+  const float* bbox_w;
+  float* grad;
+  long long rows;
+} loft_rpn_level_t;
+int loft_rpn_loss_fused(const loft_rpn_level_t* levels, int n_levels, int A, int ld, int mode_bbox,
+                        float beta, float cls_scale, float bbox_scale, float* sums,
+                        cudaStream_t stream);
 int loft_elem_loss_fwd(int mode, const float* pred, long long ld, int col_off, int ncols,
                        long long rows, const float* target, const float* weight, float beta,
                        float scale, float* out_sum, cudaStream_t stream);

@@ -11,10 +11,13 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
-TF32_TOL = 2e-3
-# gradients through a ReLU: TF32 noise flips the mask of activations within ~1e-3 of zero, which
-# moves the gradient by ~sqrt(flipped fraction) in relative L2 -- inherent to TF32, not a bug
-GRAD_TOL = 1.5e-2
+# Operands of these single-layer tests are pre-rounded to the TF32 grid, so every product is exact
+# in fp32 and the pre-activations differ from the fp32 reference by accumulation order only
+# (~1e-6 relative): a ReLU mask practically never flips, and what remains is the RNA rounding of
+# the stored output (`round_out`, 2^-11 / sqrt(3) ~ 2.8e-4 relative per value).  A wrong filter
+# tap, halo row or tile edge shows up at 1e-2 .. 1, far above these bounds.
+TF32_TOL = 5e-4          # forward outputs and data gradients (both stored TF32-rounded)
+GRAD_TOL = 2e-3          # weight / bias gradients (fp32 atomics in varying order over <= 1e5 terms)
 
 
 @pytest.fixture(scope='module', autouse=True)
@@ -36,6 +39,15 @@ def tf32_round(t):
     """round-to-nearest-away to a 10-bit mantissa, like cvt.rna.tf32.f32"""
     i = t.contiguous().view(torch.int32)
     return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def relu_like(z, y_gpu):
+    """Reference ReLU whose BACKWARD uses the mask of the GPU's own output: a pre-activation that
+    is zero to 1e-7 may land on either side, and ONE flipped unit with a large upstream gradient
+    moves the data gradient of its 3x3 neighbourhood by percents of the whole tensor's norm
+    (measured: tools/diag_dgrad.py -- 1 flip in 650 k elements = 1.0e-2 relative L2, the other
+    three groups of the same launch 2.1e-4).  Forward values are unaffected (|z| ~ 1e-7 there)."""
+    return z * (y_gpu.detach() > 0).to(z.dtype)
 
 
 class _Store:
@@ -68,8 +80,9 @@ def test_conv3x3_fwd_bwd(shape):
     xr = x.clone().requires_grad_(True)
     wr = w.clone().requires_grad_(True)
     br = b.clone().requires_grad_(True)
-    yr = F.relu(F.conv2d(xr, wr, br, padding=1))
-    assert rel(y, yr) < TF32_TOL
+    zr = F.conv2d(xr, wr, br, padding=1)
+    yr = relu_like(zr, y)
+    assert rel(y, F.relu(zr)) < TF32_TOL
     dy = tf32_round(rnd(*y.shape, seed=4))
     y.backward(dy)
     yr.backward(dy)
@@ -123,8 +136,9 @@ def test_conv_bn_residual_paths(cfg):
         w.clone().requires_grad_(True)
     gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
     z = F.conv2d(xr, wr, stride=s, padding=pad)
-    yr = F.relu(F.batch_norm(z, mean, var, gr, br, False, 0.0, 1e-5) + rr)
-    assert rel(y, yr) < TF32_TOL
+    zr = F.batch_norm(z, mean, var, gr, br, False, 0.0, 1e-5) + rr
+    yr = relu_like(zr, y)
+    assert rel(y, F.relu(zr)) < TF32_TOL
     dy = tf32_round(rnd(*y.shape, seed=8))
     y.backward(dy)
     yr.backward(dy)
@@ -175,9 +189,9 @@ def test_linear(shape):
     y = D.linear(xg, spec)
     xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), \
         b.clone().requires_grad_(True)
-    yr = F.linear(xr, wr, br)
-    yr = F.relu(yr) if relu else yr
-    assert rel(y, yr) < TF32_TOL
+    zr = F.linear(xr, wr, br)
+    yr = relu_like(zr, y) if relu else zr
+    assert rel(y, F.relu(zr) if relu else zr) < TF32_TOL
     dy = tf32_round(rnd(P, Co, seed=4))
     y.backward(dy)
     yr.backward(dy)
@@ -200,8 +214,9 @@ def test_deconv2x2():
     y = D.deconv2x2(xg, spec)
     xr, wr, br = x.clone().requires_grad_(True), wt.clone().requires_grad_(True), \
         b.clone().requires_grad_(True)
-    yr = F.relu(F.conv_transpose2d(xr, wr, br, stride=2))
-    assert rel(y, yr) < TF32_TOL
+    zr = F.conv_transpose2d(xr, wr, br, stride=2)
+    yr = relu_like(zr, y)
+    assert rel(y, F.relu(zr)) < TF32_TOL
     dy = tf32_round(rnd(*y.shape, seed=4))
     y.backward(dy)
     yr.backward(dy)
@@ -493,8 +508,9 @@ def test_grouped_conv3x3_matches_per_group():
         xr = x[g * Pg:(g + 1) * Pg].clone().requires_grad_(True)
         wr = wrefs[g].w.clone().requires_grad_(True)
         br = biases[g].clone().requires_grad_(True)
-        yr = F.relu(F.conv2d(xr, wr, br, padding=1))
-        assert rel(y[g * Pg:(g + 1) * Pg], yr) < TF32_TOL
+        zr = F.conv2d(xr, wr, br, padding=1)
+        yr = relu_like(zr, y[g * Pg:(g + 1) * Pg])
+        assert rel(y[g * Pg:(g + 1) * Pg], F.relu(zr)) < TF32_TOL
         yr.backward(dy[g * Pg:(g + 1) * Pg])
         assert rel(xg.grad[g * Pg:(g + 1) * Pg], xr.grad) < GRAD_TOL
         assert rel(wrefs[g].grad, wr.grad) < GRAD_TOL

@@ -14,15 +14,51 @@ sys.path.insert(0, os.path.join(ROOT, 'tools'))
 LOSS_TOL = 1e-3          # BASELINE.json north_star: losses within 1e-3 relative
 
 
+GRAD_TOL = 3e-2          # parameter gradients of trunk / RPN / bbox / mask heads vs the fp32 oracle
+                         # (they also receive the FOA head's data gradient, see below)
+FOA_LOCAL_TOL = 2e-3     # FOA head gradients, layer-local (teacher-forced) fp32 back-propagation
+
+
+def _check_report(rep):
+    assert rep['worst_loss_rel'] < LOSS_TOL, rep['losses']
+    assert 'missing' not in rep['grads'].values()
+    assert rep['worst_grad_rel_non_foa'][0] < GRAD_TOL, rep['worst_grad_rel_non_foa']
+    # The 10-deep FOA conv stacks.  Two forward passes that differ by TF32 rounding noise agree to
+    # 8e-4 in every activation but disagree on ~2e-4 of the ReLU masks per layer, and one flipped
+    # unit moves a gradient by ~sqrt(flipped fraction): against the fp32 oracle -- and equally
+    # against the TF32-EMULATED oracle, whose roundings decorrelate from the GPU's within five
+    # layers (tools/foa_layerwise.py, gpurun_out/foa_layerwise.txt) -- the head's gradients are off
+    # by 3-13 %; tests/test_oracle_tf32.py reproduces 9-10 % on the CPU alone.  The check a defect
+    # of the fused backward (grouped dgrad / wgrad, mask chain, column-sum bias gradients) cannot
+    # pass is layer-local: plain fp32 back-propagation through the head with the GPU's OWN
+    # activations as masks and saved operands (oracle/tf32_emu.foa_head_backward_teacher_forced).
+    assert rep['foa_grad_teacher_forced_layerwise'][0] < FOA_LOCAL_TOL, \
+        rep['foa_grad_teacher_forced_layerwise']
+    assert rep['worst_grad_rel_foa_vs_fp32'][0] < 0.2, rep['worst_grad_rel_foa_vs_fp32']
+    # ... and the deviation from the fp32 oracle is of the size TF32 rounding alone produces on
+    # the same inputs (emulated vs fp32 head, both on the CPU), not larger
+    assert rep['worst_grad_rel_foa_vs_fp32'][0] < \
+        3.0 * rep['foa_tf32_emulated_vs_fp32_same_inputs'][0] + 1e-2
+
+
 def test_step_parity_256_vs_oracle_and_reference_golden(golden_step):
     import e2e_check
     rep = e2e_check.run(size=256, n_img=1, num_gt=10, seed=0, verbose=False)
-    assert rep['worst_loss_rel'] < LOSS_TOL, rep['losses']
+    _check_report(rep)
     gold = dict(zip([str(n) for n in golden_step['loss_names']], golden_step['loss_values']))
     for k, (gpu, oracle, _) in rep['losses'].items():
         assert abs(gpu - gold[k]) <= LOSS_TOL * max(abs(gold[k]), 1e-6), (k, gpu, gold[k])
-    assert 'missing' not in rep['grads'].values()
-    assert rep['worst_grad_rel'][0] < 0.15, rep['worst_grad_rel']
+
+
+def test_step_parity_1024_baseline_config_vs_golden():
+    """BASELINE.json's own configuration (1024x1024, batch 2, G = 80): teacher-forced step against
+    tests/golden/loft_step_1024x2_g80.npz (oracle/make_golden_step.py; the oracle needs ~30 s of
+    CPU per step at this size, the golden keeps the GPU run short)."""
+    import e2e_check
+    golden = dict(np.load(os.path.join(ROOT, 'tests', 'golden', 'loft_step_1024x2_g80.npz')))
+    rep = e2e_check.run(golden=golden, verbose=False)
+    _check_report(rep)
+    assert int(golden['num_pos'].sum()) > 150        # ~100 positives per image at random init
 
 
 def test_step_parity_two_images_batched_nms():

@@ -57,3 +57,25 @@ def test_reference_live_if_present():
     _, logs = O.parse_losses(losses)
     for k, v in ref_logs.items():
         assert abs(float(logs[k]) - v) <= 1e-5 * max(1.0, abs(v)), (k, float(logs[k]), v)
+
+
+def test_golden_1024_step_inputs_reproduce_here():
+    """tests/golden/loft_step_1024x2_g80.npz (BASELINE config) replays sampler draws / proposals
+    against weights and inputs regenerated from seeds: the CPU RNG streams must reproduce them."""
+    import os
+    import sys
+    import numpy as np
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, 'tools'))
+    g = dict(np.load(os.path.join(root, 'tests', 'golden', 'loft_step_1024x2_g80.npz')))
+    from oracle import loft_cpu as O
+    from oracle.make_golden_step import checksums
+    size, n_img, num_gt, seed = (int(v) for v in g['meta'])
+    assert (size, n_img, num_gt) == (1024, 2, 80)
+    p = O.randomize_bn(O.init_params(seed), seed)
+    img, gb, gl, gm, go = O.make_inputs(seed, n_img, size, num_gt)
+    assert np.allclose(checksums(p, img, gb, go), g['checksums'], rtol=1e-9, atol=1e-6)
+    names = [str(n) for n in g['loss_names']]
+    assert names[-1] == 'loss' and abs(float(g['loss_values'][-1]) - 13.4505) < 1e-3
+    assert len(g['grad_names']) == len(g['grad_norms']) >= 250
+    assert all(g[f'proposals_{i}'].shape == (3000, 5) for i in range(n_img))
