@@ -149,9 +149,25 @@ class ParamStore:
         self.packed = []
         self.pre_finalize = []           # callables run at the start of finalize_grads
         self._fold_pairs = []
-        for m in model.modules():
+        self._owner = ''
+        for name, m in model.named_modules():
             if hasattr(m, 'loft_prepare'):
+                self._owner = name            # add_packed tags what the module registers
                 m.loft_prepare(self)
+        # The RoI heads' parameters are the tail of the trainable range (model.parameters()
+        # order): their gradients are final when autograd reaches the trunk's backward, so a
+        # data-parallel trainer can exchange them under it (Trainer, trunk._TrunkFn.backward).
+        self.head_start = self.n_train
+        names = {id(p): n for n, p in model.named_parameters()}
+        tail = True
+        for p, o in reversed(list(zip(order, offs))):
+            if o >= self.n_train:
+                continue
+            if tail and names.get(id(p), '').startswith('roi_head.') and id(p) not in bn_param_ids:
+                self.head_start = o
+            else:
+                tail = False
+        self.heads_done_hooks = []           # called at the start of the trunk's backward
         self._build_fold_tables()
         # everything whose in-place modification (load_state_dict, init_weights, an external torch
         # optimizer) must trigger a rebuild of the derived copies: the parameters themselves --
@@ -224,8 +240,22 @@ class ParamStore:
 
     # ------------------------------------------------------------------ packed weights
     def add_packed(self, packed):
+        packed.owner = self._owner
+        packed.scattered = False
         self.packed.append(packed)
         return packed
+
+    def heads_done(self):
+        """The RoI heads' backward has been issued (called by the trunk's backward node): fold
+        their packed-weight gradients into the parameter gradients now and tell the listeners."""
+        if not self.heads_done_hooks:
+            return
+        for pk in self.packed:
+            if pk.owner.startswith('roi_head') and not pk.scattered:
+                pk.scatter()
+                pk.scattered = True
+        for fn in self.heads_done_hooks:
+            fn()
 
     # ------------------------------------------------------------------ per-step protocol
     def _version_sig(self):
@@ -274,6 +304,8 @@ class ParamStore:
             self._packed_grads = [t for pk in self.packed for t in (pk.gw, pk.gb) if t is not None]
         if self._packed_grads:
             torch._foreach_zero_(self._packed_grads)
+        for pk in self.packed:
+            pk.scattered = False
         self._callback_queued = False
 
     def queue_finalize(self):
@@ -307,7 +339,9 @@ class ParamStore:
         self.join_wgrad_stream()
         self._bn_finalize()
         for pk in self.packed:
-            pk.scatter()
+            if not pk.scattered:
+                pk.scatter()
+                pk.scattered = True
         for p, g in self._grad_views:
             if g is not None and p.grad is not g:
                 p.grad = g

@@ -138,13 +138,13 @@ class RPNHead(nn.Module):
 
     def forward_train(self, x, img_metas, gt_bboxes, gt_labels=None, gt_bboxes_ignore=None,
                       proposal_cfg=None, rpn_outs=None, after_loss=None, proposals=None,
-                      **kwargs):
+                      grad_out=None, **kwargs):
         outs = rpn_outs if rpn_outs is not None else self(x)
         if gt_labels is None:
             loss_inputs = outs + (gt_bboxes, img_metas)
         else:
             loss_inputs = outs + (gt_bboxes, gt_labels, img_metas)
-        losses = self.loss(*loss_inputs, gt_bboxes_ignore=gt_bboxes_ignore)
+        losses = self.loss(*loss_inputs, gt_bboxes_ignore=gt_bboxes_ignore, grad_out=grad_out)
         if after_loss is not None:
             losses = after_loss(losses)
         if proposal_cfg is None:
@@ -242,7 +242,11 @@ class RPNHead(nn.Module):
         for tup in per_level:
             for t in tup:
                 t.record_stream(main)
-        self._prefetched = (tuple(sizes), per_level, num_total, ev, ident)
+        # a small FIFO: the next batch's targets are usually prefetched while the current
+        # batch's are still waiting to be consumed by loss()
+        slots = self.__dict__.setdefault('_prefetched', [])
+        slots.append((tuple(sizes), per_level, num_total, ev, ident))
+        del slots[:-2]
 
     @staticmethod
     def _gt_token(gt_bboxes):
@@ -259,23 +263,40 @@ class RPNHead(nn.Module):
     def has_prefetched(self, gt_bboxes):
         """True if targets for exactly these GT tensors were already prefetched (by the previous
         step's Trainer.train_step(..., prefetch=next_batch))."""
-        pre = self.__dict__.get('_prefetched')
-        return pre is not None and len(gt_bboxes) > 0 and gt_bboxes[0].is_cuda and \
-            self._same_gt(pre[4], gt_bboxes)
+        return len(gt_bboxes) > 0 and gt_bboxes[0].is_cuda and \
+            any(self._same_gt(pre[4], gt_bboxes) for pre in self.__dict__.get('_prefetched', ()))
 
-    def loss(self, cls_scores, bbox_preds, gt_bboxes, img_metas, gt_bboxes_ignore=None):
-        """AnchorHead.loss / RPNHead.loss (anchor_head.py:429-497, rpn_head.py:46-77)."""
+    def loss(self, cls_scores, bbox_preds, gt_bboxes, img_metas, gt_bboxes_ignore=None,
+             grad_out=None):
+        """AnchorHead.loss / RPNHead.loss (anchor_head.py:429-497, rpn_head.py:46-77).
+        `grad_out` (per level, a buffer shaped like the fused head output): the caller runs the
+        RPN backward itself (bonai_b200.trunk); all levels and both terms are then ONE launch that
+        also writes d(total)/d(head output) there, and the returned losses are detached."""
         featmap_sizes = [tuple(int(v) for v in f.size()[-2:]) for f in cls_scores]
         device = cls_scores[0].device
-        pre = self.__dict__.pop('_prefetched', None)
-        if pre is not None and pre[0] == tuple(featmap_sizes) and \
-                self._same_gt(pre[4], gt_bboxes):
+        slots = self.__dict__.get('_prefetched', [])
+        pre = next((q for q in slots if q[0] == tuple(featmap_sizes) and
+                    self._same_gt(q[4], gt_bboxes)), None)
+        if pre is not None:
+            slots[:] = [q for q in slots if q is not pre]
             _, per_level, num_total_samples, ev, _ = pre
             torch.cuda.current_stream(device).wait_event(ev)
         else:
             per_level, num_total_samples = self._build_targets(featmap_sizes, gt_bboxes, img_metas,
                                                                device)
         A = self.num_anchors
+        mode, beta = (K.L1, 1.0) if type(self.loss_bbox).__name__ == 'L1Loss' else \
+            (K.SMOOTH_L1, self.loss_bbox.beta)
+        if grad_out is not None and all(getattr(cs, '_loft_fused', None) is not None
+                                        for cs in cls_scores):
+            outs2d = [cs._loft_fused.permute(0, 2, 3, 1).reshape(-1, _FUSED_W) for cs in cls_scores]
+            sums = K.rpn_loss_fused(outs2d, per_level, A, mode, beta,
+                                    self.loss_cls.loss_weight / num_total_samples,
+                                    self.loss_bbox.loss_weight / num_total_samples,
+                                    grads=[g.view(-1, _FUSED_W) for g in grad_out])
+            n = len(cls_scores)
+            return dict(loss_rpn_cls=[sums[l:l + 1] for l in range(n)],
+                        loss_rpn_bbox=[sums[n + l:n + l + 1] for l in range(n)])
         loss_cls, loss_bbox = [], []
         for l, cs in enumerate(cls_scores):
             fused = getattr(cs, '_loft_fused', None)
@@ -286,8 +307,6 @@ class RPNHead(nn.Module):
             loss_cls.append(K.elem_loss(out2d, lab, lw, K.BCE_LOGITS,
                                         self.loss_cls.loss_weight / num_total_samples,
                                         col_off=0, ncols=A))
-            mode, beta = (K.L1, 1.0) if type(self.loss_bbox).__name__ == 'L1Loss' else \
-                (K.SMOOTH_L1, self.loss_bbox.beta)
             loss_bbox.append(K.elem_loss(out2d, bt, bw, mode,
                                          self.loss_bbox.loss_weight / num_total_samples,
                                          col_off=A, ncols=4 * A, beta=beta))

@@ -83,6 +83,7 @@ class TwoStageDetector(BaseDetector):
         store = get_store(self, img.device if img.is_cuda else None)
         store.begin_step()
         ready_event = kwargs.pop('ready_event', None)    # inputs staged on a copy stream
+        prefetch_next = kwargs.pop('prefetch_next', None)    # the NEXT batch (Trainer.train_step)
         if ready_event is not None:
             torch.cuda.current_stream(store.device).wait_event(ready_event)
         if not img.is_cuda:
@@ -116,20 +117,34 @@ class TwoStageDetector(BaseDetector):
             x = self.extract_feat(img)
         losses = dict()
         if self.with_rpn:
+            # with the recorded trunk the RPN loss is one launch that also writes the gradient of
+            # the head outputs into the buffers the RPN backward program reads (no autograd nodes)
+            direct = trunk is not None and trunk.direct_rpn_grads()
             rpn_losses, proposal_list = self.rpn_head.forward_train(
                 x, img_metas, gt_bboxes, gt_labels=None, gt_bboxes_ignore=gt_bboxes_ignore,
                 proposal_cfg=proposal_cfg, rpn_outs=rpn_outs, proposals=pre_proposals,
+                grad_out=trunk.current.gR if direct else None,
                 after_loss=(lambda d: trunk.early_rpn_backward(d, 'side'))
-                if trunk is not None else None)
+                if trunk is not None and not direct else None)
         else:
             proposal_list = proposals
             rpn_losses = {}
+            direct = False
+        # input-only work of the NEXT step (its RPN anchor targets) goes to the side stream now:
+        # the launch thread is about to wait for this step's forward graph in the RoI sampler
+        # anyway, and at the start of the next step nothing then stands between the optimizer
+        # launch and the next forward graph
+        if prefetch_next is not None:
+            self.prefetch(prefetch_next)
         roi_losses = self.roi_head.forward_train(x, img_metas, proposal_list, gt_bboxes, gt_labels,
                                                  gt_bboxes_ignore, gt_masks, **kwargs)
         if trunk is not None and rpn_losses:
             # RPN part of the backward now: GEMM work for the GPU while the launch thread sums the
             # losses and starts the autograd engine (bonai_b200.trunk.Trunk.early_rpn_backward)
-            rpn_losses = trunk.early_rpn_backward(rpn_losses, 'end')
+            if direct:
+                trunk.rpn_backward_direct()
+            else:
+                rpn_losses = trunk.early_rpn_backward(rpn_losses, 'end')
         losses.update(rpn_losses)
         losses.update(roi_losses)
         return losses

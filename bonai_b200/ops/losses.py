@@ -53,6 +53,43 @@ def elem_loss(pred2d, target, weight, mode, scale, col_off=0, ncols=None, beta=1
                            float(scale))
 
 
+class RpnLevel(ctypes.Structure):
+    """Mirror of ``loft_rpn_level_t``."""
+    _fields_ = [('out', ctypes.c_void_p), ('labels', ctypes.c_void_p), ('label_w', ctypes.c_void_p),
+                ('bbox_t', ctypes.c_void_p), ('bbox_w', ctypes.c_void_p), ('grad', ctypes.c_void_p),
+                ('rows', ctypes.c_longlong)]
+
+
+def rpn_loss_fused(outs2d, targets, num_anchors, mode_bbox, beta, cls_scale, bbox_scale,
+                   grads=None):
+    """AnchorHead.loss over all levels in ONE launch (anchor_head.py:382-497).  outs2d: per level
+    the fused head output [rows, ld]; targets: per level (labels, label_weights, bbox_targets,
+    bbox_weights) flat; grads: per level a buffer shaped like the output that receives
+    d(sum of all RPN loss terms)/d(output) in full (the total loss is the plain sum of its terms,
+    detectors/base.py:175-208), or None.  Returns a [2 * n_levels] tensor: per-level cls sums, then
+    per-level bbox sums (already scaled).  No autograd: the caller owns the backward."""
+    n = len(outs2d)
+    ld = outs2d[0].shape[1]
+    arr = (RpnLevel * n)()
+    keep = []
+    for l, (o, (lab, lw, bt, bw)) in enumerate(zip(outs2d, targets)):
+        assert o.is_contiguous() and o.shape[1] == ld
+        ts = [t.contiguous().float() for t in (lab, lw, bt, bw)]
+        keep.append(ts)
+        arr[l].out = o.data_ptr()
+        arr[l].labels, arr[l].label_w, arr[l].bbox_t, arr[l].bbox_w = (t.data_ptr() for t in ts)
+        if grads is not None:
+            assert grads[l].is_contiguous() and grads[l].numel() == o.numel()
+            arr[l].grad = grads[l].data_ptr()
+        else:
+            arr[l].grad = None
+        arr[l].rows = o.shape[0]
+    sums = torch.empty(2 * n, device=outs2d[0].device, dtype=torch.float32)
+    L.call('rpn_loss_fused', arr, i32(n), i32(num_anchors), i32(ld), i32(mode_bbox), L.f32(beta),
+           L.f32(cls_scale), L.f32(bbox_scale), L.ptr(sums), L.stream())
+    return sums
+
+
 class _SoftmaxCE(Function):
     @staticmethod
     def forward(ctx, logits, labels, weight, C, scale):

@@ -444,6 +444,10 @@ class _TrunkFn(Function):
     def backward(ctx, *grads):
         prog, trunk = ctx.prog, ctx.trunk
         trunk.store.queue_finalize()
+        # every gradient that reaches the FPN maps has passed through the RoI heads: their
+        # parameter gradients are final -> a data-parallel trainer starts exchanging them now,
+        # under the ~4.6 ms of trunk backward that follow
+        trunk.store.heads_done()
         n = len(prog.P)
         if not prog.rpn_done:
             # the RPN losses were not back-propagated early: their gradient arrives here
@@ -471,6 +475,7 @@ class Trunk:
         #          (measured: no gain -- that phase's bubbles are many and short);
         #   '0'    inside _TrunkFn.backward, like any other node.
         self.early_rpn = os.environ.get('LOFT_EARLY_RPN', 'end')
+        self.bwd_sm_reserve = 0        # set by a distributed Trainer that overlaps the exchange
         self.current = None
         self.step_ctx = (None, None)
         store.pre_finalize.append(self.flush)
@@ -551,8 +556,19 @@ class Trunk:
             return None
         return prog.proposals
 
+    def direct_rpn_grads(self):
+        """True when the RPN loss may write its gradient straight into the RPN backward program's
+        input buffers (training step in flight, default scheduling of the RPN backward)."""
+        return self.current is not None and torch.is_grad_enabled() and \
+            self.early_rpn in ('end', 'side') and os.environ.get('LOFT_RPN_DIRECT', '1') != '0'
+
+    def rpn_backward_direct(self):
+        """Launch the RPN part of the backward; prog.gR was filled by the fused RPN loss."""
+        if torch.is_grad_enabled():
+            self.run_rpn_backward(self.current, None, side=False)
+
     def run_rpn_backward(self, prog, grads, side):
-        for buf, g in zip(prog.gR, grads):
+        for buf, g in zip(prog.gR, grads if grads is not None else ()):
             if g is None:
                 buf.zero_()
             else:
@@ -588,9 +604,13 @@ class Trunk:
                 L.call('add', L.ptr(buf), L.ptr(gn), L.ptr(buf), L.ll(buf.numel()), i32(1),
                        L.stream())
         if not prog.bwd_ready:
+            # with a concurrent gradient exchange, leave its CTAs a few SMs (baked into the graph)
+            prev = L.lib().loft_reserve_sms(self.bwd_sm_reserve) if self.bwd_sm_reserve else 0
             prog.build_backward()
             if prog.use_graph:
                 prog.bwd.capture()
+            if self.bwd_sm_reserve:
+                L.lib().loft_reserve_sms(prev)
             # The tapes pin thousands of small Python objects; move them (and everything else
             # built so far) out of the cyclic GC's reach so a generation-2 sweep never stalls the
             # launch thread in the middle of a step.

@@ -25,6 +25,10 @@ typedef struct CUstream_st* cudaStream_t;
 
 const char* loft_last_error(void);
 int loft_abi_version(void);
+/* Leave `n` SMs out of every persistent grid launched from now on (0 = use all): lets a NCCL
+ * all-reduce run beside the trunk backward (mmdet/apis/train.py:75-79, DDP overlap).  Returns the
+ * previous setting.  Grid sizes are baked into captured CUDA graphs at capture time. */
+int loft_reserve_sms(int n);
 
 /* Fused epilogue of the dense kernels.  For pixel p, channel c:
  *   acc = sum_k ...;  if (raw_out) raw_out[p,c] = acc;           (pre-BN conv output)

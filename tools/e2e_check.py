@@ -132,7 +132,9 @@ def run(size=256, n_img=1, num_gt=10, seed=0, force_proposals=True, verbose=True
     oh.get_targets = get_targets_cap
     # observe (not alter) the activations of the FOA head's layers: outputs of its grouped conv /
     # linear launches, for the layer-local (teacher-forced) check of its backward
+    from bonai_b200.engine import get_store
     from bonai_b200.ops import dense as D
+    get_store(model, dev)                    # builds the kernel-side specs (loft_prepare)
     foa_acts = {}
     own = {id(sp): ('conv', i) for i, sp in enumerate(getattr(oh, '_group_specs', None) or [])}
     own.update({id(sp): ('fc', i) for i, sp in enumerate(oh._fc_specs)})
