@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libloft_b200.so')
+LIB_PATH = os.environ.get('LOFT_LIB_PATH') or os.path.join(_HERE, 'libloft_b200.so')   # override: A/B builds
 
 _lib = None
 

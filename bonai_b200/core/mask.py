@@ -59,3 +59,29 @@ def mask_target(pos_proposals_list, pos_assigned_gt_inds_list, gt_masks_list, cf
         m = gm.to_tensor(device=dev) if isinstance(gm, BitmapMasks) else gm.to(dev).to(torch.uint8)
         outs.append(mask_target_sample(m.contiguous(), props, gi, int(size)))
     return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
+
+
+def encode_mask_results(masks):
+    """Run-length encode instance bitmaps on the device -- the packing step of the reference's
+    test loop (mmdet/apis/test.py:53-74 `encode_mask_results` -> pycocotools `mask.encode`, COCO
+    RLE: run lengths over the column-major flattening, starting with a run of zeros).  masks:
+    bool / uint8 tensor [N, H, W] (what FCNMaskHead.get_seg_masks(to_numpy=False) returns).
+    Transitions are found and compacted on the device; ONE device->host copy of the run
+    boundaries replaces the N full-size bitmap copies.  Returns a list of
+    {'size': [H, W], 'counts': [int, ...]} (COCO's uncompressed RLE form)."""
+    N, H, W = masks.shape
+    if N == 0:
+        return []
+    flat = masks.to(torch.uint8).transpose(1, 2).reshape(N, H * W)       # column-major per mask
+    prev = torch.cat([flat.new_zeros((N, 1)), flat[:, :-1]], 1)
+    change = flat != prev                                                # run starts (first: a 1-run)
+    idx = torch.nonzero(change)                                          # sorted by (mask, position)
+    per = torch.bincount(idx[:, 0], minlength=N)
+    pos = idx[:, 1].cpu().tolist()
+    per = per.cpu().tolist()
+    out, o = [], 0
+    for n in range(N):
+        b = [0] + pos[o:o + per[n]] + [H * W]
+        o += per[n]
+        out.append({'size': [H, W], 'counts': [b[i + 1] - b[i] for i in range(len(b) - 1)]})
+    return out

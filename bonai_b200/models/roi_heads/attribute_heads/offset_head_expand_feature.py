@@ -209,9 +209,17 @@ class OffsetHeadExpandFeature(nn.Module):
         return vals * polarity
 
     def get_offsets(self, offset_pred, det_bboxes, scale_factor, rescale, img_shape=[1024, 1024]):
+        """offset_head_expand_feature.py:415-448: fusion of the four branches + decode -- one
+        launch (ops.infer.offset_fusion_decode) when the head has its four rotations."""
         if offset_pred is not None:
-            offset_pred = self.offset_fusion(offset_pred)
-            offsets = self.offset_coder.decode(det_bboxes, offset_pred, max_shape=img_shape)
+            if self.expand_feature_num == 4 and offset_pred.is_cuda and \
+                    all(float(m) == 0.0 for m in self.offset_coder.means):
+                from ....ops.infer import offset_fusion_decode
+                pred = offset_pred if offset_pred.stride(1) == 1 else offset_pred.contiguous()
+                offsets = offset_fusion_decode(pred, det_bboxes, self.offset_coder.stds, img_shape)
+            else:
+                offset_pred = self.offset_fusion(offset_pred)
+                offsets = self.offset_coder.decode(det_bboxes, offset_pred, max_shape=img_shape)
         else:
             offsets = torch.zeros((det_bboxes.size()[0], self.reg_num))
         if isinstance(offsets, torch.Tensor):

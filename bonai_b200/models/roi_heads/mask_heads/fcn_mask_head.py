@@ -7,7 +7,6 @@ import ctypes
 import numpy as np
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 from torch.nn.modules.utils import _pair
 
 from ..builder_alias import HEADS, build_loss
@@ -19,8 +18,6 @@ from ....ops import dense as D
 from ....ops import losses as K
 
 i32 = ctypes.c_int
-BYTES_PER_FLOAT = 4
-GPU_MEM_LIMIT = 1024 ** 3
 
 
 @HEADS.register_module()
@@ -151,77 +148,41 @@ class FCNMaskHead(nn.Module):
         return loss
 
     def get_seg_masks(self, mask_pred, det_bboxes, det_labels, rcnn_test_cfg, ori_shape,
-                      scale_factor, rescale):
-        """fcn_mask_head.py:151-237 (test-time paste; torch ops, not on the training hot path)."""
-        if isinstance(mask_pred, torch.Tensor):
-            mask_pred = mask_pred.sigmoid()
-        else:
+                      scale_factor, rescale, to_numpy=True):
+        """Test-time mask paste with the interface of the reference's FCNMaskHead.get_seg_masks
+        (fcn_mask_head.py:151-237): `cls_segms[label]` = list of [img_h, img_w] bitmaps, one per
+        detection.  The work is one zero-fill and one launch of the paste kernel
+        (ops.infer.paste_masks: only each detection's box window is resampled), then ONE
+        device->host copy; `to_numpy=False` keeps the [N, img_h, img_w] bitmaps on the device
+        (returned as the third element of a (cls_segms, labels, masks) tuple)."""
+        from ....ops.infer import paste_masks
+        if not isinstance(mask_pred, torch.Tensor):
             mask_pred = det_bboxes.new_tensor(mask_pred)
-        device = mask_pred.device
-        cls_segms = [[] for _ in range(self.num_classes)]
-        bboxes = det_bboxes[:, :4]
-        labels = det_labels
         if rescale:
-            img_h, img_w = ori_shape[:2]
+            img_h, img_w = (int(v) for v in ori_shape[:2])
         else:
-            # plain ints: numpy >= 2 keeps `N * np.int32 * np.int32` in int32, which overflows for
-            # N >= 512 detections at 1024^2 (the reference ran on numpy 1.x value-based casting)
             img_h = int(np.round(ori_shape[0] * scale_factor))
             img_w = int(np.round(ori_shape[1] * scale_factor))
             scale_factor = 1.0
         if not isinstance(scale_factor, (float, torch.Tensor)):
-            scale_factor = bboxes.new_tensor(scale_factor)
-        bboxes = bboxes / scale_factor
-        N = len(mask_pred)
-        if device.type == 'cpu':
-            num_chunks = N
+            scale_factor = det_bboxes.new_tensor(scale_factor)
+        bboxes = det_bboxes[:, :4] / scale_factor
+        N = mask_pred.shape[0]
+        fused = getattr(mask_pred, '_loft_fused', None)
+        if (self.class_agnostic or self._n_out == 1) and fused is not None:
+            # channel 0 of the fused [N, 4, M, M] head output (NHWC storage): pixel stride 4
+            logits = fused.permute(0, 2, 3, 1)[..., 0]
+        elif self.class_agnostic:
+            logits = mask_pred[:, 0]
         else:
-            num_chunks = int(np.ceil(N * img_h * img_w * BYTES_PER_FLOAT / GPU_MEM_LIMIT))
-            assert num_chunks <= N, 'Default GPU_MEM_LIMIT is too small; try increasing it'
-        chunks = torch.chunk(torch.arange(N, device=device), num_chunks) if N > 0 else []
-        threshold = rcnn_test_cfg.mask_thr_binary
-        im_mask = torch.zeros(N, img_h, img_w, device=device,
-                              dtype=torch.bool if threshold >= 0 else torch.uint8)
-        if not self.class_agnostic:
-            mask_pred = mask_pred[range(N), labels][:, None]
-        for inds in chunks:
-            masks_chunk, spatial_inds = _do_paste_mask(mask_pred[inds], bboxes[inds], img_h, img_w,
-                                                       skip_empty=device.type == 'cpu')
-            if threshold >= 0:
-                masks_chunk = (masks_chunk >= threshold).to(dtype=torch.bool)
-            else:
-                masks_chunk = (masks_chunk * 255).to(dtype=torch.uint8)
-            im_mask[(inds,) + spatial_inds] = masks_chunk
-        for i in range(N):
-            cls_segms[labels[i]].append(im_mask[i].cpu().numpy())
+            logits = mask_pred[torch.arange(N, device=mask_pred.device), det_labels]
+        if logits.stride(1) != logits.shape[2] * logits.stride(2):
+            logits = logits.contiguous()
+        masks = paste_masks(logits, bboxes, img_h, img_w, float(rcnn_test_cfg.mask_thr_binary))
+        cls_segms = [[] for _ in range(self.num_classes)]
+        if not to_numpy:
+            return cls_segms, det_labels, masks
+        host = masks.cpu().numpy()
+        for i, lab in enumerate(det_labels.tolist()):
+            cls_segms[lab].append(host[i])
         return cls_segms
-
-
-def _do_paste_mask(masks, boxes, img_h, img_w, skip_empty=True):
-    """fcn_mask_head.py:240-308."""
-    device = masks.device
-    if skip_empty:
-        x0_int, y0_int = torch.clamp(boxes.min(dim=0).values.floor()[:2] - 1, min=0).to(
-            dtype=torch.int32)
-        x1_int = torch.clamp(boxes[:, 2].max().ceil() + 1, max=img_w).to(dtype=torch.int32)
-        y1_int = torch.clamp(boxes[:, 3].max().ceil() + 1, max=img_h).to(dtype=torch.int32)
-    else:
-        x0_int, y0_int = 0, 0
-        x1_int, y1_int = img_w, img_h
-    x0, y0, x1, y1 = torch.split(boxes, 1, dim=1)
-    N = masks.shape[0]
-    img_y = torch.arange(y0_int, y1_int, device=device, dtype=torch.float32) + 0.5
-    img_x = torch.arange(x0_int, x1_int, device=device, dtype=torch.float32) + 0.5
-    img_y = (img_y - y0) / (y1 - y0) * 2 - 1
-    img_x = (img_x - x0) / (x1 - x0) * 2 - 1
-    if torch.isinf(img_x).any():
-        img_x[torch.where(torch.isinf(img_x))] = 0
-    if torch.isinf(img_y).any():
-        img_y[torch.where(torch.isinf(img_y))] = 0
-    gx = img_x[:, None, :].expand(N, img_y.size(1), img_x.size(1))
-    gy = img_y[:, :, None].expand(N, img_y.size(1), img_x.size(1))
-    grid = torch.stack([gx, gy], dim=3)
-    img_masks = F.grid_sample(masks.to(dtype=torch.float32), grid, align_corners=False)
-    if skip_empty:
-        return img_masks[:, 0], (slice(y0_int, y1_int), slice(x0_int, x1_int))
-    return img_masks[:, 0], ()

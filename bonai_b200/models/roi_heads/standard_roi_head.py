@@ -237,7 +237,7 @@ class StandardRoIHead(BaseRoIHead):
         _bboxes = det_bboxes[:, :4] * scale_factor if rescale else det_bboxes
         mask_rois = bbox2roi([_bboxes])
         mask_results = self._mask_forward(x, mask_rois)
-        return self.mask_head.get_seg_masks(mask_results['mask_pred'].contiguous(), _bboxes,
+        return self.mask_head.get_seg_masks(mask_results['mask_pred'], _bboxes,
                                             det_labels, self.test_cfg, ori_shape, scale_factor,
                                             rescale)
 

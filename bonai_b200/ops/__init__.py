@@ -7,6 +7,7 @@ import torch.nn as nn
 from .roi import RoIAlign, roi_align, multilevel_roi_align, mask_target_sample
 from .nms import nms, batched_nms, nms_sorted, nms_segmented, soft_nms
 from .focal import sigmoid_focal_loss
+from .infer import paste_masks, offset_fusion_decode
 
 Conv2d = nn.Conv2d            # parameter containers; their math runs through ops.dense
 ConvTranspose2d = nn.ConvTranspose2d
@@ -14,5 +15,6 @@ Linear = nn.Linear
 MaxPool2d = nn.MaxPool2d
 
 __all__ = ['RoIAlign', 'roi_align', 'multilevel_roi_align', 'mask_target_sample', 'nms',
-           'batched_nms', 'nms_sorted', 'soft_nms', 'sigmoid_focal_loss', 'Conv2d', 'ConvTranspose2d',
+           'batched_nms', 'nms_sorted', 'soft_nms', 'sigmoid_focal_loss', 'paste_masks',
+           'offset_fusion_decode', 'Conv2d', 'ConvTranspose2d',
            'Linear', 'MaxPool2d']

@@ -187,6 +187,19 @@ int loft_nms_segmented(const float* boxes, const int* seg_off, int L, const long
 int loft_soft_nms_linear(const float* boxes, const float* scores, const long long* idxs, int n,
                          float iou_thr, float min_score, int max_keep, float* dets, long long* keep,
                          int* num_keep, cudaStream_t stream);
+/* test-time mask paste: FCNMaskHead.get_seg_masks + _do_paste_mask (fcn_mask_head.py:151-308).
+ * logits: element (n, i) of the M*M mask of detection n at logits[n*ld_n + i*ld_px]; boxes row n at
+ * boxes + n*ld_box (x0,y0,x1,y1); out: uint8 [N, img_h, img_w], ZERO-FILLED by the caller -- only
+ * each detection's box window is written (thr >= 0: {0,1} = prob >= thr; thr < 0: prob*255). */
+int loft_paste_masks(const float* logits, long long ld_n, int ld_px, const float* boxes, int ld_box,
+                     int N, int M, int img_h, int img_w, float thr, unsigned char* out,
+                     cudaStream_t stream);
+/* OffsetHeadExpandFeature.offset_fusion('max') over the 4 rotated branches (pred rows b*n + i) +
+ * DeltaXYOffsetCoder.decode (offset_head_expand_feature.py:346-448, delta_xy_offset_coder.py:67-88);
+ * max_x <= 0: no clamp.  out [n, 2]. */
+int loft_offset_fusion_decode(const float* pred, int ld, long long n, const float* boxes, int ld_box,
+                              float std_x, float std_y, float max_x, float max_y, float* out,
+                              cudaStream_t stream);
 int loft_bbox_encode(const float* props, const float* gts, long long n, float s0, float s1, float s2,
                      float s3, float* out, cudaStream_t stream);
 int loft_offset_target(const float* props, const float* gt_offsets, const long long* gt_inds,

@@ -194,7 +194,7 @@ def test_abi_exports_every_declared_symbol():
     assert not missing, missing
     assert len(declared) >= 38
     lib.loft_abi_version.restype = ctypes.c_int
-    assert lib.loft_abi_version() == 2
+    assert lib.loft_abi_version() == 3
     # argument validation happens before any CUDA call
     lib.loft_last_error.restype = ctypes.c_char_p
     rc = lib.loft_copy2d(None, ctypes.c_longlong(1), None, ctypes.c_longlong(1),

@@ -21,7 +21,9 @@ from bonai_b200 import Config, _lib as L  # noqa: E402
 from bonai_b200.models import build_detector  # noqa: E402
 
 CFG = os.path.join(ROOT, 'configs', 'loft', 'loft_foa_r50_fpn_2x_b200.py')
-GROUPS = {'roi_align': ('roi_align_fwd',), 'nms': ('nms_sorted', 'soft_nms_linear'),
+GROUPS = {'roi_align': ('roi_align_fwd',),
+          'nms': ('nms_sorted', 'nms_segmented', 'soft_nms_linear', 'rpn_decode'),
+          'mask_paste': ('paste_masks',), 'offset_decode': ('offset_fusion_decode',),
           'dense': ('gemm_fprop', 'conv3x3_fprop', 'conv3x3_fprop_grouped')}
 
 
@@ -71,11 +73,6 @@ def main():
                 'note': 'includes the host-side result packing the reference API mandates '
                         '(numpy bbox/offset arrays, one bool mask per detection)'}
         if args.breakdown:
-            import bonai_b200.ops.dense as D
-            import bonai_b200.ops.roi as R
-            import bonai_b200.ops.nms as N
-            import bonai_b200.ops.misc as M
-            mods = [D.L, R.L, N.L, M.L]
             L.call = timed_call
             events.clear()
             model.simple_test(imgs[0], metas)

@@ -46,6 +46,13 @@ print(f'gaps >= {thr} us: {len(big)} totalling {sum(g[0] for g in big) / 1e3:.3f
 for g in sorted(big, key=lambda g: -g[0])[:40]:
     print(f'{g[0]:8.1f} us at +{g[3] / 1e3:7.3f} ms  after {g[1][:60]:60s} before {g[2][:60]}')
 
+if os.environ.get('LOFT_TIMELINE_LIST'):
+    # every kernel of the step: start (ms since step start), duration (us), gap before it (us)
+    end = step[0][0]
+    for s_, e_, n_ in step:
+        print(f'{(s_ - t0) / 1e3:8.3f} {e_ - s_:8.1f} {max(0.0, s_ - end):7.1f}  {n_[:90]}')
+        end = max(end, e_)
+
 # host side: which ops the launch thread spends its time in (one step)
 cpu = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CPU]
 import collections
