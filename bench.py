@@ -8,8 +8,11 @@ batch 2 per GPU, weak scaling under torchrun).
 
 One JSON line on stdout (rank 0).  `value` = whole-job img/s with inputs resident in HBM; `e2e` =
 the same through the public API with pinned-host inputs copied every step and the loss read back;
-`roofline` = the dominant tcgen05 conv launch (FPN P2 3x3, M=131072 K=2304 N=256) timed alone with
-CUDA events; `cpu_baseline` = the CPU oracle (a port of the reference path) on a bounded sample.
+`roofline` = the launch family with the largest share of the step (the grouped FOA 3x3 convs,
+10 layers x fwd / dgrad / wgrad) timed alone with CUDA events at the step's own number of
+positives, plus the largest single launch (FPN P2 3x3) as `roofline_secondary`; `cpu_baseline` =
+the CPU oracle (a port of the reference path) on a bounded sample.  The timed loop rotates over 8
+distinct batches (different GT counts, hence different numbers of positives).
 """
 import argparse
 import json
@@ -137,9 +140,13 @@ class NvmlClockSampler:
                     reasons=sorted(self.reasons), samples=len(sm), how='nvml')
 
 
-def make_batch(seed, device=None, pinned=False):
-    from oracle import loft_cpu as O           # synthetic-input recipe shared with the oracle
-    img, gb, gl, gm, go = O.make_inputs(seed, BATCH, IMG, NUM_GT)
+N_ROTATE = 8
+GT_SPREAD = (1.0, 0.8, 1.2, 0.9, 1.1, 1.0, 0.875, 1.125)     # x NUM_GT, mean 1.0
+
+
+def make_batch(seed, device=None, pinned=False, num_gt=None):
+    from bonai_b200.datasets import make_inputs
+    img, gb, gl, gm, go = make_inputs(seed, BATCH, IMG, NUM_GT if num_gt is None else num_gt)
     if pinned:
         pin = lambda t: t.contiguous().pin_memory()
         return dict(img=pin(img), gt_bboxes=[pin(b) for b in gb], gt_labels=[pin(l) for l in gl],
@@ -172,44 +179,92 @@ def h2d(batch, device):
     return out, nb
 
 
-def roofline_probe(model, device, pk):
-    """Dominant kernel: loft_gemm_tf32_kernel on the FPN P2 output conv (3x3, 256->256, 2x256x256
-    pixels).  Algorithmic FLOPs = 2*M*K*N; timed alone with CUDA events (input 134 MB > L2)."""
-    import ctypes
-    from bonai_b200 import _lib as L
-    N, H, W, C = BATCH, IMG // 4, IMG // 4, 256
-    x = torch.randn(N, H, W, C, device=device)
-    y = torch.empty(N, H, W, C, device=device)
-    conv = model.neck.fpn_convs[0].conv
-    w, b = conv.weight._loft.w, conv.bias
-    e = L.make_epilogue(shift=b, round_out=True)
-    i32 = ctypes.c_int
-
-    def launch():
-        L.call('conv3x3_fprop', L.ptr(x), L.ptr(w), L.ptr(y), i32(N), i32(H), i32(W), i32(C), i32(C),
-               ctypes.byref(e), L.stream())
-
+def _time(fn, reps=10):
     for _ in range(3):
-        launch()
+        fn()
     torch.cuda.synchronize()
-    reps = 10
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     for _ in range(reps):
-        launch()
+        fn()
     t1.record()
     torch.cuda.synchronize()
-    ms = t0.elapsed_time(t1) / reps
-    flops = 2.0 * N * H * W * (9 * C) * C
-    achieved = flops / (ms * 1e-3) / 1e12
-    return dict(bound='tensor', kernel='loft_gemm_tf32_kernel (FPROP_CONV 131072x2304x256)',
-                achieved=round(achieved, 1), peak=pk['tensor'], unit='TFLOP/s',
-                frac=round(achieved / pk['tensor'], 4),
-                traffic=225.73e6,   # dram read+write bytes/launch, profiles/r01_ncu_gemm_fprop_p2_v6.txt
-                algorithmic_bytes=2 * N * H * W * C * 4 + 9 * C * C * 4,
-                peak_source=f"{pk['source']} bf16 dense burst; TF32 operands run at half that rate",
-                frac_of_tf32_half_peak=round(achieved / (pk['tensor'] / 2), 4),
-                ms_per_launch=round(ms, 4))
+    return t0.elapsed_time(t1) / reps
+
+
+def roofline_probe(model, device, pk, n_pos, ms_per_step):
+    """The launch family with the largest share of the step: loft_gemm_tf32_kernel on the grouped
+    FOA 3x3 convs ([4P,7,7,256] -> 256, the four rotation branches in one launch; 10 layers x
+    fwd / dgrad / wgrad per step), timed alone at the step's own P with CUDA events (working set
+    4P*49*256*4 B x 2 + weights; the step's other 800 launches evict it between uses, here it is
+    L2-resident: an upper bound on the in-step rate).  Algorithmic FLOPs = 2*M*K*N per launch.
+    Second entry: the largest single launch, the FPN P2 3x3 conv (input 134 MB > L2)."""
+    import ctypes
+    from bonai_b200 import _lib as L
+    i32 = ctypes.c_int
+    oh = model.roi_head.offset_head
+    P = max(int(round(n_pos)), 1)
+    G, C, S = 4, 256, 7
+    x = torch.randn(G * P, S, S, C, device=device)
+    y = torch.empty_like(x)
+    dx = torch.empty_like(x)
+    gs = oh._group_specs[1]
+    dw = torch.zeros(G, C, 3, 3, C, device=device)
+    e = L.make_epilogue(shift=gs.b0, relu=True, round_out=True)
+    e2 = L.make_epilogue(round_out=True, mask=x)
+
+    def f():
+        L.call('conv3x3_fprop_grouped', L.ptr(x), L.ptr(gs.w0), L.ptr(y), i32(G * P), i32(S),
+               i32(S), i32(C), i32(C), i32(G), L.ll(gs.w_gstride), L.ll(gs.b_gstride),
+               ctypes.byref(e), L.stream())
+
+    def d():
+        L.call('conv3x3_dgrad_grouped', L.ptr(y), L.ptr(gs.w0), L.ptr(dx), i32(G * P), i32(S),
+               i32(S), i32(C), i32(C), i32(G), L.ll(gs.w_gstride), ctypes.byref(e2), L.stream())
+
+    def w():
+        L.call('conv3x3_wgrad_grouped', L.ptr(y), L.ptr(x), L.ptr(dw), i32(G * P), i32(S), i32(S),
+               i32(C), i32(C), i32(G), L.ll(C * 9 * C), L.stream())
+    tf, td, tw = _time(f), _time(d), _time(w)
+    flops = 2.0 * G * P * S * S * (9 * C) * C
+    n_layers = len(oh._group_specs)
+    family_ms = n_layers * (tf + td + tw)
+    ach = flops / (tf * 1e-3) / 1e12
+    roof = dict(bound='tensor',
+                kernel=f'loft_gemm_tf32_kernel, FOA grouped 3x3 conv fprop ({G * P * S * S}x2304x256 '
+                       f'in 4 groups; P={P} positives)',
+                achieved=round(ach, 1), peak=pk['tensor'], unit='TFLOP/s',
+                frac=round(ach / pk['tensor'], 4),
+                frac_of_tf32_half_peak=round(ach / (pk['tensor'] / 2), 4),
+                ms_per_launch=round(tf, 4),
+                family={'launches_per_step': 3 * n_layers, 'fprop_ms': round(tf, 4),
+                        'dgrad_ms': round(td, 4), 'wgrad_ms': round(tw, 4),
+                        'tflops': [round(flops / (t * 1e-3) / 1e12, 1) for t in (tf, td, tw)]},
+                share_of_step=round(family_ms / ms_per_step, 4),
+                traffic=None,
+                traffic_note='dram bytes of this launch from ncu: profiles/r02_ncu_foa_grouped.txt',
+                algorithmic_bytes=2 * G * P * S * S * C * 4 + G * 9 * C * C * 4,
+                peak_source=f"{pk['source']} bf16 dense burst; TF32 operands run at half that rate")
+    # largest single launch
+    N, H, W = BATCH, IMG // 4, IMG // 4
+    x2 = torch.randn(N, H, W, C, device=device)
+    y2 = torch.empty(N, H, W, C, device=device)
+    conv = model.neck.fpn_convs[0].conv
+    w2, b2 = conv.weight._loft.w, conv.bias
+    e3 = L.make_epilogue(shift=b2, round_out=True)
+    t2 = _time(lambda: L.call('conv3x3_fprop', L.ptr(x2), L.ptr(w2), L.ptr(y2), i32(N), i32(H),
+                              i32(W), i32(C), i32(C), ctypes.byref(e3), L.stream()))
+    fl2 = 2.0 * N * H * W * (9 * C) * C
+    ach2 = fl2 / (t2 * 1e-3) / 1e12
+    second = dict(bound='tensor', kernel='loft_gemm_tf32_kernel (FPROP_CONV 131072x2304x256, FPN P2)',
+                  achieved=round(ach2, 1), peak=pk['tensor'], unit='TFLOP/s',
+                  frac=round(ach2 / pk['tensor'], 4),
+                  frac_of_tf32_half_peak=round(ach2 / (pk['tensor'] / 2), 4),
+                  ms_per_launch=round(t2, 4), share_of_step=round(6 * t2 / ms_per_step, 4),
+                  traffic=225.73e6,
+                  traffic_note='dram read+write bytes/launch, profiles/r01_ncu_gemm_fprop_p2_v6.txt',
+                  algorithmic_bytes=2 * N * H * W * C * 4 + 9 * C * C * 4)
+    return roof, second
 
 
 def cpu_oracle_step(n_img, threads):
@@ -298,11 +353,7 @@ def main():
                     help='GT boxes per tile: 80 = BONAI mean (init-like, P~100/img), 256 = '
                          'steady-state-like (P=256/img), SURVEY 8(d)')
     args = ap.parse_args()
-    # The first ~35 steps of a process see sporadic 50-350 ms stalls (allocator growth while the
-    # number of positives wanders, lazy initialisation in the driver / ATen; measured with
-    # LOFT_STEP_TIMES=1: none after step 40) -- warm up past them; the reported `warmup` is the
-    # number actually run.
-    args.warmup = max(args.warmup, 40) if args.impl != 'reference' else args.warmup
+    args.warmup = max(args.warmup, 3)            # timing rule: W >= 3 (reported as run)
     globals()['NUM_GT'] = args.num_gt
     if args.impl == 'reference':
         return run_reference(args)
@@ -330,16 +381,25 @@ def main():
     torch.manual_seed(100 + rank)
     pk = peaks()
 
-    dev_batch = make_batch(seed=rank, device=device)
-    data = to_model_inputs(dev_batch)
+    # The caching allocator grows while the number of positives wanders from batch to batch; a
+    # cudaMalloc in the middle of a step stalls it for milliseconds.  Like any long-running
+    # trainer, take the pool up front (one allocation, returned to the allocator's cache).
+    trainer.reserve_memory(float(os.environ.get('LOFT_RESERVE_GB', '8')))
+    # a rotating set of distinct batches: different GT counts -> different numbers of positives
+    # (P), RoI-level mixes and allocator request sizes every step, as with real data
+    gts = [max(1, int(round(NUM_GT * f))) for f in GT_SPREAD[:N_ROTATE]]
+    batches = [to_model_inputs(make_batch(seed=rank * 100 + i, device=device, num_gt=gts[i]))
+               for i in range(N_ROTATE)]
 
     def sync_all():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    it = 0
     for _ in range(args.warmup):
-        trainer.train_step(data, prefetch=data)
+        trainer.train_step(batches[it % N_ROTATE], prefetch=batches[(it + 1) % N_ROTATE])
+        it += 1
     sync_all()
     how = os.environ.get('LOFT_CLOCKS', 'nvml')
     clocks = ClockSampler(local) if how == 'smi' else NvmlClockSampler(local)
@@ -347,60 +407,31 @@ def main():
         clocks.start()
     L.LAUNCHES[0] = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    wd = None
-    if os.environ.get('LOFT_WATCHDOG'):
-        # debugging aid: sample every Python thread's stack each 5 ms; after the loop print what
-        # the launch threads were doing during any step that took more than twice the median
-        import collections, traceback
-        wd = dict(samples=[], stop=threading.Event(), host=[])
-
-        def _sample():
-            me = threading.get_ident()
-            while not wd['stop'].is_set():
-                t = time.perf_counter()
-                for tid, fr in sys._current_frames().items():
-                    if tid != me:
-                        st = traceback.extract_stack(fr)[-4:]
-                        wd['samples'].append((t, tid, ' < '.join(
-                            f'{os.path.basename(f.filename)}:{f.lineno}:{f.name}' for f in reversed(st))))
-                time.sleep(0.005)
-        threading.Thread(target=_sample, daemon=True).start()
     e0.record()
-    marks = []
+    marks, n_pos_sum = [], 0
     for _ in range(args.steps):
-        trainer.train_step(data, prefetch=data)      # a training loop knows its next batch
-        if wd is not None:
-            wd['host'].append(time.perf_counter())
-        if os.environ.get('LOFT_STEP_TIMES'):
-            ev = torch.cuda.Event(enable_timing=True)
-            ev.record()
-            marks.append(ev)
+        # a training loop knows its next batch
+        trainer.train_step(batches[it % N_ROTATE], prefetch=batches[(it + 1) % N_ROTATE])
+        it += 1
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        marks.append(ev)
+        # host-side shapes only (no sync): positives sampled this step
+        n_pos_sum += sum(s.pos_bboxes.shape[0] for s in model.roi_head._last_sampling_results)
     e1.record()
     sync_all()
-    if wd is not None:
-        wd['stop'].set()
-        hs = wd['host']
-        d = [b - a for a, b in zip(hs[:-1], hs[1:])]
-        med = sorted(d)[len(d) // 2] if d else 0
-        for i, dt in enumerate(d):
-            if dt > 2 * med:
-                c = collections.Counter(s for t, tid, s in wd['samples'] if hs[i] <= t <= hs[i + 1])
-                print(f'[rank {rank}] slow step {i + 1}: host {dt * 1e3:.1f} ms (median {med * 1e3:.1f}); '
-                      f'top stacks:', file=sys.stderr)
-                for s, n in c.most_common(6):
-                    print(f'    {n:4d}  {s}', file=sys.stderr)
-    if marks and rank == 0:
-        ts = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
-        print('per-step ms: ' + ' '.join(f'{t:.1f}' for t in ts), file=sys.stderr)
+    step_ms = sorted(a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks))
+    if os.environ.get('LOFT_STEP_TIMES') and rank == 0:
+        print('per-step ms (sorted): ' + ' '.join(f'{t:.1f}' for t in step_ms), file=sys.stderr)
     launches = L.LAUNCHES[0]
     ms = e0.elapsed_time(e1)
     if getattr(trainer, '_comm_events', None):
         ts = [a.elapsed_time(b) for a, b in trainer._comm_events[-args.steps:]]
-        print(f'[rank {rank}] grad all-reduce ms/step: mean {sum(ts) / len(ts):.3f} min {min(ts):.3f} '
-              f'max {max(ts):.3f}; step {ms / args.steps:.3f}', file=sys.stderr)
+        print(f'[rank {rank}] exposed grad exchange ms/step: mean {sum(ts) / len(ts):.3f} min '
+              f'{min(ts):.3f} max {max(ts):.3f}; step {ms / args.steps:.3f}', file=sys.stderr)
     clk = clocks.stop() if (rank == 0 and how != 'off') else None
     logs = trainer.read_logs()
-    n_pos = sum(s.pos_bboxes.shape[0] for s in model.roi_head._last_sampling_results)
+    n_pos = n_pos_sum / args.steps                      # positives per step (both tiles)
     t = torch.tensor([ms], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -415,33 +446,28 @@ def main():
         return
     # ---- end to end: pinned host inputs copied every step (on the trainer's copy stream, the way
     # a prefetching loader feeds it) and the loss vector read back every step
-    host_batch = to_model_inputs(make_batch(seed=rank, pinned=True))
-    cur = trainer.stage(host_batch)
-    for _ in range(5):                          # first use of the staging path (pinned copies,
-        nxt = trainer.stage(host_batch)         # events, log buffers)
+    host_batches = [to_model_inputs(make_batch(seed=rank * 100 + i, pinned=True, num_gt=gts[i]))
+                    for i in range(N_ROTATE)]
+    cur = trainer.stage(host_batches[0])
+    for j in range(3):                          # first use of the staging path (pinned copies,
+        nxt = trainer.stage(host_batches[(j + 1) % N_ROTATE])    # events, log buffers)
         trainer.train_step(cur, read_logs='async', prefetch=nxt)
         cur = nxt
     trainer.flush_logs()
-    h2d_bytes = trainer.staged_bytes
     sync_all()
-    cur = trainer.stage(host_batch)
+    cur = trainer.stage(host_batches[0])
+    h2d_total = trainer.staged_bytes
     torch.cuda.synchronize()
     e0.record()
-    marks = []
-    for _ in range(args.steps):
-        nxt = trainer.stage(host_batch)          # next batch's copies overlap this step
+    for j in range(args.steps):
+        nxt = trainer.stage(host_batches[(j + 1) % N_ROTATE])    # next batch's copies overlap
+        h2d_total += trainer.staged_bytes if j + 1 < args.steps else 0
         trainer.train_step(cur, read_logs='async', prefetch=nxt)   # D2H of every step's loss
         cur = nxt                                # vector, read one step late
-        if os.environ.get('LOFT_STEP_TIMES'):
-            ev = torch.cuda.Event(enable_timing=True)
-            ev.record()
-            marks.append(ev)
     out = trainer.flush_logs()                   # the last step's losses, inside the timed region
     e1.record()
     sync_all()
-    if marks and rank == 0:
-        ts = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
-        print('e2e per-step ms: ' + ' '.join(f'{t:.1f}' for t in ts), file=sys.stderr)
+    h2d_bytes = h2d_total // args.steps
     t = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -450,7 +476,7 @@ def main():
 
     if rank != 0:
         return
-    roof = roofline_probe(model, device, pk)
+    roof, roof2 = roofline_probe(model, device, pk, n_pos / 2, ms / args.steps)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
@@ -461,6 +487,7 @@ def main():
                'sample': f'1 tile of 1024x1024 (G={NUM_GT}), fwd+bwd+SGD on the CPU oracle, 1 warm-up '
                          f'+ 1 timed step ({sec:.1f} s)'}
     flops_img = 1.114e12 + 1024 * 83.4e6 + (n_pos / BATCH) * 10.35e9
+    pct = lambda q: round(step_ms[min(len(step_ms) - 1, int(q * len(step_ms)))], 3)
     line = {
         'metric': METRIC, 'value': round(value, 3), 'unit': 'img/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(ms / args.steps, 3),
@@ -469,11 +496,22 @@ def main():
         'config': {'workload': 'LOFT offset_rcnn R50-FPN 2x, 1024x1024, batch 2/GPU, training '
                                '(fwd+bwd+clip+SGD)', 'global_batch': BATCH * world,
                    'num_gt_per_img': NUM_GT, 'rois_per_img': 1024,
-                   'positives_per_img': n_pos / BATCH, 'parallelism': f'dp{world}',
+                   'batches': f'{N_ROTATE} distinct batches in rotation, GT per tile '
+                              f'{min(gts)}..{max(gts)} (mean {sum(gts) / len(gts):.0f})',
+                   'positives_per_img': round(n_pos / BATCH, 1), 'parallelism': f'dp{world}',
                    'l2_policy': 'per-step working set (>3 GB of activations) exceeds the 126 MB L2',
                    'algorithmic_tflop_per_img': round(flops_img / 1e12, 3),
                    'achieved_tflops': round(flops_img * value / 1e12, 1)},
+        'step_ms': {'p50': pct(0.5), 'p90': pct(0.9), 'p99': pct(0.99), 'max': round(step_ms[-1], 3),
+                    'min': round(step_ms[0], 3)},
         'roofline': roof,
+        'roofline_secondary': roof2,
+        'gemm_frac_step': {'achieved_tflops': round(flops_img * value / 1e12, 1),
+                           'frac_of_tf32_half_peak_sustained': round(
+                               flops_img * value / 1e12 / (pk['tensor_sustained'] / 2), 4),
+                           'note': 'algorithmic FLOPs of the WHOLE step (SURVEY 8d formula at the '
+                                   'measured P) / step time: dense and non-dense launches, idle '
+                                   'gaps included'},
         'cpu_baseline': cpu,
         'e2e': {'value': round(e2e_value, 3), 'unit': 'img/s', 'h2d_bytes_per_step': h2d_bytes,
                 'd2h_bytes_per_step': 4 * len(out), 'ms_per_step': round(e2e_ms / args.steps, 3),

@@ -165,7 +165,11 @@ class Trainer:
         self._head_works = []
         if self.overlap:
             self.store.heads_done_hooks.append(self._exchange_heads)
+            # the collective runs beside the trunk backward's persistent GEMM grids: cap its CTAs
+            # and leave it as many SMs (read by NCCL when the communicator is created, i.e. at
+            # the first collective below)
             self._sm_reserve = int(os.environ.get('LOFT_COMM_SMS', '8'))
+            os.environ.setdefault('NCCL_MAX_CTAS', str(self._sm_reserve))
         if self.distributed:
             self.sync_replicas()
 
@@ -205,6 +209,16 @@ class Trainer:
             self._head_works = []
         else:
             allreduce_flat(st.G, bucket_bytes=self.bucket_bytes)
+
+    def reserve_memory(self, gigabytes):
+        """Grow the caching allocator's pool once, up front: one block of `gigabytes` is allocated
+        and released to the cache, from which the per-step temporaries (whose sizes follow the
+        number of positives) are then carved without a cudaMalloc in the middle of a step."""
+        if gigabytes and gigabytes > 0:
+            free, _ = torch.cuda.mem_get_info(self.store.device)
+            n = int(min(gigabytes * (1 << 30), free * 0.5))
+            blk = torch.empty(n, dtype=torch.uint8, device=self.store.device)
+            del blk
 
     def set_epoch(self, epoch):
         self.epoch = int(epoch)

@@ -150,6 +150,18 @@ class TwoStageDetector(BaseDetector):
         return losses
 
     @torch.no_grad()
+    def simple_test_batch(self, img, img_metas, max_dets=None):
+        """Batched test-time forward with device-resident results (see
+        LoftRoIHead.simple_test_batch): img [B,3,H,W], one meta per tile."""
+        store = get_store(self, img.device if img.is_cuda else None)
+        store.refresh_weights()
+        if not img.is_cuda:
+            img = img.to(store.device, non_blocking=True)
+        x = self.extract_feat(img)
+        proposal_list = self.rpn_head.simple_test_rpn(x, img_metas)
+        return self.roi_head.simple_test_batch(x, proposal_list, img_metas, max_dets=max_dets)
+
+    @torch.no_grad()
     def simple_test(self, img, img_metas, proposals=None, rescale=False):
         """TwoStageDetector.simple_test (two_stage.py:187-199)."""
         assert self.with_bbox, 'Bbox head must be implemented.'

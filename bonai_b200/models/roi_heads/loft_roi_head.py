@@ -76,6 +76,60 @@ class LoftRoIHead(StandardRoIHead):
         offset_pred = self.offset_head(offset_feats)
         return dict(offset_pred=offset_pred, offset_feats=offset_feats)
 
+    # ------------------------------------------------------------------ batched device inference
+    @torch.no_grad()
+    def simple_test_batch(self, x, proposal_list, img_metas, max_dets=None):
+        """Test-time RoI stage for a BATCH of tiles with every result left on the device: the
+        per-image steps of LoftRoIHead.simple_test (loft_roi_head.py:196-227, test_mixins.py:53-72,
+        152-177, 211-241) with the dense work batched across images -- one RoIAlign + bbox-head
+        pass over all proposals, one mask-head and one FOA pass over all detections -- and only the
+        per-image pieces (soft-NMS, mask paste) in a loop.  rescale=False semantics (scale 1).
+        Returns per image (dets [k,5], labels [k], masks bool [k,H,W], offsets [k,2])."""
+        from ...ops.infer import offset_fusion_decode, paste_masks
+        cfg = self.test_cfg
+        n_img = len(img_metas)
+        rois = bbox2roi([p[:, :4] for p in proposal_list])
+        bb = self._bbox_forward(x, rois)
+        counts = [p.shape[0] for p in proposal_list]
+        cls_l = bb['cls_score'].split(counts, 0)
+        reg_l = bb['bbox_pred'].split(counts, 0)
+        roi_l = rois.split(counts, 0)
+        dets, labels = [], []
+        for i in range(n_img):
+            d, l = self.bbox_head.get_bboxes(roi_l[i], cls_l[i].contiguous(), reg_l[i].contiguous(),
+                                             img_metas[i]['img_shape'], 1.0, rescale=False, cfg=cfg)
+            if max_dets is not None:
+                d, l = d[:max_dets], l[:max_dets]
+            dets.append(d)
+            labels.append(l)
+        k = [d.shape[0] for d in dets]
+        out = []
+        if sum(k) == 0:
+            for i in range(n_img):
+                h, w = img_metas[i]['img_shape'][:2]
+                out.append((dets[i], labels[i], dets[i].new_zeros((0, h, w), dtype=torch.bool),
+                            dets[i].new_zeros((0, 2))))
+            return out
+        det_rois = bbox2roi([d[:, :4] for d in dets])
+        mask_pred = self._mask_forward(x, det_rois)['mask_pred']
+        off_feats = self.offset_roi_extractor(x[:self.offset_roi_extractor.num_inputs], det_rois)
+        off_pred = self.offset_head(off_feats)                     # [4 * sum k, 2] branch-major
+        fused_m = getattr(mask_pred, '_loft_fused', None)
+        logits = fused_m.permute(0, 2, 3, 1)[..., 0] if fused_m is not None else mask_pred[:, 0]
+        K = sum(k)
+        off4 = off_pred.reshape(4, K, -1)
+        o = 0
+        for i in range(n_img):
+            h, w = img_metas[i]['img_shape'][:2]
+            sl = slice(o, o + k[i])
+            masks = paste_masks(logits[sl], dets[i], h, w, float(cfg.mask_thr_binary))
+            pred_i = off4[:, sl].reshape(4 * k[i], -1)
+            offs = offset_fusion_decode(pred_i.contiguous(), dets[i], self.offset_head.offset_coder.stds,
+                                        [1024, 1024])      # get_offsets' default img_shape
+            out.append((dets[i], labels[i], masks, offs))
+            o += k[i]
+        return out
+
     # ------------------------------------------------------------------ inference
     def simple_test_offset(self, x, img_metas, det_bboxes, det_labels, rescale=False):
         """OffsetTestMixin.simple_test_offset (test_mixins.py:211-241)."""

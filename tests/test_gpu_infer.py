@@ -75,3 +75,35 @@ def test_rle_of_pasted_masks():
             o += c
             v ^= 1
         assert np.array_equal(dec.astype(bool), flat)
+
+
+def test_batched_device_inference_equals_per_tile_api():
+    """model.simple_test_batch (dense work batched over tiles, results on the device) gives what
+    the reference-format simple_test gives tile by tile."""
+    import os
+    from bonai_b200 import Config
+    from bonai_b200.models import build_detector
+    from oracle import loft_cpu as O
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = Config.fromfile(os.path.join(root, 'configs', 'loft', 'loft_foa_r50_fpn_2x_b200.py'))
+    model = build_detector(cfg.model, train_cfg=cfg.train_cfg, test_cfg=cfg.test_cfg)
+    model.load_state_dict(O.randomize_bn(O.init_params(0), 0))
+    model.eval()
+    S = 256
+    g = torch.Generator().manual_seed(0)
+    imgs = torch.randn(2, 3, S, S, generator=g).cuda()
+    meta = dict(img_shape=(S, S, 3), ori_shape=(S, S, 3), pad_shape=(S, S, 3), scale_factor=1.0,
+                flip=False)
+    batch = model.simple_test_batch(imgs, [meta, meta])
+    for i in range(2):
+        bbox_r, segm_r, off_r = model.simple_test(imgs[i:i + 1], [meta])
+        dets, labels, masks, offs = batch[i]
+        want = torch.from_numpy(bbox_r[0])
+        assert dets.shape == want.shape
+        # same proposals / scores up to the batch-size dependence of GEMM tiling (fp32 sums in a
+        # different order): boxes to 1e-3 px, scores to 1e-5
+        assert torch.allclose(dets.cpu(), want, rtol=1e-4, atol=2e-3)
+        assert torch.allclose(offs.cpu(), torch.from_numpy(np.asarray(off_r)), rtol=1e-3, atol=2e-2)
+        host = masks.cpu().numpy()
+        mism = sum(int((host[j] != segm_r[0][j]).sum()) for j in range(len(segm_r[0])))
+        assert mism <= 1e-4 * host.size, mism

@@ -309,3 +309,15 @@ def test_bench_reference_arm_schema(monkeypatch, capsys):
     monkeypatch.setenv('RANK', '1')                     # other ranks exit without work or output
     bench.run_reference(args)
     assert capsys.readouterr().out.strip() == ''
+
+
+def test_synthetic_inputs_equal_the_oracles_recipe():
+    """bonai_b200.datasets.make_inputs (what bench.py feeds the GPU arm) and the oracle's own
+    restatement of the SURVEY 8(d) recipe draw identical batches."""
+    from bonai_b200.datasets import make_inputs
+    from oracle import loft_cpu as O
+    a = make_inputs(3, 2, (96, 128), [5, 2])
+    b = O.make_inputs(3, 2, (96, 128), [5, 2])
+    assert torch.equal(a[0], b[0])
+    for x, y in zip(a[1:], b[1:]):
+        assert all(torch.equal(u, v) for u, v in zip(x, y))
