@@ -365,6 +365,8 @@ def main():
 
     world = int(os.environ.get('WORLD_SIZE', 1))
     rank, local = 0, 0
+    # stdout carries exactly one JSON line: NCCL's own messages (version banner, INFO) go to stderr
+    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
     if world > 1:
         rank, world = init_dist('nccl')
         local = int(os.environ.get('LOCAL_RANK', rank))
@@ -390,6 +392,11 @@ def main():
     gts = [max(1, int(round(NUM_GT * f))) for f in GT_SPREAD[:N_ROTATE]]
     batches = [to_model_inputs(make_batch(seed=rank * 100 + i, device=device, num_gt=gts[i]))
                for i in range(N_ROTATE)]
+    torch.cuda.synchronize()
+    resident = torch.cuda.Event()
+    resident.record()                      # "this batch is in HBM": what a loader hands over with
+    for b in batches:                      # a staged batch (Trainer.stage) -- lets the next
+        b['ready_event'] = resident        # batch's RPN targets start without waiting for the step
 
     def sync_all():
         if world > 1:
@@ -420,9 +427,15 @@ def main():
         n_pos_sum += sum(s.pos_bboxes.shape[0] for s in model.roi_head._last_sampling_results)
     e1.record()
     sync_all()
-    step_ms = sorted(a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks))
-    if os.environ.get('LOFT_STEP_TIMES') and rank == 0:
-        print('per-step ms (sorted): ' + ' '.join(f'{t:.1f}' for t in step_ms), file=sys.stderr)
+    step_seq = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
+    if os.environ.get('LOFT_STEP_TIMES'):
+        print(f'[rank {rank}] per-step ms in order: ' + ' '.join(f'{t:.1f}' for t in step_seq),
+              file=sys.stderr)
+    step_ms = sorted(step_seq)
+    worst = torch.tensor([step_ms[-1]], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+    worst = float(worst.item())
     launches = L.LAUNCHES[0]
     ms = e0.elapsed_time(e1)
     if getattr(trainer, '_comm_events', None):
@@ -503,7 +516,7 @@ def main():
                    'algorithmic_tflop_per_img': round(flops_img / 1e12, 3),
                    'achieved_tflops': round(flops_img * value / 1e12, 1)},
         'step_ms': {'p50': pct(0.5), 'p90': pct(0.9), 'p99': pct(0.99), 'max': round(step_ms[-1], 3),
-                    'min': round(step_ms[0], 3)},
+                    'min': round(step_ms[0], 3), 'max_over_ranks': round(worst, 3)},
         'roofline': roof,
         'roofline_secondary': roof2,
         'gemm_frac_step': {'achieved_tflops': round(flops_img * value / 1e12, 1),

@@ -169,7 +169,8 @@ class Trainer:
             # and leave it as many SMs (read by NCCL when the communicator is created, i.e. at
             # the first collective below)
             self._sm_reserve = int(os.environ.get('LOFT_COMM_SMS', '8'))
-            os.environ.setdefault('NCCL_MAX_CTAS', str(self._sm_reserve))
+            if os.environ.get('LOFT_COMM_CAP_CTAS', '0') != '0':
+                os.environ.setdefault('NCCL_MAX_CTAS', str(self._sm_reserve))
         if self.distributed:
             self.sync_replicas()
 
@@ -219,6 +220,25 @@ class Trainer:
             n = int(min(gigabytes * (1 << 30), free * 0.5))
             blk = torch.empty(n, dtype=torch.uint8, device=self.store.device)
             del blk
+
+    def _gc_policy(self):
+        """Keep Python's cyclic collector off the launch thread's critical path.  A generation-2
+        sweep over the heap of a built model (hundreds of thousands of objects: modules, recorded
+        launch programs, ctypes argument tuples) takes 10-30 ms, and when it fires in the middle of
+        a step every other rank waits for this one in the gradient exchange.  After the programs
+        are recorded the existing heap is frozen out of the collector's reach, automatic
+        collection is switched off, and the young generations are collected explicitly every 16
+        steps right here -- after the optimizer launch, when the launch thread is ~5 ms ahead of
+        the GPU.  LOFT_GC=auto restores Python's default behaviour."""
+        import gc
+        if os.environ.get('LOFT_GC', 'managed') != 'managed':
+            return
+        if self.iter == 3:
+            gc.collect()
+            gc.freeze()
+            gc.disable()
+        elif self.iter > 3 and self.iter % 16 == 0:
+            gc.collect(1)
 
     def set_epoch(self, epoch):
         self.epoch = int(epoch)
@@ -317,6 +337,7 @@ class Trainer:
         self.store.sgd_step(self.current_lr(), self.momentum, self.weight_decay, self.max_norm,
                             grad_scale=1.0 / self.world)
         self.iter += 1
+        self._gc_policy()
         if self.iters_per_epoch and self.iter % self.iters_per_epoch == 0:
             self.end_epoch()
         if prefetch is not None and not at_fwd and hasattr(model, 'prefetch') and \
