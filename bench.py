@@ -349,12 +349,18 @@ def main():
     ap.add_argument('--impl', default='loft_b200', choices=['loft_b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile', action='store_true', help='timed steps only (for ncu)')
+    ap.add_argument('--backbone', default='r50', choices=['r50', 'hrnet_w32'],
+                    help='r50 = BASELINE configs[1] (the metric); hrnet_w32 = configs[3], the '
+                         'LOFT+FOA heads over HRNetV2p-W32 + HRFPN (multi-branch conv stress)')
     ap.add_argument('--num-gt', type=int, default=80,
                     help='GT boxes per tile: 80 = BONAI mean (init-like, P~100/img), 256 = '
                          'steady-state-like (P=256/img), SURVEY 8(d)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)            # timing rule: W >= 3 (reported as run)
     globals()['NUM_GT'] = args.num_gt
+    if args.backbone == 'hrnet_w32':
+        globals()['CFG'] = os.path.join(ROOT, 'configs', 'loft', 'loft_foa_hrnetv2p_w32_2x_b200.py')
+        globals()['METRIC'] = 'train images/sec LOFT HRNetV2p-W32 1024x1024'
     if args.impl == 'reference':
         return run_reference(args)
 
@@ -506,8 +512,10 @@ def main():
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': round(ms / args.steps, 3),
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'tf32',
         'data': 'synthetic',
-        'config': {'workload': 'LOFT offset_rcnn R50-FPN 2x, 1024x1024, batch 2/GPU, training '
-                               '(fwd+bwd+clip+SGD)', 'global_batch': BATCH * world,
+        'config': {'workload': ('LOFT offset_rcnn R50-FPN 2x' if args.backbone == 'r50'
+                                else 'LOFT+FOA HRNetV2p-W32 HRFPN') +
+                               ', 1024x1024, batch 2/GPU, training (fwd+bwd+clip+SGD)',
+                   'global_batch': BATCH * world,
                    'num_gt_per_img': NUM_GT, 'rois_per_img': 1024,
                    'batches': f'{N_ROTATE} distinct batches in rotation, GT per tile '
                               f'{min(gts)}..{max(gts)} (mean {sum(gts) / len(gts):.0f})',

@@ -337,11 +337,13 @@ class ParamStore:
         for fn in self.pre_finalize:
             fn()
         self.join_wgrad_stream()
-        self._bn_finalize()
+        # packed gradients first: a packed weight may belong to a BN-folded conv (HRNet stem),
+        # whose gamma gradient bn_finalize derives from the un-packed weight gradient
         for pk in self.packed:
             if not pk.scattered:
                 pk.scatter()
                 pk.scattered = True
+        self._bn_finalize()
         for p, g in self._grad_views:
             if g is not None and p.grad is not g:
                 p.grad = g

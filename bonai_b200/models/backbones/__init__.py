@@ -1,3 +1,4 @@
-from .resnet import ResNet, Bottleneck, BasicBlock, ResLayer
+from .resnet import ResNet, Bottleneck, ResLayer
+from .hrnet import HRNet, HRModule, BasicBlock
 
-__all__ = ['ResNet', 'Bottleneck', 'BasicBlock', 'ResLayer']
+__all__ = ['ResNet', 'Bottleneck', 'BasicBlock', 'ResLayer', 'HRNet', 'HRModule']

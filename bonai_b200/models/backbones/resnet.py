@@ -112,11 +112,12 @@ class Bottleneck(nn.Module):
 
 
 class BasicBlock(nn.Module):
+    """ResNet-18/34 are not on the LOFT path (the HRNet stages use backbones/hrnet.BasicBlock)."""
     expansion = 1
 
     def __init__(self, *args, **kwargs):
         super().__init__()
-        raise NotImplementedError('BasicBlock (ResNet-18/34) is not on the LOFT path')
+        raise NotImplementedError('BasicBlock ResNets (depth 18/34) are not on the LOFT path')
 
 
 @BACKBONES.register_module()

@@ -1,3 +1,4 @@
 from .fpn import FPN
+from .hrfpn import HRFPN
 
-__all__ = ['FPN']
+__all__ = ['FPN', 'HRFPN']
