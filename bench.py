@@ -194,8 +194,8 @@ def _time(fn, reps=10):
 
 def roofline_probe(model, device, pk, n_pos, ms_per_step):
     """The launch family with the largest share of the step: loft_gemm_tf32_kernel on the grouped
-    FOA 3x3 convs ([4P,7,7,256] -> 256, the four rotation branches in one launch; 10 layers x
-    fwd / dgrad / wgrad per step), timed alone at the step's own P with CUDA events (working set
+    FOA 3x3 convs ([4P,7,7,256] -> 256, the four rotation branches in one launch, P = positives of
+    both tiles; 10 layers x fwd / dgrad / wgrad per step), timed alone at the step's own P (working set
     4P*49*256*4 B x 2 + weights; the step's other 800 launches evict it between uses, here it is
     L2-resident: an upper bound on the in-step rate).  Algorithmic FLOPs = 2*M*K*N per launch.
     Second entry: the largest single launch, the FPN P2 3x3 conv (input 134 MB > L2)."""
@@ -232,7 +232,7 @@ def roofline_probe(model, device, pk, n_pos, ms_per_step):
     ach = flops / (tf * 1e-3) / 1e12
     roof = dict(bound='tensor',
                 kernel=f'loft_gemm_tf32_kernel, FOA grouped 3x3 conv fprop ({G * P * S * S}x2304x256 '
-                       f'in 4 groups; P={P} positives)',
+                       f'in 4 groups; P={P} positives per step)',
                 achieved=round(ach, 1), peak=pk['tensor'], unit='TFLOP/s',
                 frac=round(ach / pk['tensor'], 4),
                 frac_of_tf32_half_peak=round(ach / (pk['tensor'] / 2), 4),
@@ -495,7 +495,7 @@ def main():
 
     if rank != 0:
         return
-    roof, roof2 = roofline_probe(model, device, pk, n_pos / 2, ms / args.steps)
+    roof, roof2 = roofline_probe(model, device, pk, n_pos, ms / args.steps)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1

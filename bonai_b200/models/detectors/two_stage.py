@@ -1,4 +1,6 @@
 """TwoStageDetector (mmdet/models/detectors/two_stage.py:9-214)."""
+import os
+
 import torch
 import torch.nn as nn
 
@@ -136,13 +138,19 @@ class TwoStageDetector(BaseDetector):
         # launch and the next forward graph
         if prefetch_next is not None:
             self.prefetch(prefetch_next)
+        rpn_bwd_at_sample = direct and os.environ.get('LOFT_RPN_BWD_AT', 'sample') == 'sample' and \
+            hasattr(self.roi_head, 'offset_head')
+        if rpn_bwd_at_sample:
+            kwargs['after_sample'] = trunk.rpn_backward_direct
         roi_losses = self.roi_head.forward_train(x, img_metas, proposal_list, gt_bboxes, gt_labels,
                                                  gt_bboxes_ignore, gt_masks, **kwargs)
         if trunk is not None and rpn_losses:
-            # RPN part of the backward now: GEMM work for the GPU while the launch thread sums the
-            # losses and starts the autograd engine (bonai_b200.trunk.Trunk.early_rpn_backward)
+            # RPN part of the backward: GEMM work for the GPU while the launch thread is busy --
+            # right after the RoI sampler's host sync (default), or here while it sums the losses
+            # and starts the autograd engine (bonai_b200.trunk.Trunk.early_rpn_backward)
             if direct:
-                trunk.rpn_backward_direct()
+                if not rpn_bwd_at_sample:
+                    trunk.rpn_backward_direct()
             else:
                 rpn_losses = trunk.early_rpn_backward(rpn_losses, 'end')
         losses.update(rpn_losses)

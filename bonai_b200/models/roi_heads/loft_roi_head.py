@@ -25,10 +25,15 @@ class LoftRoIHead(StandardRoIHead):
         self.offset_head.init_weights()
 
     def forward_train(self, x, img_metas, proposal_list, gt_bboxes, gt_labels,
-                      gt_bboxes_ignore=None, gt_masks=None, gt_offsets=None):
+                      gt_bboxes_ignore=None, gt_masks=None, gt_offsets=None, after_sample=None):
         sampling_results = self.assign_and_sample(x, img_metas, proposal_list, gt_bboxes, gt_labels,
                                                   gt_bboxes_ignore)
         self._last_sampling_results = sampling_results
+        if after_sample is not None:
+            # the sampler's one host sync has just returned: the GPU is idle and the launch
+            # thread has ~200 small launches ahead of it.  The caller queues independent GPU work
+            # here (the RPN part of the backward, one graph launch, ~1.3 ms) to cover them.
+            after_sample()
         losses = dict()
         if self.with_bbox:
             bbox_results = self._bbox_forward_train(x, sampling_results, gt_bboxes, gt_labels,

@@ -436,6 +436,12 @@ class _TrunkFn(Function):
     def forward(ctx, img, trunk, *params):
         prog = trunk.run_forward(img)
         ctx.prog, ctx.trunk = prog, trunk
+        # Outputs that receive no gradient through autograd (the FPN maps: RoIAlign's backward
+        # accumulates straight into the gradient sinks; the fused RPN maps when the RPN loss wrote
+        # its gradient itself) must arrive as None, not as materialised zero tensors -- per step
+        # those were five zero-fills, five layout copies and five adds over up to 134 MB each
+        # (~0.35 ms, profiles/r02_launch_summary.txt).
+        ctx.set_materialize_grads(False)
         outs = [t.permute(0, 3, 1, 2) for t in prog.P] + \
                [t.permute(0, 3, 1, 2) for t in prog.rpn_out]
         return tuple(outs)
