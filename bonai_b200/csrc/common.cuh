@@ -86,66 +86,66 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
 // mbarrier that receives the complete_tx may live in the peer CTA of the pair (the leader's), given
 // as a shared::cluster address (mapa).
 template <bool Pair>
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uint32_t bar, int c0,
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0,
                                             int c1) {
   if constexpr (Pair)
     asm volatile(
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
-        "[%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+        "[%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
         "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
   else
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, "
-        "{%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+        "{%3, %4}], [%2];" ::"r"(dst),
         "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
 template <bool Pair>
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint32_t bar, int c0,
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0,
                                             int c1, int c2) {
   if constexpr (Pair)
     asm volatile(
         "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
-        "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+        "[%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
         "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
   else
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, "
-        "{%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+        "{%3, %4, %5}], [%2];" ::"r"(dst),
         "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
 template <bool Pair>
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uint32_t bar, int c0,
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0,
                                             int c1, int c2, int c3) {
   if constexpr (Pair)
     asm volatile(
         "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
-        "[%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+        "[%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
         "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
   else
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, "
-        "{%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+        "{%3, %4, %5, %6}], [%2];" ::"r"(dst),
         "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
 template <bool Pair>
-__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uint32_t bar, int c0,
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0,
                                             int c1, int c2, int c3, int c4) {
   if constexpr (Pair)
     asm volatile(
         "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
-        "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_u32(dst)),
+        "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
         "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
         : "memory");
   else
     asm volatile(
         "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, "
-        "{%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_u32(dst)),
+        "{%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
         "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
         : "memory");
 }
@@ -250,6 +250,37 @@ __device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t adesc, 
       "}\n" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// Same with the two 64-bit shared-memory descriptors given as (low, high) words, so the issuing
+// loop advances them with 32-bit adds.
+template <bool Pair>
+__device__ __forceinline__ void umma_tf32_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi,
+                                               uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                               uint32_t accumulate) {
+  if constexpr (Pair)
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        "setp.ne.b32 p, %6, 0;\n"
+        "mov.b64 da, {%1, %2};\n"
+        "mov.b64 db, {%3, %4};\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %5, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        "setp.ne.b32 p, %6, 0;\n"
+        "mov.b64 da, {%1, %2};\n"
+        "mov.b64 db, {%3, %4};\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 // ... and its completion signal: arrives on the mbarrier at this shared-memory offset in every
 // CTA of the pair named by `cta_mask`.

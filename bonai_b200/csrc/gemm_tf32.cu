@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "loft_b200.h"
 #include <stdlib.h>
+#include <type_traits>
 
 namespace {
 
@@ -51,7 +52,8 @@ struct GemmParams {
   int kb_per_split;
   int n_mma;  // UMMA N
   int n_half; // B rows (pixels / cin) one CTA stages per k-block: n_mma, or n_mma/2 in pair mode
-  int stages;            // operand pipeline depth (4..8) and bytes per stage, set by launch()
+  int stages;            // operand pipeline depth (barrier slots) and bytes per k-block, set by launch()
+  int kgroup;            // k-blocks per barrier slot (1 or 2): one full / empty round trip per slot
   uint32_t stage_bytes;
   uint32_t tx_bytes;
   uint64_t a_desc, b_desc;  // smem descriptor templates (address field zero)
@@ -91,6 +93,8 @@ struct GemmParams {
   int splits;               // WGRAD: split-K factor per (group, tap, tile)
   int pair;                 // host only: launch the cta_group::2 form (clusters of 2 CTAs)
   unsigned long long* trace;  // debug (loft_debug_set_trace): 8 globaltimer stamps per CTA
+  int dbg_skip;             // debug (LOFT_GEMM_SKIP, results invalid): 1 no A loads, 2 no B loads,
+                            // 4 one MMA per k-block -- attributes the k-loop time
   long long vec_gstride;    // scale / shift stride between groups (floats)
   long long out_gstride;    // WGRAD: dW stride between groups (floats)
 };
@@ -126,7 +130,7 @@ __device__ __forceinline__ void tile_pixel_origin(const GemmParams& p, int ptile
 // the same 128 x 256 x 32 block of MMA work per SM), the leader CTA issues the MMAs for both, and
 // each CTA drains its own 128 TMEM lanes.  Operand delivery (L2 -> SM), not the tensor pipe, is
 // what bounds the 1-CTA form (profiles/r01_ncu_layer4_conv.txt: 33x operand re-fetch).
-template <bool kPair>
+template <bool kPair, int kGroup>
 __global__ void __launch_bounds__(kThreads, 1)
 loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
                       const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
@@ -143,13 +147,18 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
   // pixel column of B): 4 for 256-column tiles, up to 8 for 64-column ones.  Small tiles are
   // bound by the TMA round trip per stage, not by bytes, so depth is what they need (measured:
   // layer4's 3x3 took 51 us whatever the tile width with 4 stages).
+  // Barrier slots hold p.kgroup k-blocks each: the producer and issuer loops are single-warp
+  // dependent chains (try_wait ~90 cycles + address arithmetic + issue: measured ~175 ns per round
+  // trip even with no loads and one MMA, LOFT_GEMM_SKIP=7), so at <= 128 columns, where a
+  // k-block's MMAs take <= 133 ns, one round trip per k-block bounds the k-loop.
   const int n_stages = p.stages;
+  constexpr int kgroup = kGroup;
   const uint32_t stage_bytes = p.stage_bytes;
   int* row_tab = reinterpret_cast<int*>(smem + kStages * kStageBytes + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  unsigned long long* trace = p.trace ? p.trace + 8ull * blockIdx.x : nullptr;
+  unsigned long long* trace = p.trace ? p.trace + 16ull * blockIdx.x : nullptr;
   if (trace && threadIdx.x == 0) trace[0] = gtime();
   // pair mode: rank 0 is the leader (owns the full / tmem-empty barriers, issues the MMAs)
   const uint32_t rank = kPair ? cluster_ctarank() : 0u;
@@ -232,80 +241,114 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
         n0 += gn0;
       }
       const int tdh = tap / 3 - 1, tdw = tap % 3 - 1;  // WGRAD_CONV tap shift
-      // running coordinates of the k-block (no division in the loop):
+      // The k-loop is specialised per mode (one switch per tile, not per k-block): the loop is a
+      // single-warp dependent chain, so an indirect branch and the other modes' counters inside it
+      // are per-k-block latency.  Coordinates are running counters (no division in the loop):
       //   conv fprop / dgrad: k-block = (filter tap (dh, dw), 32-channel chunk ch)
       //   conv wgrad:         k-block = 32-pixel patch (kwi, khi, kni) of the group's images
-      int ch = 0, tp = 0, dh = p.ntaps == 9 ? -1 : 0, dw = p.ntaps == 9 ? -1 : 0;
-      int kwi = 0, khi = 0, kni = 0;
-      if (p.mode == WGRAD_CONV) {
-        kwi = kb_begin % p.tiles_w;
-        const int r = kb_begin / p.tiles_w;
-        khi = r % p.tiles_h;
-        kni = r / p.tiles_h;
-      }
-      for (int kbi = 0; kbi < kb_count; ++kbi) {
-        const int kb = kb_begin + kbi;
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        uint8_t* sa = smem + s * stage_bytes;
-        uint8_t* sb = sa + kABytes;
+      auto k_loop = [&](auto mode_c) {
+        constexpr int kM = decltype(mode_c)::value;
+        int ch = 0, tp = 0, dh = -1, dw = -1;
+        int kwi = 0, khi = 0, kni = 0;
+        if constexpr (kM == WGRAD_CONV) {
+          kwi = kb_begin % p.tiles_w;
+          const int r = kb_begin / p.tiles_w;
+          khi = r % p.tiles_h;
+          kni = r / p.tiles_h;
+        }
+        const uint32_t smem_a0 = smem_u32(smem);
         // pair mode: both CTAs' loads complete on the LEADER's full barrier, which expects the
         // bytes of both (a peer complete_tx that lands before the leader's expect_tx only drives
         // the tx-count negative; the phase cannot complete before the leader's arrival)
-        const uint32_t fb = kPair ? mapa_shared(smem_u32(&full_bar[s]), 0u) : smem_u32(&full_bar[s]);
-        if (elected) {
-          if (!kPair || leader) mbar_expect_tx(&full_bar[s], p.tx_bytes);
-          switch (p.mode) {
-            case FPROP_2D:
-              tma_load_2d<kPair>(sa, &tmap_a, fb, kb * kKB, ct * kBlockC);
-              tma_load_2d<kPair>(sb, &tmap_b, fb, kb * kKB, pt * p.n_half);
-              break;
-            case FPROP_CONV:
-              tma_load_3d<kPair>(sa, &tmap_a, fb, kb * kKB, ct * kBlockC, grp);
-              tma_load_4d<kPair>(sb, &tmap_b, fb, ch * kKB, w0 + dw, h0 + dh, n0);
-              break;
-            case DGRAD_2D:
-              // A view: (32 cin, Cout rows, Cin/32 chunks); k-block = 32 cout rows
-              tma_load_3d<kPair>(sa, &tmap_a, fb, 0, kb * kKB, ct * (kBlockC / 32));
-              tma_load_2d<kPair>(sb, &tmap_b, fb, kb * kKB, pt * p.n_half);
-              break;
-            case DGRAD_CONV:
-              // A view of W[Cout][ntaps*Cin]: chunk index = (tap*Cin + cin0)/32
-              tma_load_4d<kPair>(sa, &tmap_a, fb, 0, ch * kKB,
-                                 tp * (p.tap_stride / 32) + ct * (kBlockC / 32), grp);
-              tma_load_4d<kPair>(sb, &tmap_b, fb, ch * kKB, w0 - dw, h0 - dh, n0);
-              break;
-            case WGRAD_2D:
-              tma_load_3d<kPair>(sa, &tmap_a, fb, 0, kb * kKB, ct * (kBlockC / 32));
-              tma_load_3d<kPair>(sb, &tmap_b, fb, 0, kb * kKB, pt * (p.n_half / 32));
-              break;
-            case WGRAD_CONV: {
-              const int kw0 = kwi * p.tw, kh0 = khi * p.th, kn0 = kni * p.tn + gn0;
-              tma_load_5d<kPair>(sa, &tmap_a, fb, 0, kw0, kh0, kn0, ct * (kBlockC / 32));
-              tma_load_5d<kPair>(sb, &tmap_b, fb, 0, kw0 + tdw, kh0 + tdh, kn0,
-                                 pt * (p.n_half / 32));
-              break;
+        const uint32_t fb0 = kPair ? mapa_shared(smem_u32(&full_bar[0]), 0u) : smem_u32(&full_bar[0]);
+#ifdef LOFT_KTRACE
+        long long kt_wait = 0;
+        const long long kt_begin = clock64();
+#endif
+        for (int kbi = 0; kbi < kb_count; kbi += kgroup) {
+          const int nsub = min(kgroup, kb_count - kbi);
+#ifdef LOFT_KTRACE
+          const long long kt0 = clock64();
+#endif
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+#ifdef LOFT_KTRACE
+          kt_wait += clock64() - kt0;
+#endif
+          const uint32_t fb = fb0 + 8u * (uint32_t)s;
+          if (elected && (!kPair || leader))
+            mbar_expect_tx(&full_bar[s], p.tx_bytes * (uint32_t)nsub);
+#pragma unroll
+          for (int sub = 0; sub < kgroup; ++sub) {
+            if (sub >= nsub) break;
+            const int kb = kb_begin + kbi + sub;
+            const uint32_t sa = smem_a0 + (uint32_t)(s * kgroup + sub) * stage_bytes;
+            const uint32_t sb = sa + kABytes;
+            if (elected) {
+              if constexpr (kM == FPROP_2D) {
+                // (dbg_skip: stage only one operand, or none; launch() reduced tx_bytes to match)
+                if (!(p.dbg_skip & 1)) tma_load_2d<kPair>(sa, &tmap_a, fb, kb * kKB, ct * kBlockC);
+                if (!(p.dbg_skip & 2)) tma_load_2d<kPair>(sb, &tmap_b, fb, kb * kKB, pt * p.n_half);
+              } else if constexpr (kM == FPROP_CONV) {
+                tma_load_3d<kPair>(sa, &tmap_a, fb, kb * kKB, ct * kBlockC, grp);
+                tma_load_4d<kPair>(sb, &tmap_b, fb, ch * kKB, w0 + dw, h0 + dh, n0);
+              } else if constexpr (kM == DGRAD_2D) {
+                // A view: (32 cin, Cout rows, Cin/32 chunks); k-block = 32 cout rows
+                tma_load_3d<kPair>(sa, &tmap_a, fb, 0, kb * kKB, ct * (kBlockC / 32));
+                tma_load_2d<kPair>(sb, &tmap_b, fb, kb * kKB, pt * p.n_half);
+              } else if constexpr (kM == DGRAD_CONV) {
+                // A view of W[Cout][ntaps*Cin]: chunk index = (tap*Cin + cin0)/32
+                tma_load_4d<kPair>(sa, &tmap_a, fb, 0, ch * kKB,
+                                   tp * (p.tap_stride / 32) + ct * (kBlockC / 32), grp);
+                tma_load_4d<kPair>(sb, &tmap_b, fb, ch * kKB, w0 - dw, h0 - dh, n0);
+              } else if constexpr (kM == WGRAD_2D) {
+                tma_load_3d<kPair>(sa, &tmap_a, fb, 0, kb * kKB, ct * (kBlockC / 32));
+                tma_load_3d<kPair>(sb, &tmap_b, fb, 0, kb * kKB, pt * (p.n_half / 32));
+              } else {
+                const int kw0 = kwi * p.tw, kh0 = khi * p.th, kn0 = kni * p.tn + gn0;
+                tma_load_5d<kPair>(sa, &tmap_a, fb, 0, kw0, kh0, kn0, ct * (kBlockC / 32));
+                tma_load_5d<kPair>(sb, &tmap_b, fb, 0, kw0 + tdw, kh0 + tdh, kn0,
+                                   pt * (p.n_half / 32));
+              }
+            }
+            if constexpr (kM == FPROP_CONV || kM == DGRAD_CONV) {
+              if (++ch == p.cchunks) {          // next filter tap
+                ch = 0;
+                ++tp;
+                if (++dw == 2) {
+                  dw = -1;
+                  ++dh;
+                }
+              }
+            }
+            if constexpr (kM == WGRAD_CONV) {
+              if (++kwi == p.tiles_w) {         // next pixel patch
+                kwi = 0;
+                if (++khi == p.tiles_h) {
+                  khi = 0;
+                  ++kni;
+                }
+              }
             }
           }
-        }
-        if (++ch == p.cchunks) {          // next filter tap (conv fprop / dgrad)
-          ch = 0;
-          ++tp;
-          if (++dw == 2) {
-            dw = -1;
-            ++dh;
+          if (++s == n_stages) {
+            s = 0;
+            ph ^= 1u;
           }
         }
-        if (++kwi == p.tiles_w) {         // next pixel patch (conv wgrad)
-          kwi = 0;
-          if (++khi == p.tiles_h) {
-            khi = 0;
-            ++kni;
-          }
+#ifdef LOFT_KTRACE
+        if (trace && tile == tile0 && elected) {   // producer: cycles waiting for a free slot / total
+          trace[10] = (unsigned long long)kt_wait;
+          trace[11] = (unsigned long long)(clock64() - kt_begin);
         }
-        if (++s == n_stages) {
-          s = 0;
-          ph ^= 1u;
-        }
+#endif
+      };
+      switch (p.mode) {
+        case FPROP_2D: k_loop(std::integral_constant<int, FPROP_2D>{}); break;
+        case FPROP_CONV: k_loop(std::integral_constant<int, FPROP_CONV>{}); break;
+        case DGRAD_2D: k_loop(std::integral_constant<int, DGRAD_2D>{}); break;
+        case DGRAD_CONV: k_loop(std::integral_constant<int, DGRAD_CONV>{}); break;
+        case WGRAD_2D: k_loop(std::integral_constant<int, WGRAD_2D>{}); break;
+        default: k_loop(std::integral_constant<int, WGRAD_CONV>{}); break;
       }
     }
   } else if (warp == 1) {
@@ -316,8 +359,11 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
       int s = 0;
       uint32_t ph = 0;
       const uint32_t smem_base = smem_u32(smem);
-      const uint64_t a_desc = p.a_desc, b_desc = p.b_desc;
       const uint32_t a_kstep = p.a_kstep, b_kstep = p.b_kstep, idesc = p.idesc;
+      const uint32_t a_hi = (uint32_t)(p.a_desc >> 32), b_hi = (uint32_t)(p.b_desc >> 32);
+      const uint32_t a_lo0 = (uint32_t)p.a_desc + ((smem_base >> 4) & 0x3FFFu);
+      const uint32_t b_lo0 = (uint32_t)p.b_desc + (((smem_base + kABytes) >> 4) & 0x3FFFu);
+      const uint32_t kb_step = stage_bytes >> 4, slot_step = kb_step * kgroup;
       for (int tile = tile0; tile < p.num_tiles; tile += tile_step, ++lt) {
         int kb_count = p.num_kb;
         if (is_wgrad) {
@@ -328,25 +374,39 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
         mbar_wait(&tempty_bar[as], aph ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * kMaxN;
-        for (int kbi = 0; kbi < kb_count; ++kbi) {
+#ifdef LOFT_KTRACE
+        long long kt_wait = 0;
+        const long long kt_begin = clock64();
+#endif
+        for (int kbi = 0; kbi < kb_count; kbi += kgroup) {
+          const int nsub = min(kgroup, kb_count - kbi);
+#ifdef LOFT_KTRACE
+          const long long kt0 = clock64();
           mbar_wait(&full_bar[s], ph);
+          kt_wait += clock64() - kt0;
+#else
+          mbar_wait(&full_bar[s], ph);
+#endif
           tc_fence_after();
           if (trace && lt == 0 && kbi == 0 && elected) trace[2] = gtime();
-          const uint32_t sa = smem_base + s * stage_bytes;
-          const uint32_t sb = sa + kABytes;
-          const uint64_t ad = a_desc + (uint64_t)((sa >> 4) & 0x3FFFu);
-          const uint64_t bd = b_desc + (uint64_t)((sb >> 4) & 0x3FFFu);
+          // 32-bit descriptor arithmetic: the address field (bits 0-13 of the low word, 16-byte
+          // units) never carries into the LBO field for offsets inside the 192 KB arena
+          const uint32_t a_lo = a_lo0 + (uint32_t)s * slot_step;
+          const uint32_t b_lo = b_lo0 + (uint32_t)s * slot_step;
           if (elected) {
 #pragma unroll
-            for (int ks = 0; ks < kKB / 8; ++ks) {
-              if constexpr (kPair)
-                umma_tf32_pair(tmem_d, ad + (uint64_t)(ks * a_kstep), bd + (uint64_t)(ks * b_kstep),
-                               idesc, (kbi | ks) != 0 ? 1u : 0u);
-              else
-                umma_tf32(tmem_d, ad + (uint64_t)(ks * a_kstep), bd + (uint64_t)(ks * b_kstep),
-                          idesc, (kbi | ks) != 0 ? 1u : 0u);
+            for (int sub = 0; sub < kgroup; ++sub) {
+              if (sub < nsub) {
+#pragma unroll
+                for (int ks = 0; ks < kKB / 8; ++ks) {
+                  if ((p.dbg_skip & 4) && ks > 0) break;
+                  umma_tf32_lohi<kPair>(tmem_d, a_lo + sub * kb_step + ks * a_kstep, a_hi,
+                                        b_lo + sub * kb_step + ks * b_kstep, b_hi, idesc,
+                                        (kbi | sub | ks) != 0 ? 1u : 0u);
+                }
+              }
             }
-            // frees the stage in BOTH CTAs of a pair (the MMA read both shared memories)
+            // frees the slot in BOTH CTAs of a pair (the MMA read both shared memories)
             if constexpr (kPair) umma_commit_pair(&empty_bar[s], 3);
             else umma_commit(&empty_bar[s]);
           }
@@ -359,6 +419,13 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
           if constexpr (kPair) umma_commit_pair(&tfull_bar[as], 3);
           else umma_commit(&tfull_bar[as]);
           if (trace && lt == 0) trace[3] = gtime();
+#ifdef LOFT_KTRACE
+          if (trace && lt == 0) {   // issuer: cycles waiting for operands / total, first tile
+            trace[8] = (unsigned long long)kt_wait;
+            trace[9] = (unsigned long long)(clock64() - kt_begin);
+            trace[12] = (unsigned long long)kb_count;
+          }
+#endif
         }
       }
     }
@@ -771,15 +838,29 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p_in,
       if (max_st < 2) max_st = 2;
       if (max_st > kMaxStages) max_st = kMaxStages;
     }
-    p.stages = st < max_st ? st : max_st;
+    st = st < max_st ? st : max_st;
+    // two k-blocks per barrier slot for tiles of <= 64 columns per CTA (8 stages -> 4 slots), the
+    // only ones whose MMAs (4 x 32 cycles per k-block) are shorter than a single-warp barrier round
+    // trip + issue (~300 cycles): measured per shape (gpurun_out/gemm_shapes_kgroup{1,2}.txt) the
+    // layer4 / P5 / P6 3x3 convs gain 10 %, wider tiles lose 3-8 % (fewer, larger refills).
+    static int kg_env = -1;
+    if (kg_env < 0) {
+      const char* e = getenv("LOFT_KGROUP");
+      kg_env = e ? atoi(e) : 0;
+    }
+    p.kgroup = kg_env > 0 ? (kg_env > 2 ? 2 : kg_env) : (st >= 8 && p.mode < WGRAD_2D ? 2 : 1);
+    if (st / p.kgroup < 2) p.kgroup = 1;
+    p.stages = st / p.kgroup;
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(loft_gemm_tf32_kernel<false>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(loft_gemm_tf32_kernel<true>,
-                               cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t e = cudaSuccess;
+    for (const void* fn : {(const void*)loft_gemm_tf32_kernel<false, 1>,
+                           (const void*)loft_gemm_tf32_kernel<false, 2>,
+                           (const void*)loft_gemm_tf32_kernel<true, 1>,
+                           (const void*)loft_gemm_tf32_kernel<true, 2>})
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) {
       loft_set_error("gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return LOFT_ERR_CUDA;
@@ -788,9 +869,23 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p_in,
   }
   if (p.num_tiles <= 0) return LOFT_OK;
   int grid = p.num_tiles < loft_num_sms() ? p.num_tiles : loft_num_sms();
+  static int dbg_skip = -1, dbg_max_ctas = 0;
+  if (dbg_skip < 0) {
+    const char* e = getenv("LOFT_GEMM_SKIP");
+    dbg_skip = e ? atoi(e) : 0;
+    e = getenv("LOFT_GEMM_MAXCTAS");
+    dbg_max_ctas = e ? atoi(e) : 0;
+  }
+  if (dbg_skip && !p.pair && p.mode == FPROP_2D) {
+    p.dbg_skip = dbg_skip;
+    if (dbg_skip & 1) p.tx_bytes -= kABytes;
+    if (dbg_skip & 2) p.tx_bytes -= (uint32_t)(p.n_half * kKB * 4);
+  }
+  if (dbg_max_ctas > 0 && grid > dbg_max_ctas) grid = dbg_max_ctas;
   if (p.pair) {   // one cluster (CTA pair) per pair tile, at most one per TPC
     const int slots = pair_slots();
     grid = 2 * (p.num_tiles < slots ? p.num_tiles : slots);
+    if (dbg_max_ctas > 0 && grid > dbg_max_ctas) grid = dbg_max_ctas & ~1;
   }
   static int use_pdl = -1;
   if (use_pdl < 0) {
@@ -818,8 +913,13 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p_in,
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  cudaError_t le = p.pair ? cudaLaunchKernelEx(&cfg, loft_gemm_tf32_kernel<true>, ta, tb, p)
-                          : cudaLaunchKernelEx(&cfg, loft_gemm_tf32_kernel<false>, ta, tb, p);
+  cudaError_t le;
+  if (p.pair)
+    le = p.kgroup == 2 ? cudaLaunchKernelEx(&cfg, loft_gemm_tf32_kernel<true, 2>, ta, tb, p)
+                       : cudaLaunchKernelEx(&cfg, loft_gemm_tf32_kernel<true, 1>, ta, tb, p);
+  else
+    le = p.kgroup == 2 ? cudaLaunchKernelEx(&cfg, loft_gemm_tf32_kernel<false, 2>, ta, tb, p)
+                       : cudaLaunchKernelEx(&cfg, loft_gemm_tf32_kernel<false, 1>, ta, tb, p);
   if (le != cudaSuccess) {
     loft_set_error("loft_gemm_tf32_kernel: launch failed: %s", cudaGetErrorString(le));
     return LOFT_ERR_CUDA;
@@ -1049,8 +1149,8 @@ void set_epilogue(GemmParams& p, const loft_epilogue_t* e, float* out, long long
 
 extern "C" {
 
-// Debug: every later GEMM launch writes 8 globaltimer stamps per CTA into `buf` (device memory,
-// >= 8 * 8 * num_SMs bytes; NULL turns it off): kernel entry, operands may be read (after the
+// Debug: every later GEMM launch writes 8 globaltimer stamps per CTA (stride 16 words) into `buf`
+// (device memory, >= 16 * 8 * num_SMs bytes; NULL turns it off): kernel entry, operands may be read (after the
 // programmatic-dependency wait), first stage landed, last MMA of the first tile issued, first
 // accumulator complete, first tile stored, last tile stored, tiles done by the CTA.
 void loft_debug_set_trace(unsigned long long* buf) { g_trace = buf; }

@@ -96,8 +96,9 @@ int loft_conv3x3_wgrad_grouped(const float* dy, const float* x, float* dw, int N
 /* bring-up only: override UMMA descriptor fields (-1 = keep default) */
 void loft_debug_set_desc(long long a_desc, long long b_desc, long long a_kstep, long long b_kstep,
                          long long idesc);
-/* profiling only: 8 globaltimer stamps per CTA of every later GEMM launch into `buf` (device
- * memory, 64 B per CTA; NULL = off) -- tools/gemm_timeline.py */
+/* profiling only: 8 globaltimer stamps (+ k-loop cycle counts in -DLOFT_KTRACE builds) per CTA of
+ * every later GEMM launch into `buf` (device memory, 128 B per CTA; NULL = off) --
+ * tools/gemm_timeline.py */
 void loft_debug_set_trace(unsigned long long* buf);
 
 /* ---- HBM-bound layout / activation / optimizer kernels (elementwise.cu) ------------------------

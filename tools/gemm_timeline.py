@@ -30,6 +30,8 @@ SHAPES = {
     'l4_1x1': ('gemm', (2048, 2048, 512)),
     'fc2': ('gemm', (2048, 1024, 1024)),
     'fc1': ('gemm', (2048, 12544, 1024)),
+    'l3_2d': ('gemm', (8192, 2304, 256)),     # the l3 / l4 3x3 contractions in the 2-D mode
+    'l4_2d': ('gemm', (2048, 4608, 512)),
 }
 
 
@@ -37,7 +39,7 @@ def main():
     names = sys.argv[1:] or list(SHAPES)
     lib = L.lib()
     nsm = torch.cuda.get_device_properties(0).multi_processor_count
-    buf = torch.zeros(8 * 1024 + 4 * 64, dtype=torch.int64, device=dev)
+    buf = torch.zeros(16 * 1024, dtype=torch.int64, device=dev)
     print(f'{"shape":12s} {"ctas":>4s} {"tiles":>5s} | {"wait":>6s} {"1st_ld":>6s} {"mma_t0":>6s} '
           f'{"drain":>6s} {"epi_t0":>6s} {"rest":>7s} | {"total":>7s} {"event":>7s}  (us, median CTA; '
           f'total = first entry -> last store)')
@@ -83,8 +85,7 @@ def main():
         launch()
         torch.cuda.synchronize()
         lib.loft_debug_set_trace(ctypes.c_void_p(0))
-        kt = buf[8 * 1024:].view(64, 4).cpu().double()
-        t = buf[:8 * 1024].view(-1, 8).cpu()
+        t = buf.view(-1, 16).cpu()
         t = t[t[:, 0] > 0].double()
         n_cta = t.shape[0]
         lead = t[t[:, 2] > 0]                   # CTAs that issued MMAs (all, or the pair leaders)
@@ -96,13 +97,11 @@ def main():
               f'{med(t[:, 4] - t[:, 1]) - med(lead[:, 3] - lead[:, 1]):6.2f} '
               f'{med(t[:, 5] - t[:, 4]):6.2f} {med(t[:, 6] - t[:, 5]):7.2f} | {total:7.2f} '
               f'{ev_us:7.2f}  {flops / ev_us / 1e6:6.0f} TF/s')
-        if os.environ.get('LOFT_KTRACE'):
-            t0 = float(t[0, 1])
-            rows = [(k, *((kt[k] - t0) / 1e3).tolist()) for k in range(64) if kt[k, 0] > 0]
-            print('   CTA 0, us since start: k-block | empty acquired | TMA issued | full acquired | '
-                  'MMAs issued')
-            for r in rows[:40]:
-                print('   %3d  %7.2f %7.2f %7.2f %7.2f' % r)
+        if lead[:, 9].max() > 0:   # built with -DLOFT_KTRACE: cycle accounting of the first tile's k-loop
+            kb = float(lead[:, 12].median())
+            print(f'   k-loop cycles per k-block ({int(kb)} k-blocks): issuer total {med(lead[:, 9]) * 1e3 / kb:6.1f} '
+                  f'waiting for operands {med(lead[:, 8]) * 1e3 / kb:6.1f} | producer total '
+                  f'{med(t[:, 11]) * 1e3 / kb:6.1f} waiting for a free slot {med(t[:, 10]) * 1e3 / kb:6.1f}')
 
 
 if __name__ == '__main__':

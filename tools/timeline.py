@@ -46,6 +46,16 @@ print(f'gaps >= {thr} us: {len(big)} totalling {sum(g[0] for g in big) / 1e3:.3f
 for g in sorted(big, key=lambda g: -g[0])[:40]:
     print(f'{g[0]:8.1f} us at +{g[3] / 1e3:7.3f} ms  after {g[1][:60]:60s} before {g[2][:60]}')
 
+# GPU time per kernel name inside the step (warm durations, unlike the serialised ncu launch list)
+import collections as _c
+_agg = _c.defaultdict(lambda: [0, 0.0])
+for s_, e_, n_ in step:
+    _agg[n_][0] += 1
+    _agg[n_][1] += e_ - s_
+print('--- kernels of the step by GPU time (count, ms)')
+for n_, (c_, us_) in sorted(_agg.items(), key=lambda kv: -kv[1][1])[:40]:
+    print(f'{n_[:100]:100s} {c_:5d} {us_ / 1e3:8.3f}')
+
 if os.environ.get('LOFT_TIMELINE_LIST'):
     # every kernel of the step: start (ms since step start), duration (us), gap before it (us)
     end = step[0][0]
