@@ -359,7 +359,7 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
       int s = 0;
       uint32_t ph = 0;
       const uint32_t smem_base = smem_u32(smem);
-      const uint32_t a_kstep = p.a_kstep, b_kstep = p.b_kstep, idesc = p.idesc;
+      const uint32_t idesc = p.idesc;
       const uint32_t a_hi = (uint32_t)(p.a_desc >> 32), b_hi = (uint32_t)(p.b_desc >> 32);
       const uint32_t a_lo0 = (uint32_t)p.a_desc + ((smem_base >> 4) & 0x3FFFu);
       const uint32_t b_lo0 = (uint32_t)p.b_desc + (((smem_base + kABytes) >> 4) & 0x3FFFu);
@@ -378,43 +378,57 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
         long long kt_wait = 0;
         const long long kt_begin = clock64();
 #endif
-        for (int kbi = 0; kbi < kb_count; kbi += kgroup) {
-          const int nsub = min(kgroup, kb_count - kbi);
+        // k-step of the descriptors inside a k-block as compile-time constants (K-major: 32 B,
+        // MN-major: 1024 B, in 16-byte units): the four descriptors of a k-block are then
+        // independent immediate adds instead of a chain fed by constant-bank loads
+        auto k_loop = [&](auto ak_c, auto bk_c) {
+          constexpr uint32_t kAK = decltype(ak_c)::value, kBK = decltype(bk_c)::value;
+          for (int kbi = 0; kbi < kb_count; kbi += kgroup) {
+            const int nsub = min(kgroup, kb_count - kbi);
 #ifdef LOFT_KTRACE
-          const long long kt0 = clock64();
-          mbar_wait(&full_bar[s], ph);
-          kt_wait += clock64() - kt0;
+            const long long kt0 = clock64();
+            mbar_wait(&full_bar[s], ph);
+            kt_wait += clock64() - kt0;
 #else
-          mbar_wait(&full_bar[s], ph);
+            mbar_wait(&full_bar[s], ph);
 #endif
-          tc_fence_after();
-          if (trace && lt == 0 && kbi == 0 && elected) trace[2] = gtime();
-          // 32-bit descriptor arithmetic: the address field (bits 0-13 of the low word, 16-byte
-          // units) never carries into the LBO field for offsets inside the 192 KB arena
-          const uint32_t a_lo = a_lo0 + (uint32_t)s * slot_step;
-          const uint32_t b_lo = b_lo0 + (uint32_t)s * slot_step;
-          if (elected) {
+            tc_fence_after();
+            if (trace && lt == 0 && kbi == 0 && elected) trace[2] = gtime();
+            // 32-bit descriptor arithmetic: the address field (bits 0-13 of the low word, 16-byte
+            // units) never carries into the LBO field for offsets inside the 192 KB arena
+            const uint32_t a_lo = a_lo0 + (uint32_t)s * slot_step;
+            const uint32_t b_lo = b_lo0 + (uint32_t)s * slot_step;
+            if (elected) {
 #pragma unroll
-            for (int sub = 0; sub < kgroup; ++sub) {
-              if (sub < nsub) {
+              for (int sub = 0; sub < kgroup; ++sub) {
+                if (sub < nsub) {
 #pragma unroll
-                for (int ks = 0; ks < kKB / 8; ++ks) {
-                  if ((p.dbg_skip & 4) && ks > 0) break;
-                  umma_tf32_lohi<kPair>(tmem_d, a_lo + sub * kb_step + ks * a_kstep, a_hi,
-                                        b_lo + sub * kb_step + ks * b_kstep, b_hi, idesc,
-                                        (kbi | sub | ks) != 0 ? 1u : 0u);
+                  for (int ks = 0; ks < kKB / 8; ++ks) {
+#ifdef LOFT_KTRACE
+                    if ((p.dbg_skip & 4) && ks > 0) break;
+#endif
+                    umma_tf32_lohi<kPair>(tmem_d, a_lo + sub * kb_step + ks * kAK, a_hi,
+                                          b_lo + sub * kb_step + ks * kBK, b_hi, idesc,
+                                          (kbi | sub | ks) != 0 ? 1u : 0u);
+                  }
                 }
               }
+              // frees the slot in BOTH CTAs of a pair (the MMA read both shared memories)
+              if constexpr (kPair) umma_commit_pair(&empty_bar[s], 3);
+              else umma_commit(&empty_bar[s]);
             }
-            // frees the slot in BOTH CTAs of a pair (the MMA read both shared memories)
-            if constexpr (kPair) umma_commit_pair(&empty_bar[s], 3);
-            else umma_commit(&empty_bar[s]);
+            if (++s == n_stages) {
+              s = 0;
+              ph ^= 1u;
+            }
           }
-          if (++s == n_stages) {
-            s = 0;
-            ph ^= 1u;
-          }
-        }
+        };
+        if (p.mode <= FPROP_CONV)
+          k_loop(std::integral_constant<uint32_t, 2>{}, std::integral_constant<uint32_t, 2>{});
+        else if (p.mode <= DGRAD_CONV)
+          k_loop(std::integral_constant<uint32_t, 64>{}, std::integral_constant<uint32_t, 2>{});
+        else
+          k_loop(std::integral_constant<uint32_t, 64>{}, std::integral_constant<uint32_t, 64>{});
         if (elected) {
           if constexpr (kPair) umma_commit_pair(&tfull_bar[as], 3);
           else umma_commit(&tfull_bar[as]);
@@ -506,12 +520,24 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const unsigned vm = __ballot_sync(0xffffffffu, row >= 0);
         if (lane == 0) s_vmask[et >> 5] = vm;
       }
+      const int c = ct * kBlockC + q * 32 + lane;
+      const bool c_ok = c < p.Cm;
+      // per-channel scale / shift are fetched BEFORE waiting for the accumulator: a dependent
+      // global load after the wait is ~1 us of exposed latency per tile (measured: the epilogue of
+      // a 128-column tile took 2.3 us with neither tensor-memory loads nor stores)
+      const long long vo = (long long)grp * p.vec_gstride;
+      float sc = 1.f, sh = 0.f;
+      if (!is_wgrad && c_ok) {
+        if (p.scale != nullptr) sc = __ldg(p.scale + vo + c);
+        if (p.shift != nullptr) sh = __ldg(p.shift + vo + c);
+      }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
       if (trace && lt == 0 && et == 0) trace[4] = gtime();
-      const int c = ct * kBlockC + q * 32 + lane;
-      const bool c_ok = c < p.Cm;
+#ifdef LOFT_KTRACE
+      const long long ke0 = clock64();
+#endif
       const uint32_t taddr = tmem_base + as * kMaxN + ((uint32_t)(q * 32) << 16);
 
       if (is_wgrad) {
@@ -537,9 +563,6 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
           }
         }
       } else {
-        const long long vo = (long long)grp * p.vec_gstride;
-        const float sc = (p.scale != nullptr && c_ok) ? p.scale[vo + c] : 1.f;
-        const float sh = (p.shift != nullptr && c_ok) ? p.shift[vo + c] : 0.f;
         int ocol = c, row_add = 0;
         if (p.out_map == 1) {
           // deconv 2x2 stride 2: channel index c = (i*2 + j2)*Co + co
@@ -563,6 +586,12 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
         float csum = 0.f;
         for (int cc = half * kCh; cc < p.n_mma; cc += 2 * kCh) {
           float v[kCh];
+#ifdef LOFT_KTRACE
+          if (p.dbg_skip & 16) {    // attribution: no tensor-memory loads
+#pragma unroll
+            for (int j = 0; j < kCh; ++j) v[j] = (float)(cc + j);
+          } else
+#endif
           tmem_ld32(taddr + cc, v);
           if (!c_ok) continue;
           int rows[kCh];
@@ -634,6 +663,15 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
               for (int j = 0; j < kCh; ++j) csum += v[j];
             }
+#ifdef LOFT_KTRACE
+            if (p.dbg_skip & 8) {   // attribution: no global stores (keep v alive with one store)
+              float z = 0.f;
+#pragma unroll
+              for (int j = 0; j < kCh; ++j) z += v[j];
+              if (z == 123.456f) outb[off[0]] = z;
+              continue;
+            }
+#endif
 #pragma unroll
             for (int j = 0; j < kCh; ++j) outb[LOFT_OFF(j)] = v[j];
 #undef LOFT_OFF
@@ -701,6 +739,9 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
         else mbar_arrive_cluster(tempty_remote + as * 8u);
       }
       if (trace && et == 0) {
+#ifdef LOFT_KTRACE
+        if (lt == 0) trace[13] = (unsigned long long)(clock64() - ke0);   // epilogue cycles, warp 2
+#endif
         if (lt == 0) trace[5] = gtime();
         trace[6] = gtime();
         trace[7] = lt + 1;
@@ -876,7 +917,8 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p_in,
     e = getenv("LOFT_GEMM_MAXCTAS");
     dbg_max_ctas = e ? atoi(e) : 0;
   }
-  if (dbg_skip && !p.pair && p.mode == FPROP_2D) {
+  if (dbg_skip & 24) p.dbg_skip = dbg_skip & 24;   // epilogue attribution bits (KTRACE builds)
+  if ((dbg_skip & 7) && !p.pair && p.mode == FPROP_2D) {
     p.dbg_skip = dbg_skip;
     if (dbg_skip & 1) p.tx_bytes -= kABytes;
     if (dbg_skip & 2) p.tx_bytes -= (uint32_t)(p.n_half * kKB * 4);

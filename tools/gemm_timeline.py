@@ -101,7 +101,8 @@ def main():
             kb = float(lead[:, 12].median())
             print(f'   k-loop cycles per k-block ({int(kb)} k-blocks): issuer total {med(lead[:, 9]) * 1e3 / kb:6.1f} '
                   f'waiting for operands {med(lead[:, 8]) * 1e3 / kb:6.1f} | producer total '
-                  f'{med(t[:, 11]) * 1e3 / kb:6.1f} waiting for a free slot {med(t[:, 10]) * 1e3 / kb:6.1f}')
+                  f'{med(t[:, 11]) * 1e3 / kb:6.1f} waiting for a free slot {med(t[:, 10]) * 1e3 / kb:6.1f}'
+                  f' | epilogue of the first tile {med(t[:, 13]) * 1e3:7.0f} cycles')
 
 
 if __name__ == '__main__':
