@@ -241,8 +241,10 @@ def roofline_probe(model, device, pk, n_pos, ms_per_step):
                         'dgrad_ms': round(td, 4), 'wgrad_ms': round(tw, 4),
                         'tflops': [round(flops / (t * 1e-3) / 1e12, 1) for t in (tf, td, tw)]},
                 share_of_step=round(family_ms / ms_per_step, 4),
-                traffic=None,
-                traffic_note='dram bytes of this launch from ncu: profiles/r02_ncu_foa_grouped.txt',
+                traffic=55.84e6,
+                traffic_note='dram__bytes_read.sum + dram__bytes_write.sum of the fprop launch at '
+                             'P=210 (51.68 + 4.16 MB; L2-resident activations), ncu --set full, '
+                             'profiles/r02_ncu_kernels.txt',
                 algorithmic_bytes=2 * G * P * S * S * C * 4 + G * 9 * C * C * 4,
                 peak_source=f"{pk['source']} bf16 dense burst; TF32 operands run at half that rate")
     # largest single launch
@@ -261,8 +263,9 @@ def roofline_probe(model, device, pk, n_pos, ms_per_step):
                   frac=round(ach2 / pk['tensor'], 4),
                   frac_of_tf32_half_peak=round(ach2 / (pk['tensor'] / 2), 4),
                   ms_per_launch=round(t2, 4), share_of_step=round(6 * t2 / ms_per_step, 4),
-                  traffic=225.73e6,
-                  traffic_note='dram read+write bytes/launch, profiles/r01_ncu_gemm_fprop_p2_v6.txt',
+                  traffic=225.2e6,
+                  traffic_note='dram__bytes_read.sum + dram__bytes_write.sum per launch (136.78 + '
+                               '88.42 MB), ncu --set full, profiles/r02_ncu_kernels.txt',
                   algorithmic_bytes=2 * N * H * W * C * 4 + 9 * C * C * 4)
     return roof, second
 
@@ -528,8 +531,9 @@ def main():
         'roofline': roof,
         'roofline_secondary': roof2,
         'gemm_frac_step': {'achieved_tflops': round(flops_img * value / 1e12, 1),
+                           'achieved_tflops_per_gpu': round(flops_img * value / 1e12 / world, 1),
                            'frac_of_tf32_half_peak_sustained': round(
-                               flops_img * value / 1e12 / (pk['tensor_sustained'] / 2), 4),
+                               flops_img * value / 1e12 / world / (pk['tensor_sustained'] / 2), 4),
                            'note': 'algorithmic FLOPs of the WHOLE step (SURVEY 8d formula at the '
                                    'measured P) / step time: dense and non-dense launches, idle '
                                    'gaps included'},
