@@ -103,6 +103,179 @@ __global__ void mask_flip_pad_kernel(const uint8_t* __restrict__ in, uint8_t* __
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Polygon -> bitmap (LoadAnnotations(poly2mask=True), pipelines/loading.py:301-326,345-368: every
+// BONAI building mask is `maskUtils.decode(maskUtils.merge(maskUtils.frPyObjects(polys, h, w)))`).
+// The rasteriser is the one of pycocotools 2.0.x (common/maskApi.c: rleFrPoly / rleMerge /
+// rleDecode), restated so the bitmaps are the reference's bit for bit:
+//   1. vertices are scaled by 5 and rounded ((int)(5*x + .5), C truncation);
+//   2. every edge is walked one unit step along its longer axis (endpoints swapped so the walk
+//      ascends, the slope a double, positions rounded with +.5 and truncation);
+//   3. wherever the upsampled column index changes between consecutive boundary points, the point
+//      is mapped back to pixel units; it is kept only if it lies exactly on a pixel column inside
+//      the image, and becomes the run boundary  a = x*h + ceil(clamp(y, 0, h))  of the
+//      COLUMN-major run-length code;
+//   4. pixel i (column-major) is set iff an odd number of boundaries are <= i; parts are OR-ed.
+// Kernel 1 finds and sorts the run boundaries of one polygon part per block, kernel 2 writes the
+// row-major uint8 bitmap, one thread per image column (a warp stores 32 consecutive bytes of a
+// row; every output byte is written exactly once, zeros included).
+constexpr int kPolyMaxCross = 8192;     // run boundaries per part held (and sorted) in shared memory
+
+__device__ __forceinline__ int poly_up(double c) {      // (int)(scale*c + .5), no FMA contraction
+  return (int)__dadd_rn(__dmul_rn(5.0, c), 0.5);
+}
+
+// boundary point `d` (0..max(dx,dy)) of edge (xs,ys)->(xe,ye) in walk order
+__device__ __forceinline__ void poly_edge_point(int xs, int ys, int xe, int ye, int d, int& u,
+                                                int& v) {
+  const int dx = abs(xe - xs), dy = abs(ys - ye);
+  const bool flip = (dx >= dy && xs > xe) || (dx < dy && ys > ye);
+  if (flip) {
+    int t = xs; xs = xe; xe = t;
+    t = ys; ys = ye; ye = t;
+  }
+  if (dx >= dy) {
+    const double s = dx == 0 ? 0.0 : __ddiv_rn((double)(ye - ys), (double)dx);
+    const int t = flip ? dx - d : d;
+    u = t + xs;
+    v = (int)__dadd_rn(__dadd_rn((double)ys, __dmul_rn(s, (double)t)), 0.5);
+  } else {
+    const double s = __ddiv_rn((double)(xe - xs), (double)dy);
+    const int t = flip ? dy - d : d;
+    v = t + ys;
+    u = (int)__dadd_rn(__dadd_rn((double)xs, __dmul_rn(s, (double)t)), 0.5);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+poly_cross_kernel(const double* __restrict__ xy, const long long* __restrict__ part_off, int h, int w,
+                  long long* __restrict__ edge_off,      // [total vertices + parts] scratch
+                  unsigned* __restrict__ cross,          // [parts][kPolyMaxCross] sorted boundaries
+                  int* __restrict__ cross_n,             // [parts]
+                  int* __restrict__ err) {
+  __shared__ unsigned s_a[kPolyMaxCross];
+  __shared__ int s_n;
+  __shared__ long long s_m;
+  const int part = blockIdx.x;
+  const long long v0 = part_off[part];
+  const int k = (int)(part_off[part + 1] - v0);
+  const double* p = xy + 2 * v0;
+  long long* eoff = edge_off + v0 + part;                 // k + 1 entries
+  if (threadIdx.x == 0) {
+    s_n = 0;
+    long long m = 0;                                       // dense boundary points before edge j
+    for (int j = 0; j < k; ++j) {
+      const int jn = j + 1 == k ? 0 : j + 1;
+      const int dx = abs(poly_up(p[2 * j]) - poly_up(p[2 * jn]));
+      const int dy = abs(poly_up(p[2 * j + 1]) - poly_up(p[2 * jn + 1]));
+      eoff[j] = m;
+      m += (dx > dy ? dx : dy) + 1;
+    }
+    eoff[k] = m;
+    s_m = m;
+  }
+  __syncthreads();
+  const long long m = s_m;
+  for (long long j = 1 + threadIdx.x; j < m; j += blockDim.x) {
+    // edge of point j: last e with eoff[e] <= j
+    int lo = 0, hi = k - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (eoff[mid] <= j) lo = mid; else hi = mid - 1;
+    }
+    const int e = lo, en = e + 1 == k ? 0 : e + 1;
+    const int d = (int)(j - eoff[e]);
+    int u, v, up, vp;
+    poly_edge_point(poly_up(p[2 * e]), poly_up(p[2 * e + 1]), poly_up(p[2 * en]),
+                    poly_up(p[2 * en + 1]), d, u, v);
+    if (d > 0) {
+      poly_edge_point(poly_up(p[2 * e]), poly_up(p[2 * e + 1]), poly_up(p[2 * en]),
+                      poly_up(p[2 * en + 1]), d - 1, up, vp);
+    } else {                                               // last point of the previous edge
+      const int ep = e - 1;
+      poly_edge_point(poly_up(p[2 * ep]), poly_up(p[2 * ep + 1]), poly_up(p[2 * e]),
+                      poly_up(p[2 * e + 1]), (int)(eoff[e] - eoff[ep]) - 1, up, vp);
+    }
+    if (u == up) continue;
+    double xd = (double)(u < up ? u : u - 1);
+    xd = __dadd_rn(__ddiv_rn(__dadd_rn(xd, 0.5), 5.0), -0.5);
+    if (floor(xd) != xd || xd < 0 || xd > (double)(w - 1)) continue;
+    double yd = (double)(v < vp ? v : vp);
+    yd = __dadd_rn(__ddiv_rn(__dadd_rn(yd, 0.5), 5.0), -0.5);
+    if (yd < 0) yd = 0; else if (yd > (double)h) yd = (double)h;
+    yd = ceil(yd);
+    const int slot = atomicAdd(&s_n, 1);
+    if (slot < kPolyMaxCross) s_a[slot] = (unsigned)((int)xd * h + (int)yd);
+  }
+  __syncthreads();
+  int n = s_n;
+  if (n > kPolyMaxCross) {
+    if (threadIdx.x == 0) atomicExch(err, 1 + part);
+    n = kPolyMaxCross;
+  }
+  // bitonic sort of the first pow2 >= n entries (padding = UINT_MAX)
+  int np2 = 1;
+  while (np2 < n) np2 <<= 1;
+  for (int i = n + threadIdx.x; i < np2; i += blockDim.x) s_a[i] = 0xffffffffu;
+  __syncthreads();
+  for (int size = 2; size <= np2; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+        const int jx = i ^ stride;
+        if (jx > i) {
+          const unsigned a = s_a[i], b = s_a[jx];
+          const bool asc = (i & size) == 0;
+          if ((a > b) == asc) {
+            s_a[i] = b;
+            s_a[jx] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  unsigned* dst = cross + (long long)part * kPolyMaxCross;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = s_a[i];
+  if (threadIdx.x == 0) cross_n[part] = n;
+}
+
+__global__ void __launch_bounds__(128)
+poly_fill_kernel(const unsigned* __restrict__ cross, const int* __restrict__ cross_n,
+                 const int* __restrict__ inst_part_off, int h, int w, uint8_t* __restrict__ out) {
+  const int inst = blockIdx.y;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= w) return;
+  uint8_t* col = out + (long long)inst * h * w + x;
+  const int p0 = inst_part_off[inst], p1 = inst_part_off[inst + 1];
+  if (p0 == p1) {
+    for (int y = 0; y < h; ++y) col[(long long)y * w] = 0;
+    return;
+  }
+  for (int part = p0; part < p1; ++part) {
+    const unsigned* a = cross + (long long)part * kPolyMaxCross;
+    const int n = cross_n[part];
+    const unsigned base = (unsigned)x * (unsigned)h;
+    int lo = 0, hi = n;                                   // first boundary >= base
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (a[mid] < base) lo = mid + 1; else hi = mid;
+    }
+    int ptr = lo;
+    unsigned parity = (unsigned)lo & 1u;                  // boundaries in earlier columns carry over
+    unsigned next = ptr < n ? a[ptr] : 0xffffffffu;
+    for (int y = 0; y < h; ++y) {
+      const unsigned i = base + (unsigned)y;
+      while (next <= i) {
+        parity ^= 1u;
+        ++ptr;
+        next = ptr < n ? a[ptr] : 0xffffffffu;
+      }
+      if (part == p0) col[(long long)y * w] = (uint8_t)parity;
+      else if (parity) col[(long long)y * w] = 1;         // rleMerge(union): OR of the parts
+    }
+  }
+}
+
 inline int grid_for(long long n, int per_block = 256, int max_blocks = 148 * 16) {
   long long b = (n + per_block - 1) / per_block;
   if (b < 1) b = 1;
@@ -147,6 +320,40 @@ int loft_mask_flip_pad(const uint8_t* in, uint8_t* out, long long G, int H, int 
   mask_flip_pad_kernel<<<grid_for(total), 256, 0, stream>>>(in, out, G, H, W, Hp, Wp, flip,
                                                             aligned16);
   LOFT_CUDA_LAUNCH_CHECK("mask_flip_pad");
+  return LOFT_OK;
+}
+
+
+long long loft_poly_scratch_bytes(long long total_vertices, int n_parts) {
+  // edge offsets (8 B each) + sorted boundaries + counts + error flag, each 16-byte aligned
+  long long b = ((total_vertices + n_parts) * 8 + 15) / 16 * 16;
+  b += (long long)n_parts * kPolyMaxCross * 4;
+  b += ((long long)n_parts * 4 + 15) / 16 * 16;
+  return b + 16;
+}
+
+int loft_poly_rasterize(const double* xy, const long long* part_off, const int* inst_part_off,
+                        int n_inst, int n_parts, long long total_vertices, int H, int W,
+                        uint8_t* out, void* scratch, int* err, cudaStream_t stream) {
+  LOFT_CHECK_ARG(out && inst_part_off && err, "poly_rasterize: null pointer");
+  LOFT_CHECK_SHAPE(n_inst >= 0 && n_parts >= 0 && H > 0 && W > 0 &&
+                       (long long)H * W < (1ll << 31) - H,
+                   "poly_rasterize: bad sizes n_inst=%d n_parts=%d H=%d W=%d", n_inst, n_parts, H, W);
+  if (n_inst == 0) return LOFT_OK;
+  LOFT_CHECK_ARG(n_parts == 0 || (xy && part_off && scratch), "poly_rasterize: null pointer");
+  char* sp = static_cast<char*>(scratch);
+  long long* edge_off = reinterpret_cast<long long*>(sp);
+  sp += ((total_vertices + n_parts) * 8 + 15) / 16 * 16;
+  unsigned* cross = reinterpret_cast<unsigned*>(sp);
+  sp += (long long)n_parts * kPolyMaxCross * 4;
+  int* cross_n = reinterpret_cast<int*>(sp);
+  if (n_parts > 0) {
+    poly_cross_kernel<<<n_parts, 256, 0, stream>>>(xy, part_off, H, W, edge_off, cross, cross_n, err);
+    LOFT_CUDA_LAUNCH_CHECK("poly_cross");
+  }
+  poly_fill_kernel<<<dim3(loft_cdiv(W, 128), n_inst), 128, 0, stream>>>(cross, cross_n,
+                                                                        inst_part_off, H, W, out);
+  LOFT_CUDA_LAUNCH_CHECK("poly_fill");
   return LOFT_OK;
 }
 

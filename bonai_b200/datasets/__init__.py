@@ -1,2 +1,4 @@
-from .gpu_pipeline import GpuTrainPipeline, image_prep, mask_flip_pad  # noqa: F401
+from .gpu_pipeline import (GpuTrainPipeline, image_prep, mask_flip_pad,  # noqa: F401
+                           polygons_to_bitmaps)
 from .synthetic import make_inputs  # noqa: F401
+from .bonai import BONAI, DATASETS, build_dataset  # noqa: F401

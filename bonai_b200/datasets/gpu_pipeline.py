@@ -61,6 +61,49 @@ def mask_flip_pad(masks_u8, flip=None, size_divisor=32):
     return out
 
 
+def polygons_to_bitmaps(masks_ann, H, W, device='cuda'):
+    """LoadAnnotations._load_masks with poly2mask=True (loading.py:301-326,345-368) on the device:
+    `masks_ann` = per instance a list of polygon parts (flat [x0, y0, x1, y1, ...]); returns the
+    uint8 [G,H,W] bitmaps pycocotools' frPyObjects -> merge -> decode would produce
+    (`loft_poly_rasterize`).  As in frPyObjects, an instance whose first part has exactly 4
+    numbers is a list of [x, y, w, h] boxes."""
+    dev = torch.device(device)
+    G = len(masks_ann)
+    out = torch.empty((G, H, W), device=dev, dtype=torch.uint8)
+    if G == 0:
+        return out
+    xy, part_off, inst_off = [], [0], [0]
+    for parts in masks_ann:
+        if isinstance(parts, dict):
+            raise NotImplementedError('RLE mask annotations are not on the BONAI path')
+        as_bbox = len(parts) > 0 and len(parts[0]) == 4
+        for p in parts:
+            p = [float(v) for v in p]
+            if as_bbox:
+                xs, ys, xe, ye = p[0], p[1], p[0] + p[2], p[1] + p[3]
+                p = [xs, ys, xs, ye, xe, ye, xe, ys]
+            if len(p) % 2:
+                raise L.LoftError('polygon with an odd number of coordinates')
+            xy.extend(p)
+            part_off.append(part_off[-1] + len(p) // 2)
+        inst_off.append(len(part_off) - 1)
+    n_parts, n_vert = len(part_off) - 1, part_off[-1]
+    xy_d = torch.tensor(xy if xy else [0.0], dtype=torch.float64).to(dev, non_blocking=True)
+    po_d = torch.tensor(part_off, dtype=torch.int64).to(dev, non_blocking=True)
+    io_d = torch.tensor(inst_off, dtype=torch.int32).to(dev, non_blocking=True)
+    lib = L.lib()
+    lib.loft_poly_scratch_bytes.restype = ctypes.c_longlong
+    nbytes = int(lib.loft_poly_scratch_bytes(ctypes.c_longlong(n_vert), i32(n_parts)))
+    scratch = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+    err = torch.zeros(1, device=dev, dtype=torch.int32)
+    L.call('poly_rasterize', L.ptr(xy_d), L.ptr(po_d), L.ptr(io_d), i32(G), i32(n_parts),
+           L.ll(n_vert), i32(H), i32(W), L.ptr(out), L.ptr(scratch), L.ptr(err), L.stream())
+    e = int(err.item())            # loader path, not the training step: one read-back per tile
+    if e:
+        raise L.LoftError(f'polygon part {e - 1} has more than 8192 run boundaries')
+    return out
+
+
 class GpuTrainPipeline:
     """Same parameters as the reference's transform dicts.  `__call__` takes what
     LoadImageFromFile + LoadAnnotations produce for one tile and returns the keys `Collect`

@@ -96,4 +96,11 @@ train_pipeline = [
     dict(type='DefaultFormatBundle'),
     dict(type='Collect', keys=['img', 'gt_bboxes', 'gt_labels', 'gt_masks', 'gt_offsets']),
 ]
-data = dict(samples_per_gpu=2, workers_per_gpu=2, train=dict(type='BONAI', pipeline=train_pipeline))
+# the five city files of configs/_base_/datasets/bonai_instance.py:31-48
+data_root = 'data/BONAI/'
+cities = ['shanghai', 'beijing', 'jinan', 'haerbin', 'chengdu']
+train_ann_file = [data_root + 'coco/bonai_{}_trainval.json'.format(c) for c in cities]
+img_prefix = [data_root + 'trainval/images/' for _ in cities]
+data = dict(samples_per_gpu=2, workers_per_gpu=2,
+            train=dict(type='BONAI', ann_file=train_ann_file, img_prefix=img_prefix,
+                       bbox_type='building', mask_type='roof', pipeline=train_pipeline))

@@ -219,6 +219,18 @@ int loft_image_prep(const uint8_t* img_hwc, float* out_chw, int H, int W, int Hp
 int loft_mask_flip_pad(const uint8_t* in, uint8_t* out, long long G, int H, int W, int Hp, int Wp,
                        int flip, cudaStream_t stream);
 
+/* Polygon -> bitmap: LoadAnnotations(poly2mask=True) (pipelines/loading.py:301-326,345-368), i.e.
+ * pycocotools 2.0.x `decode(merge(frPyObjects(polygons, h, w)))` (common/maskApi.c rleFrPoly /
+ * rleMerge / rleDecode; the dependency is not vendored in the reference tree).  xy: vertices of all
+ * parts as (x, y) doubles; part_off[n_parts+1]: first vertex of each part; inst_part_off[n_inst+1]:
+ * first part of each instance; out: uint8 [n_inst, H, W] row-major, every byte written.  scratch:
+ * loft_poly_scratch_bytes() bytes of device memory; *err (device int, zero it first) is set to
+ * 1 + part index if a part has more than 8192 run boundaries (its bitmap is then incomplete). */
+long long loft_poly_scratch_bytes(long long total_vertices, int n_parts);
+int loft_poly_rasterize(const double* xy, const long long* part_off, const int* inst_part_off,
+                        int n_inst, int n_parts, long long total_vertices, int H, int W,
+                        uint8_t* out, void* scratch, int* err, cudaStream_t stream);
+
 /* ---- losses (loss.cu) ----------------------------------------------------------------------------
  * mode 0 = BCE-with-logits (cross_entropy_loss.py:58-125), 1 = L1, 2 = SmoothL1
  * (smooth_l1_loss.py:8-42); sums are accumulated into device scalars (weight_reduce_loss,

@@ -33,3 +33,30 @@ print(json.dumps(dict(image_prep_us=round(t_img * 1e6, 1), image_prep_GBs=round(
                       mask_flip_pad_us=round(t_msk * 1e6, 1), mask_flip_pad_GBs=round(b_msk / t_msk / 1e9, 1),
                       tile_us=round((t_img + t_msk) * 1e6, 1), cpu_numpy_tile_ms=round(t_cpu * 1e3, 1),
                       algorithmic_bytes_per_tile=b_img + b_msk)))
+
+# polygon -> bitmap (LoadAnnotations poly2mask): 80 rotated-rectangle / star buildings per tile
+from bonai_b200 import _lib as L
+import ctypes
+from bonai_b200.datasets import polygons_to_bitmaps
+from oracle.polygon_cpu import poly2mask
+polys = []
+for i in range(G):
+    cx, cy = rng.uniform(50, W - 50), rng.uniform(50, H - 50)
+    k = 4 if i % 2 == 0 else 12
+    ang = np.sort(rng.uniform(0, 2 * np.pi, k)); r = rng.uniform(10, 60, k)
+    polys.append([np.stack([cx + r * np.cos(ang), cy + r * np.sin(ang)], 1).reshape(-1).tolist()])
+for _ in range(3):
+    polygons_to_bitmaps(polys, H, W, 'cuda')
+torch.cuda.synchronize()
+t0 = time.time()
+for _ in range(10):
+    polygons_to_bitmaps(polys, H, W, 'cuda')          # includes the wrapper's H2D copies + one sync
+torch.cuda.synchronize()
+t_poly = (time.time() - t0) / 10
+t0 = time.time()
+for p in polys[:20]:
+    poly2mask(p, H, W)
+t_poly_cpu = (time.time() - t0) / 20 * G
+print(json.dumps(dict(poly_rasterize_tile_us_wall=round(t_poly * 1e6, 1),
+                      poly_rasterize_GBs_written=round(G * H * W / t_poly / 1e9, 1),
+                      cpu_numpy_restatement_tile_ms=round(t_poly_cpu * 1e3, 1))))
