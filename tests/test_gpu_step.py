@@ -160,20 +160,32 @@ def test_full_size_conv_linearity():
 
 
 def test_soft_nms_kernel_vs_oracle():
+    """Both forms of `loft_soft_nms_linear` -- the one-barrier-per-iteration kernel (n <= 4096) and
+    the general one -- against the CPU restatement: same keep order, same decayed scores; class-aware
+    form == the oracle on coordinate-offset boxes (batched_nms' trick, bbox_nms.py:5-69)."""
     from bonai_b200.ops import soft_nms
     from oracle import ops_cpu
     g = torch.Generator().manual_seed(0)
-    n = 1500
-    c = torch.rand(n, 2, generator=g) * 256
-    wh = torch.exp(torch.rand(n, 2, generator=g) * 2.5) * 6
-    boxes = torch.cat([c - wh / 2, c + wh / 2], 1).clamp(0, 256)
-    scores = torch.rand(n, generator=g) * 0.9 + 0.06
-    d0, k0 = ops_cpu.soft_nms_linear(boxes, scores, 0.5, 1e-3)
-    d1, k1 = soft_nms(boxes.cuda(), scores.cuda(), 0.5, min_score=1e-3)
-    assert k1.shape == k0.shape and torch.equal(k1.cpu(), k0)
-    assert torch.allclose(d1.cpu(), d0, rtol=1e-6, atol=1e-7)
-    d2, k2 = soft_nms(boxes.cuda(), scores.cuda(), 0.5, min_score=1e-3, max_keep=100)
-    assert torch.equal(k2.cpu(), k0[:100])
+    for n in (1500, 700, 2048, 3000, 4500):
+        side = 256 if n <= 3000 else 1024      # (denser scenes decay scores into exact ties, where
+        c = torch.rand(n, 2, generator=g) * side    # the oracle's swap-based order is arbitrary)
+        wh = torch.exp(torch.rand(n, 2, generator=g) * 2.5) * 6
+        boxes = torch.cat([c - wh / 2, c + wh / 2], 1).clamp(0, side)
+        scores = torch.rand(n, generator=g) * 0.9 + 0.06
+        d0, k0 = ops_cpu.soft_nms_linear(boxes, scores, 0.5, 1e-3)
+        d1, k1 = soft_nms(boxes.cuda(), scores.cuda(), 0.5, min_score=1e-3)
+        assert k1.shape == k0.shape and torch.equal(k1.cpu(), k0), n
+        assert torch.allclose(d1.cpu(), d0, rtol=1e-6, atol=1e-7), n
+        d2, k2 = soft_nms(boxes.cuda(), scores.cuda(), 0.5, min_score=1e-3, max_keep=100)
+        assert torch.equal(k2.cpu(), k0[:100]), n
+        if n <= 1500:
+            idxs = torch.randint(0, 3, (n,), generator=g)
+            shifted = boxes + (idxs.float() * (boxes.max() + 1))[:, None]
+            d3, k3 = ops_cpu.soft_nms_linear(shifted, scores, 0.5, 1e-3)
+            d4, k4 = soft_nms(boxes.cuda(), scores.cuda(), 0.5, min_score=1e-3, idxs=idxs.cuda())
+            assert torch.equal(k4.cpu(), k3), n
+            assert torch.allclose(d4[:, 4].cpu(), d3[:, 4], rtol=1e-6, atol=1e-7), n
+            assert torch.equal(d4[:, :4].cpu(), boxes[k3]), n
 
 
 def test_inference_parity_256():

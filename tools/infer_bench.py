@@ -95,6 +95,11 @@ def main():
         line['breakdown_ms_per_img'] = {g: round(sum(agg.get(n, 0.0) for n in names) / B, 3)
                                         for g, names in GROUPS.items()}
         line['breakdown_ms_per_img']['all_c_abi_calls'] = round(sum(agg.values()) / B, 3)
+        cnt = {}
+        for name, _, _ in events:
+            cnt[name] = cnt.get(name, 0) + 1
+        line['top_calls_ms_per_img'] = {n: [round(v / B, 3), cnt[n]] for n, v in
+                                        sorted(agg.items(), key=lambda kv: -kv[1])[:8]}
         if args.api:
             for _ in range(2):
                 model.simple_test(imgs[:1], [meta])
