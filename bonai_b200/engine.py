@@ -168,6 +168,31 @@ class ParamStore:
             else:
                 tail = False
         self.heads_done_hooks = []           # called at the start of the trunk's backward
+        # Second cut for an overlapped gradient exchange: the parameters of backbone.layer3 /
+        # layer4, the neck and the RPN head are a contiguous range [mid_start, head_start) of the
+        # flat buffer whose gradients are final once the trunk's backward has passed layer3 -- the
+        # trunk then calls upper_done() between its two backward programs.  None if the layout
+        # does not have that shape (other backbones).
+        upper = ('backbone.layer3.', 'backbone.layer4.', 'neck.', 'rpn_head.')
+        self.mid_start = None
+        lo = None
+        ok = True
+        for p, o in zip(order, offs):
+            if o >= self.head_start:
+                continue
+            nm = names.get(id(p), '')
+            if nm.startswith(upper):
+                lo = o if lo is None else min(lo, o)
+        if lo is not None:
+            for p, o in zip(order, offs):
+                nm = names.get(id(p), '')
+                if lo <= o < self.head_start and not nm.startswith(upper):
+                    ok = False
+                if o < lo and nm.startswith(upper):
+                    ok = False
+            if ok and 0 < lo < self.head_start:
+                self.mid_start = lo
+        self.upper_done_hooks = []
         self._build_fold_tables()
         # everything whose in-place modification (load_state_dict, init_weights, an external torch
         # optimizer) must trigger a rebuild of the derived copies: the parameters themselves --
@@ -255,6 +280,11 @@ class ParamStore:
                 pk.scatter()
                 pk.scattered = True
         for fn in self.heads_done_hooks:
+            fn()
+
+    def upper_done(self):
+        """The trunk's backward has produced every gradient of [mid_start, head_start)."""
+        for fn in self.upper_done_hooks:
             fn()
 
     # ------------------------------------------------------------------ per-step protocol

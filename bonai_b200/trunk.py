@@ -89,6 +89,10 @@ class _Program:
         self.model, self.N, self.H, self.W, self.dev, self.train = model, N, H, W, dev, train
         self.img = torch.empty((N, 3, H, W), device=dev, dtype=torch.float32)
         self.fwd, self.bwd = Tape('trunk_forward_graph'), Tape('trunk_backward_graph')
+        # the tail of the main backward (the stages below `split_stage`), recorded separately when
+        # a data-parallel trainer wants to exchange the upper stages' gradients under it
+        self.bwd_tail = Tape('trunk_backward_tail_graph')
+        self.split_stage = None
         self.bwd_rpn = Tape('trunk_rpn_backward_graph')
         self.fwd_ready = self.bwd_ready = self.bwd_rpn_ready = False
         self.rpn_done, self.rpn_event = False, None
@@ -381,6 +385,11 @@ class _Program:
                 recs = self.stages[s]
                 if not recs[0]['blk']._trainable:
                     break
+                if self.split_stage is not None and s == self.split_stage - 1:
+                    # everything from here on goes to the tail program: the gradients of stages
+                    # >= split_stage, the FPN and the RPN are final at this point
+                    self.bwd.__exit__(None, None, None)
+                    self.bwd_tail.__enter__()
                 last = recs[-1]['blk']
                 ldb = last._s3.bias_grad
                 ldb2 = last._sd.bias_grad if last._sd is not None else None
@@ -399,6 +408,10 @@ class _Program:
                         self._block_bwd(rec, g)
                         below = s > 0 and self.stages[s - 1][0]['blk']._trainable
                         g = self._stage_boundary_bwd(rec, g, s - 1, dlat[s - 1]) if below else None
+            if L.RECORD is self.bwd_tail.calls:
+                # leave the recording state the enclosing `with self.bwd` expects to close
+                self.bwd_tail.__exit__(None, None, None)
+                L.RECORD = self.bwd.calls
         self.bwd_ready = True
 
     def _stage_boundary_bwd(self, rec, g, s_in, dlat_in):
@@ -482,6 +495,9 @@ class Trunk:
         #   '0'    inside _TrunkFn.backward, like any other node.
         self.early_rpn = os.environ.get('LOFT_EARLY_RPN', 'end')
         self.bwd_sm_reserve = 0        # set by a distributed Trainer that overlaps the exchange
+        # main backward in two programs: stages >= split_stage (+ FPN, RPN) first, the rest after
+        # `store.upper_done()` -- only when something listens (store.upper_done_hooks)
+        self.split_stage = int(os.environ.get('LOFT_SPLIT_BWD', '2'))
         self.current = None
         self.step_ctx = (None, None)
         store.pre_finalize.append(self.flush)
@@ -612,11 +628,16 @@ class Trunk:
         if not prog.bwd_ready:
             # with a concurrent gradient exchange, leave its CTAs a few SMs (baked into the graph)
             prev = L.lib().loft_reserve_sms(self.bwd_sm_reserve) if self.bwd_sm_reserve else 0
+            prog.split_stage = self.split_stage if self.store.upper_done_hooks else None
             prog.build_backward()
             if prog.use_graph:
                 prog.bwd.capture()
+                if prog.bwd_tail.calls:
+                    prog.bwd_tail.capture()
             if self.bwd_sm_reserve:
                 L.lib().loft_reserve_sms(prev)
+            # (the recording pass executed both parts back to back: this step's upper-stage
+            # gradients are exchanged with the rest, after the backward)
             # The tapes pin thousands of small Python objects; move them (and everything else
             # built so far) out of the cyclic GC's reach so a generation-2 sweep never stalls the
             # launch thread in the middle of a step.
@@ -625,6 +646,9 @@ class Trunk:
             gc.freeze()
         else:
             prog.bwd.launch()
+            if prog.bwd_tail.calls:
+                self.store.upper_done()
+                prog.bwd_tail.launch()
         prog.rpn_done = False
 
     def early_rpn_backward(self, losses, when):
