@@ -584,16 +584,8 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
         const bool contig = (p.mode == FPROP_2D || p.mode == DGRAD_2D) && p.out_map == 0;
         const bool do_colsum = p.colsum != nullptr;
         float csum = 0.f;
-        for (int cc = half * kCh; cc < p.n_mma; cc += 2 * kCh) {
-          float v[kCh];
-#ifdef LOFT_KTRACE
-          if (p.dbg_skip & 16) {    // attribution: no tensor-memory loads
-#pragma unroll
-            for (int j = 0; j < kCh; ++j) v[j] = (float)(cc + j);
-          } else
-#endif
-          tmem_ld32(taddr + cc, v);
-          if (!c_ok) continue;
+        // ---- the generic chunk body: any flag combination, per-column validity
+        auto generic_chunk = [&](const int cc, float (&v)[kCh]) {
           int rows[kCh];
           float rv[kCh];
           if (p.fast_epi && s_vmask[cc >> 5] == 0xffffffffu) {
@@ -669,13 +661,13 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
               for (int j = 0; j < kCh; ++j) z += v[j];
               if (z == 123.456f) outb[off[0]] = z;
-              continue;
+              return;
             }
 #endif
 #pragma unroll
             for (int j = 0; j < kCh; ++j) outb[LOFT_OFF(j)] = v[j];
 #undef LOFT_OFF
-            continue;
+            return;
           }
 #pragma unroll
           for (int j = 0; j < kCh; ++j) rows[j] = s_row[cc + j];
@@ -726,6 +718,141 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
             csum += acc;
             outb[(long long)rows[j] * ldo] = acc;
           }
+        };
+        // ---- tile-level dispatch.  A chunk of 32 fully valid columns with the common flag
+        // combinations (no raw copy, residual at the output's own pitch or none) runs a body
+        // specialised at compile time on {consecutive rows, residual, mask}: the generic body
+        // re-decides every flag per chunk with uniform branches fed by constant-bank loads, and
+        // with two warps per scheduler each of those is exposed latency (measured: 2.3 us for a
+        // 128 x 128 tile with neither stores nor tensor-memory loads).  ReLU is a max against
+        // 0 / -inf and the column sum is always accumulated, so they cost no variants.
+        const bool spec_ok = p.fast_epi && rawb == nullptr &&
+                             (res_mode == 0 || (res_mode == 1 && ldr == ldo));
+        const float relu_lo = relu ? 0.f : -INFINITY;
+        auto spec_loop = [&](auto contig_c, auto res_c, auto mask_c) {
+          constexpr bool kContig = decltype(contig_c)::value, kRes = decltype(res_c)::value,
+                         kMask = decltype(mask_c)::value;
+          const int ldo32 = (int)ldo;
+          for (int cc = half * kCh; cc < p.n_mma; cc += 2 * kCh) {
+            float v[kCh];
+#ifdef LOFT_KTRACE
+            if (p.dbg_skip & 16) {
+#pragma unroll
+              for (int j = 0; j < kCh; ++j) v[j] = (float)(cc + j);
+            } else
+#endif
+            tmem_ld32(taddr + cc, v);
+            if (!c_ok) continue;
+            if (s_vmask[cc >> 5] != 0xffffffffu) {
+              // ragged chunk (image border, last tile, columns past n_mma): same arithmetic with
+              // per-column predicates
+              int off[kCh];
+              float rv[kCh];
+#pragma unroll
+              for (int j = 0; j < kCh; ++j) {
+                const int r = s_row[cc + j];
+                off[j] = r >= 0 ? r * ldo32 : -1;
+              }
+              if constexpr (kRes) {
+#pragma unroll
+                for (int j = 0; j < kCh; ++j) rv[j] = off[j] >= 0 ? resb[off[j]] : 0.f;
+              }
+#pragma unroll
+              for (int j = 0; j < kCh; ++j) v[j] = fmaf(v[j], sc, sh);
+              if constexpr (kRes) {
+#pragma unroll
+                for (int j = 0; j < kCh; ++j) v[j] += rv[j];
+              }
+              if constexpr (kMask) {
+#pragma unroll
+                for (int j = 0; j < kCh; ++j) rv[j] = off[j] >= 0 ? mskb[off[j]] : 0.f;
+              }
+#pragma unroll
+              for (int j = 0; j < kCh; ++j) {
+                float a = fmaxf(v[j], relu_lo);
+                if constexpr (kMask) a = (rv[j] > 0.f) ? a : 0.f;
+                if (round_out) {
+                  uint32_t rr;
+                  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(rr) : "f"(a));
+                  a = __uint_as_float(rr);
+                }
+                if (off[j] >= 0) {
+                  csum += a;
+                  outb[off[j]] = a;
+                }
+              }
+              continue;
+            }
+            int off[kCh];
+            if constexpr (kContig) {
+              const int r0 = s_row[cc] * ldo32;
+#pragma unroll
+              for (int j = 0; j < kCh; ++j) off[j] = r0 + j * ldo32;
+            } else {
+#pragma unroll
+              for (int j = 0; j < kCh; ++j) off[j] = s_row[cc + j] * ldo32;
+            }
+            float rv[kCh];
+            if constexpr (kRes) {
+#pragma unroll
+              for (int j = 0; j < kCh; ++j) rv[j] = resb[off[j]];
+            }
+#pragma unroll
+            for (int j = 0; j < kCh; ++j) v[j] = fmaf(v[j], sc, sh);
+            if constexpr (kRes) {
+#pragma unroll
+              for (int j = 0; j < kCh; ++j) v[j] += rv[j];
+            }
+            if constexpr (kMask) {
+#pragma unroll
+              for (int j = 0; j < kCh; ++j) rv[j] = mskb[off[j]];
+            }
+#pragma unroll
+            for (int j = 0; j < kCh; ++j) v[j] = fmaxf(v[j], relu_lo);
+            if constexpr (kMask) {
+#pragma unroll
+              for (int j = 0; j < kCh; ++j) v[j] = (rv[j] > 0.f) ? v[j] : 0.f;
+            }
+            if (round_out) {
+#pragma unroll
+              for (int j = 0; j < kCh; ++j) {
+                uint32_t rr;
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(rr) : "f"(v[j]));
+                v[j] = __uint_as_float(rr);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < kCh; ++j) csum += v[j];
+#ifdef LOFT_KTRACE
+            if (p.dbg_skip & 8) {
+              if (csum == 123.456f) outb[off[0]] = csum;
+              continue;
+            }
+#endif
+#pragma unroll
+            for (int j = 0; j < kCh; ++j) outb[off[j]] = v[j];
+          }
+        };
+        using T_ = std::true_type;
+        using F_ = std::false_type;
+        const int variant = !spec_ok ? -1
+                                     : (contig ? 1 : 0) | (res_mode == 1 ? 2 : 0) | (mskb ? 4 : 0);
+        switch (variant) {
+          case 0: spec_loop(F_{}, F_{}, F_{}); break;
+          case 1: spec_loop(T_{}, F_{}, F_{}); break;
+          case 2: spec_loop(F_{}, T_{}, F_{}); break;
+          case 3: spec_loop(T_{}, T_{}, F_{}); break;
+          case 4: spec_loop(F_{}, F_{}, T_{}); break;
+          case 5: spec_loop(T_{}, F_{}, T_{}); break;
+          case 6: spec_loop(F_{}, T_{}, T_{}); break;
+          case 7: spec_loop(T_{}, T_{}, T_{}); break;
+          default:
+            for (int cc = half * kCh; cc < p.n_mma; cc += 2 * kCh) {
+              float v[kCh];
+              tmem_ld32(taddr + cc, v);
+              if (!c_ok) continue;
+              generic_chunk(cc, v);
+            }
         }
         if (p.colsum != nullptr && c_ok) {
           atomicAdd(p.colsum + (long long)grp * p.colsum_gstride + ocol, csum);
