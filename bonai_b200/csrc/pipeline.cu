@@ -276,6 +276,89 @@ poly_fill_kernel(const unsigned* __restrict__ cross, const int* __restrict__ cro
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Resize(keep_ratio) for tiles that are not already at img_scale (transforms.py:186-215,244-253):
+// mmcv.imrescale -> cv2.resize.  Image: INTER_LINEAR on uint8, restated from OpenCV's
+// imgproc/resize.cpp (resizeGeneric_ / HResizeLinear / VResizeLinear<uchar>): source coordinate
+// (float)((d + .5) * scale - .5), 11-bit fixed-point weights rounded half-to-even, horizontal pass
+// in int, vertical pass ((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2.
+// Bitmaps: INTER_NEAREST, source index min(floor(d * scale), size - 1).  cv2 is not in this image:
+// the oracle (oracle/pipeline_cpu.py) is the same restatement -- PARITY UNPINNED for this step.
+// The BONAI configuration never takes this path (1024^2 tiles at img_scale 1024: identity).
+struct LinTap {
+  int s0, s1;      // source indices (clamped)
+  int a0, a1;      // fixed-point weights, sum 2048
+};
+
+__device__ __forceinline__ LinTap lin_tap_x(int d, double scale, int ssize) {
+  float f = (float)__dadd_rn(__dmul_rn((double)d + 0.5, scale), -0.5);
+  int s = (int)floorf(f);
+  f -= (float)s;
+  if (s < 0) {
+    f = 0.f;
+    s = 0;
+  }
+  if (s >= ssize - 1) {
+    f = 0.f;
+    s = ssize - 1;
+  }
+  LinTap t;
+  t.s0 = s;
+  t.s1 = s + 1 < ssize ? s + 1 : ssize - 1;
+  t.a0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
+  t.a1 = __float2int_rn(__fmul_rn(f, 2048.f));
+  return t;
+}
+
+__device__ __forceinline__ LinTap lin_tap_y(int d, double scale, int ssize) {
+  float f = (float)__dadd_rn(__dmul_rn((double)d + 0.5, scale), -0.5);
+  const int s = (int)floorf(f);
+  f -= (float)s;                       // the weights are NOT reset at the border, the rows are clipped
+  LinTap t;
+  t.s0 = min(max(s, 0), ssize - 1);
+  t.s1 = min(max(s + 1, 0), ssize - 1);
+  t.a0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
+  t.a1 = __float2int_rn(__fmul_rn(f, 2048.f));
+  return t;
+}
+
+__global__ void resize_bilinear_u8c3_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                            int sh, int sw, int dh, int dw, double scale_x,
+                                            double scale_y) {
+  const long long total = (long long)dh * dw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int dx = (int)(i % dw), dy = (int)(i / dw);
+    const LinTap tx = lin_tap_x(dx, scale_x, sw), ty = lin_tap_y(dy, scale_y, sh);
+    const uint8_t* r0 = src + (long long)ty.s0 * sw * 3;
+    const uint8_t* r1 = src + (long long)ty.s1 * sw * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const int h0 = (int)r0[tx.s0 * 3 + c] * tx.a0 + (int)r0[tx.s1 * 3 + c] * tx.a1;
+      const int h1 = (int)r1[tx.s0 * 3 + c] * tx.a0 + (int)r1[tx.s1 * 3 + c] * tx.a1;
+      const int v = (((ty.a0 * (h0 >> 4)) >> 16) + ((ty.a1 * (h1 >> 4)) >> 16) + 2) >> 2;
+      dst[i * 3 + c] = (uint8_t)min(max(v, 0), 255);
+    }
+  }
+}
+
+__global__ void resize_nearest_u8_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                         long long G, int sh, int sw, int dh, int dw, double scale_x,
+                                         double scale_y) {
+  const long long total = G * dh * dw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int dx = (int)(i % dw);
+    const long long t = i / dw;
+    const int dy = (int)(t % dh);
+    const long long g = t / dh;
+    const int sx = min((int)floor(__dmul_rn((double)dx, scale_x)), sw - 1);
+    const int sy = min((int)floor(__dmul_rn((double)dy, scale_y)), sh - 1);
+    dst[i] = src[(g * sh + sy) * (long long)sw + sx];
+  }
+}
+
 inline int grid_for(long long n, int per_block = 256, int max_blocks = 148 * 16) {
   long long b = (n + per_block - 1) / per_block;
   if (b < 1) b = 1;
@@ -354,6 +437,33 @@ int loft_poly_rasterize(const double* xy, const long long* part_off, const int* 
   poly_fill_kernel<<<dim3(loft_cdiv(W, 128), n_inst), 128, 0, stream>>>(cross, cross_n,
                                                                         inst_part_off, H, W, out);
   LOFT_CUDA_LAUNCH_CHECK("poly_fill");
+  return LOFT_OK;
+}
+
+
+int loft_resize_bilinear_u8(const uint8_t* src_hwc, uint8_t* dst_hwc, int sh, int sw, int dh, int dw,
+                            cudaStream_t stream) {
+  LOFT_CHECK_ARG(src_hwc && dst_hwc, "resize_bilinear_u8: null pointer");
+  LOFT_CHECK_SHAPE(sh > 0 && sw > 0 && dh > 0 && dw > 0, "resize_bilinear_u8: bad sizes %dx%d -> %dx%d",
+                   sh, sw, dh, dw);
+  // cv2.resize with dsize: inv_scale = dsize / ssize, scale = 1 / inv_scale
+  const double scale_x = 1.0 / ((double)dw / (double)sw), scale_y = 1.0 / ((double)dh / (double)sh);
+  resize_bilinear_u8c3_kernel<<<grid_for((long long)dh * dw), 256, 0, stream>>>(
+      src_hwc, dst_hwc, sh, sw, dh, dw, scale_x, scale_y);
+  LOFT_CUDA_LAUNCH_CHECK("resize_bilinear_u8");
+  return LOFT_OK;
+}
+
+int loft_resize_nearest_u8(const uint8_t* src, uint8_t* dst, long long G, int sh, int sw, int dh,
+                           int dw, cudaStream_t stream) {
+  LOFT_CHECK_ARG(src && dst, "resize_nearest_u8: null pointer");
+  LOFT_CHECK_SHAPE(G >= 0 && sh > 0 && sw > 0 && dh > 0 && dw > 0,
+                   "resize_nearest_u8: bad sizes G=%lld %dx%d -> %dx%d", G, sh, sw, dh, dw);
+  if (G == 0) return LOFT_OK;
+  const double scale_x = 1.0 / ((double)dw / (double)sw), scale_y = 1.0 / ((double)dh / (double)sh);
+  resize_nearest_u8_kernel<<<grid_for(G * dh * dw), 256, 0, stream>>>(src, dst, G, sh, sw, dh, dw,
+                                                                      scale_x, scale_y);
+  LOFT_CUDA_LAUNCH_CHECK("resize_nearest_u8");
   return LOFT_OK;
 }
 

@@ -5,9 +5,10 @@
 In the reference this runs in DataLoader worker processes on the CPU and ships a float32 image
 (12 MB) plus uint8 bitmaps (1 MB per building) per tile; at >100 tiles/s per GPU those two worker
 processes are the bottleneck.  Here the tile crosses PCIe as uint8 (3 MB) and two
-kernels do the rest in one pass each (csrc/pipeline.cu).  Scope of this first slice: tiles whose
-Resize is the identity (scale factor 1 -- the BONAI case: 1024^2 tiles at img_scale=(1024,1024));
-image decoding and polygon rasterisation stay with the loader.
+kernels do the rest in one pass each (csrc/pipeline.cu); the building polygons are rasterised on
+the device too (`polygons_to_bitmaps`).  For BONAI the Resize is the identity (1024^2 tiles at
+img_scale=(1024,1024)); other tile sizes go through the restated cv2.resize kernels
+(`resize_bilinear_u8`, `resize_nearest_u8`).  Image decoding stays on the host (datasets/bonai.py).
 """
 import ctypes
 
@@ -58,6 +59,28 @@ def mask_flip_pad(masks_u8, flip=None, size_divisor=32):
     out = torch.empty((G, Hp, Wp), device=masks_u8.device, dtype=torch.uint8)
     L.call('mask_flip_pad', L.ptr(masks_u8), L.ptr(out), L.ll(G), i32(H), i32(W), i32(Hp), i32(Wp),
            i32(_FLIP[flip]), L.stream())
+    return out
+
+
+def resize_bilinear_u8(img_u8, new_h, new_w):
+    """cv2.resize(INTER_LINEAR) of a uint8 [H,W,3] device tensor (`loft_resize_bilinear_u8`)."""
+    assert img_u8.is_cuda and img_u8.dtype == torch.uint8 and img_u8.dim() == 3 and \
+        img_u8.shape[2] == 3
+    img_u8 = img_u8.contiguous()
+    out = torch.empty((new_h, new_w, 3), device=img_u8.device, dtype=torch.uint8)
+    L.call('resize_bilinear_u8', L.ptr(img_u8), L.ptr(out), i32(img_u8.shape[0]),
+           i32(img_u8.shape[1]), i32(new_h), i32(new_w), L.stream())
+    return out
+
+
+def resize_nearest_u8(masks_u8, new_h, new_w):
+    """cv2.resize(INTER_NEAREST) of uint8 [G,H,W] device bitmaps (BitmapMasks.rescale)."""
+    assert masks_u8.is_cuda and masks_u8.dtype == torch.uint8 and masks_u8.dim() == 3
+    masks_u8 = masks_u8.contiguous()
+    G, H, W = (int(v) for v in masks_u8.shape)
+    out = torch.empty((G, new_h, new_w), device=masks_u8.device, dtype=torch.uint8)
+    L.call('resize_nearest_u8', L.ptr(masks_u8), L.ptr(out), L.ll(G), i32(H), i32(W), i32(new_h),
+           i32(new_w), L.stream())
     return out
 
 
@@ -163,19 +186,22 @@ class GpuTrainPipeline:
     def __call__(self, img, gt_bboxes, gt_labels, gt_masks, gt_offsets, flip=None):
         dev = self.device
         img = torch.as_tensor(img)
-        H, W = int(img.shape[0]), int(img.shape[1])
-        sf = self._scale_factor(H, W)
-        if int(W * sf + 0.5) != W or int(H * sf + 0.5) != H:
-            raise NotImplementedError(
-                f'tile {H}x{W} needs resampling to fit {self.img_scale}: this pipeline covers '
-                'tiles whose Resize is the identity (BONAI 1024^2 tiles)')
+        H0, W0 = int(img.shape[0]), int(img.shape[1])
+        sf = self._scale_factor(H0, W0)
+        W, H = int(W0 * float(sf) + 0.5), int(H0 * float(sf) + 0.5)       # mmcv.rescale_size
+        resample = (H, W) != (H0, W0)
         if flip is None:
             flip = bool(self.rng.rand() < self.flip_ratio) if self.flip_ratio is not None else False
         d = self.direction if flip else None
         img_d = img.to(dev, non_blocking=True)
+        if resample:       # not the BONAI case (1024^2 tiles at img_scale 1024): cv2.resize restated
+            img_d = resize_bilinear_u8(img_d, H, W)
         x = image_prep(img_d, self.mean, self.std, self.to_rgb, d, self.size_divisor)
+        scale4 = np.array([W / W0, H / H0, W / W0, H / H0], dtype=np.float32)
         # Resize clips the boxes to the image even at scale 1 (transforms.py:222-229)
         b = torch.as_tensor(gt_bboxes, dtype=torch.float32).to(dev, non_blocking=True).clone()
+        if resample:
+            b = b * torch.from_numpy(scale4).to(dev)
         b[:, 0::2].clamp_(0, W)
         b[:, 1::2].clamp_(0, H)
         o = torch.as_tensor(gt_offsets, dtype=torch.float32).to(dev, non_blocking=True).clone()
@@ -188,10 +214,13 @@ class GpuTrainPipeline:
                 o[:, 1] = -o[:, 1]
         m = gt_masks.to_tensor(device=dev) if isinstance(gt_masks, BitmapMasks) else \
             torch.as_tensor(gt_masks).to(dev, non_blocking=True)
-        m = mask_flip_pad(m.to(torch.uint8), d, self.size_divisor)
+        m = m.to(torch.uint8)
+        if resample:
+            m = resize_nearest_u8(m, H, W)
+        m = mask_flip_pad(m, d, self.size_divisor)
         Hp, Wp = int(x.shape[1]), int(x.shape[2])
-        meta = dict(img_shape=(H, W, 3), ori_shape=(H, W, 3), pad_shape=(Hp, Wp, 3),
-                    scale_factor=np.array([1.0, 1.0, 1.0, 1.0], dtype=np.float32), flip=bool(flip),
+        meta = dict(img_shape=(H, W, 3), ori_shape=(H0, W0, 3), pad_shape=(Hp, Wp, 3),
+                    scale_factor=scale4, flip=bool(flip),
                     flip_direction=self.direction,
                     img_norm_cfg=dict(mean=self.mean, std=self.std, to_rgb=self.to_rgb))
         labels = torch.as_tensor(gt_labels, dtype=torch.long).to(dev, non_blocking=True)

@@ -219,6 +219,15 @@ int loft_image_prep(const uint8_t* img_hwc, float* out_chw, int H, int W, int Hp
 int loft_mask_flip_pad(const uint8_t* in, uint8_t* out, long long G, int H, int W, int Hp, int Wp,
                        int flip, cudaStream_t stream);
 
+/* Resize(keep_ratio) for tiles not already at img_scale (transforms.py:186-215,244-253 ->
+ * mmcv.imrescale -> cv2.resize): uint8 HWC image with INTER_LINEAR (OpenCV's 11-bit fixed-point
+ * arithmetic restated), uint8 [G,H,W] bitmaps with INTER_NEAREST.  The BONAI configuration never
+ * takes this path (1024^2 tiles at img_scale 1024). */
+int loft_resize_bilinear_u8(const uint8_t* src_hwc, uint8_t* dst_hwc, int sh, int sw, int dh, int dw,
+                            cudaStream_t stream);
+int loft_resize_nearest_u8(const uint8_t* src, uint8_t* dst, long long G, int sh, int sw, int dh,
+                           int dw, cudaStream_t stream);
+
 /* Polygon -> bitmap: LoadAnnotations(poly2mask=True) (pipelines/loading.py:301-326,345-368), i.e.
  * pycocotools 2.0.x `decode(merge(frPyObjects(polygons, h, w)))` (common/maskApi.c rleFrPoly /
  * rleMerge / rleDecode; the dependency is not vendored in the reference tree).  xy: vertices of all

@@ -53,9 +53,8 @@ def test_pipeline_builds_from_reference_config():
         assert np.array_equal(q.mean, p.mean) and np.array_equal(q.std, p.std)
     with pytest.raises(NotImplementedError):
         GpuTrainPipeline.from_cfg([dict(type='RandomCrop', crop_size=(512, 512))], device='cpu')
-    with pytest.raises(NotImplementedError):          # a tile that would need resampling
-        p(np.zeros((2048, 2048, 3), np.uint8), np.zeros((0, 4)), np.zeros((0,)),
-          np.zeros((0, 2048, 2048), np.uint8), np.zeros((0, 2)))
+    assert p._scale_factor(2048, 2048) == 0.5 and p._scale_factor(1024, 1024) == 1.0
+    assert p._scale_factor(512, 1024) == 1.0          # keep_ratio: the long edge decides
 
 
 @pytest.mark.gpu
@@ -283,3 +282,65 @@ def test_bonai_dataset_tile_equals_cpu_pipeline(tmp_path):
         assert np.array_equal(out['gt_offsets'].cpu().numpy(), o)
         assert out['gt_labels'].tolist() == a['labels'].tolist()
         assert out['img_metas']['pad_shape'] == tuple(meta['pad_shape'])
+
+
+def test_resize_oracle_known_answers():
+    """cv2.resize restatement (PARITY UNPINNED, cv2 is not in this image): properties any correct
+    INTER_LINEAR / INTER_NEAREST has -- identity size, constants stay constant, exact 2x nearest
+    replication, exact 2x down-sampling = mean of the two centre taps, monotone ramps stay monotone."""
+    from oracle import pipeline_cpu as P
+    rng = np.random.RandomState(0)
+    img = rng.randint(0, 256, (37, 53, 3)).astype(np.uint8)
+    assert np.array_equal(P.resize_bilinear_u8(img, 53, 37), img)
+    const = np.full((20, 30, 3), 77, np.uint8)
+    assert (P.resize_bilinear_u8(const, 71, 45) == 77).all()
+    m = rng.randint(0, 2, (3, 16, 24)).astype(np.uint8)
+    up = P.resize_nearest_u8(m, 48, 32)
+    assert np.array_equal(up, m.repeat(2, axis=1).repeat(2, axis=2))
+    assert np.array_equal(P.resize_nearest_u8(m, 24, 16), m)
+    even = rng.randint(0, 256, (16, 32, 3)).astype(np.uint8)
+    dn = P.resize_bilinear_u8(even, 16, 8).astype(np.int64)
+    e = even.astype(np.int64)
+    ref = (e[0::2, 0::2] + e[0::2, 1::2] + e[1::2, 0::2] + e[1::2, 1::2] + 2) >> 2
+    assert np.abs(dn - ref).max() <= 1                 # 2x: both taps weigh 1024/2048
+    ramp = np.tile(np.arange(64, dtype=np.uint8)[None, :, None] * 4, (8, 1, 3))
+    r = P.resize_bilinear_u8(ramp, 150, 8).astype(np.int64)
+    assert (np.diff(r[0, :, 0]) >= 0).all() and r[0, 0, 0] == 0 and r[0, -1, 0] == 252
+    assert P.rescale_size(2048, 1536, (1024, 1024)) == (1024, 768)
+    assert P.rescale_size(1024, 1024, (1024, 1024)) == (1024, 1024)
+
+
+@pytest.mark.gpu
+def test_resize_kernels_bit_exact_vs_oracle_and_pipeline():
+    """`loft_resize_bilinear_u8` / `loft_resize_nearest_u8` == the CPU restatement, bit for bit, up
+    and down, odd sizes; and the whole pipeline on a tile that needs resampling == the oracle."""
+    from oracle import pipeline_cpu as P
+    from bonai_b200.datasets import GpuTrainPipeline, resize_bilinear_u8, resize_nearest_u8
+    rng = np.random.RandomState(1)
+    for (h, w), (nh, nw) in [((37, 53), (74, 106)), ((128, 96), (64, 48)), ((100, 75), (333, 250)),
+                             ((333, 250), (100, 75)), ((1536, 2048), (768, 1024)), ((5, 7), (5, 7))]:
+        img = rng.randint(0, 256, (h, w, 3)).astype(np.uint8)
+        got = resize_bilinear_u8(torch.from_numpy(img).cuda(), nh, nw).cpu().numpy()
+        assert np.array_equal(got, P.resize_bilinear_u8(img, nw, nh)), (h, w, nh, nw)
+        m = rng.randint(0, 2, (4, h, w)).astype(np.uint8)
+        gm = resize_nearest_u8(torch.from_numpy(m).cuda(), nh, nw).cpu().numpy()
+        assert np.array_equal(gm, P.resize_nearest_u8(m, nw, nh)), (h, w, nh, nw)
+    # whole pipeline, 96 x 128 tile onto img_scale (64, 64): keep_ratio -> 48 x 64
+    H, W, G = 96, 128, 5
+    img = rng.randint(0, 256, (H, W, 3)).astype(np.uint8)
+    xy = np.stack([rng.uniform(0, W - 20, G), rng.uniform(0, H - 20, G)], 1)
+    bb = np.concatenate([xy, xy + rng.uniform(4, 30, (G, 2))], 1).astype(np.float32)
+    masks = (rng.rand(G, H, W) > 0.6).astype(np.uint8)
+    offs = rng.uniform(-20, 20, (G, 2)).astype(np.float32)
+    for flip in (False, True):
+        p = GpuTrainPipeline(img_scale=(64, 64), direction='horizontal', device='cuda')
+        out = p(img, bb, np.zeros(G, np.int64), torch.from_numpy(masks), offs, flip=flip)
+        x, b, m, o, meta = P.train_pipeline(img, bb, masks, offs, flip, 'horizontal', p.mean, p.std,
+                                            img_scale=(64, 64))
+        assert out['img'].shape == (3, 64, 64) and meta['img_shape'] == (48, 64, 3)
+        assert np.array_equal(out['img'].cpu().numpy(), x)
+        assert np.array_equal(out['gt_bboxes'].cpu().numpy(), b)
+        assert np.array_equal(out['gt_masks'].to_tensor(device='cuda').cpu().numpy(), m)
+        assert np.array_equal(out['gt_offsets'].cpu().numpy(), o)
+        assert np.array_equal(out['img_metas']['scale_factor'], meta['scale_factor'])
+        assert out['img_metas']['img_shape'] == (48, 64, 3)
