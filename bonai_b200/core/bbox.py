@@ -158,9 +158,29 @@ class SamplingResult:
         self.pos_gt_labels = assign_result.labels[pos_inds] \
             if assign_result.labels is not None else None
 
+    @classmethod
+    def from_fused(cls, sel, boxes, gt_idx, is_gt, n_pos, n_neg, gt_bboxes, gt_labels):
+        """From the outputs of `loft_rcnn_sample` for one image (rows: positives, then negatives):
+        every field is a view of those rows, except the two gathers from the gt arrays."""
+        r = cls.__new__(cls)
+        n = n_pos + n_neg
+        r.pos_inds, r.neg_inds = sel[:n_pos], sel[n_pos:n]
+        r.pos_bboxes, r.neg_bboxes = boxes[:n_pos], boxes[n_pos:n]
+        r._bboxes = boxes[:n]
+        r.pos_is_gt = is_gt[:n_pos]
+        r.num_gts = gt_bboxes.shape[0]
+        r.pos_assigned_gt_inds = gt_idx[:n_pos]
+        if gt_bboxes.numel() == 0:
+            r.pos_gt_bboxes = torch.empty_like(gt_bboxes).view(-1, 4)
+        else:
+            r.pos_gt_bboxes = gt_bboxes.view(-1, 4)[r.pos_assigned_gt_inds, :]
+        r.pos_gt_labels = gt_labels[r.pos_assigned_gt_inds] if gt_labels is not None else None
+        return r
+
     @property
     def bboxes(self):
-        return torch.cat([self.pos_bboxes, self.neg_bboxes])
+        b = getattr(self, '_bboxes', None)
+        return b if b is not None else torch.cat([self.pos_bboxes, self.neg_bboxes])
 
 
 @BBOX_SAMPLERS.register_module()

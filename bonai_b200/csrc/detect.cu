@@ -422,6 +422,183 @@ nms_compact_kernel(const unsigned long long* __restrict__ ws, long long ws_strid
   if (t == 0) num_keep[b] = min(s_base, max_keep);
 }
 
+// ---------------------------------------------------------------- RCNN RoI sampling
+// BaseSampler.sample + RandomSampler (core/bbox/samplers/base_sampler.py:34-101,
+// random_sampler.py:31-75) for one image per block, after MaxIoUAssigner has labelled the
+// proposals: candidates are [gt boxes (add_gt_as_proposals), proposals]; up to num_pos positives
+// (assigned gt > 0) and then num - (#positives taken) negatives (assigned gt == 0) are drawn
+// uniformly WITHOUT replacement and emitted in ascending candidate order (the reference's
+// `.unique()` sorts them), positives first.  Replaces ~120 ATen launches per step
+// (cat / where / nonzero / randperm / sort / index chains issued one by one from Python).
+// A uniform subset of size m = the m smallest of independent random 64-bit keys (hash of a seed
+// and the candidate index, made unique by the index in the low bits): radix select of the m-th
+// smallest key, then an ordered compaction of everything not above it.
+constexpr int kSampThreads = 1024;
+constexpr int kSampPer = 4;                       // candidates per thread: n <= 4096
+constexpr int kSampMaxOut = 1024;
+
+__device__ __forceinline__ unsigned samp_hash(unsigned long long seed, unsigned j) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(j + 1u);   // splitmix64
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (unsigned)(z >> 32);
+}
+
+// m-th smallest (m >= 1) of the keys of class `cls` among this block's candidates; keys are
+// unique.  Threads hold their candidates' (key, class) in registers.
+__device__ unsigned long long samp_select(const unsigned long long (&key)[kSampPer],
+                                          const int (&kls)[kSampPer], int cls, int m,
+                                          unsigned* s_hist, unsigned long long* s_prefix,
+                                          int* s_want) {
+  const int t = threadIdx.x;
+  if (t == 0) {
+    *s_prefix = 0ull;
+    *s_want = m;
+  }
+  __syncthreads();
+  for (int pass = 0; pass < 8; ++pass) {           // 8 bits per pass, most significant first
+    for (int i = t; i < 256; i += kSampThreads) s_hist[i] = 0u;
+    __syncthreads();
+    const int sh = 56 - 8 * pass;
+    const unsigned long long prefix = *s_prefix;
+    const unsigned long long pmask = pass == 0 ? 0ull : (~0ull << (sh + 8));
+#pragma unroll
+    for (int k = 0; k < kSampPer; ++k)
+      if (kls[k] == cls && (key[k] & pmask) == prefix)
+        atomicAdd(&s_hist[(unsigned)(key[k] >> sh) & 255u], 1u);
+    __syncthreads();
+    if (t == 0) {
+      int want = *s_want, d = 0;
+      unsigned c = s_hist[0];
+      while ((int)c < want) {                      // walk up from the smallest digit
+        want -= (int)c;
+        ++d;
+        c = s_hist[d];
+      }
+      *s_prefix = prefix | ((unsigned long long)d << sh);
+      *s_want = want;
+    }
+    __syncthreads();
+  }
+  return *s_prefix;                                // all 64 bits fixed: the m-th smallest key
+}
+
+__global__ void __launch_bounds__(kSampThreads)
+rcnn_sample_kernel(const float* __restrict__ props, long long prop_stride, int K, int prop_ld,
+                   const int* __restrict__ num_valid, const long long* __restrict__ prop_gt_inds,
+                   const float* __restrict__ gts, const int* __restrict__ gt_off, int num,
+                   int num_pos_max, unsigned long long seed, long long* __restrict__ sel,
+                   float* __restrict__ out_boxes, long long* __restrict__ out_gt,
+                   unsigned char* __restrict__ out_isgt, int* __restrict__ cnt) {
+  __shared__ unsigned s_hist[256];
+  __shared__ unsigned long long s_prefix;
+  __shared__ int s_want;
+  __shared__ int s_warp[kSampThreads / 32];
+  __shared__ int s_tot[2];
+  const int img = blockIdx.x, t = threadIdx.x;
+  const int g0 = gt_off[img], G = gt_off[img + 1] - g0;
+  const int nv = num_valid ? min(num_valid[img], K) : K;
+  const int n = G + K;
+  const float* pr = props + (long long)img * prop_stride;
+  const long long* pg = prop_gt_inds + (long long)img * K;
+  // candidate j = t * kSampPer + k (consecutive per thread: the compaction keeps index order)
+  unsigned long long key[kSampPer];
+  int kls[kSampPer];                               // 1 positive, 0 negative, -1 neither
+  long long gti[kSampPer];
+  int npos = 0, nneg = 0;
+#pragma unroll
+  for (int k = 0; k < kSampPer; ++k) {
+    const int j = t * kSampPer + k;
+    kls[k] = -1;
+    gti[k] = -1;
+    key[k] = ~0ull;
+    if (j < n) {
+      long long gi;
+      if (j < G) gi = j + 1;                       // a gt box is assigned to itself
+      else gi = (j - G < nv) ? (G > 0 ? pg[j - G] : 0) : -1;     // padding rows are ignored
+      gti[k] = gi;
+      kls[k] = gi > 0 ? 1 : (gi == 0 ? 0 : -1);
+      key[k] = ((unsigned long long)samp_hash(seed + (unsigned long long)img * 0x100000001B3ull,
+                                              (unsigned)j) << 32) | (unsigned)j;
+      npos += kls[k] == 1;
+      nneg += kls[k] == 0;
+    }
+  }
+  // block totals of both classes
+  int v = (npos << 16) | nneg;                     // n <= 4096: both fit in 16 bits
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((t & 31) == 0) s_warp[t >> 5] = v;
+  __syncthreads();
+  if (t == 0) {
+    int a = 0;
+    for (int w = 0; w < kSampThreads / 32; ++w) a += s_warp[w];
+    s_tot[0] = a >> 16;
+    s_tot[1] = a & 0xffff;
+  }
+  __syncthreads();
+  const int tot_pos = s_tot[0], tot_neg = s_tot[1];
+  const int take_pos = min(tot_pos, num_pos_max);
+  const int take_neg = min(tot_neg, num - take_pos);
+  unsigned long long thr_pos = ~0ull, thr_neg = ~0ull;          // take everything of the class
+  if (take_pos < tot_pos) thr_pos = samp_select(key, kls, 1, take_pos, s_hist, &s_prefix, &s_want);
+  __syncthreads();
+  if (take_neg < tot_neg && take_neg > 0)
+    thr_neg = samp_select(key, kls, 0, take_neg, s_hist, &s_prefix, &s_want);
+  __syncthreads();
+  // ordered compaction: positives to [0, take_pos), negatives to [take_pos, take_pos + take_neg)
+  int fp[kSampPer], fn[kSampPer], cp = 0, cn = 0;
+#pragma unroll
+  for (int k = 0; k < kSampPer; ++k) {
+    fp[k] = kls[k] == 1 && take_pos > 0 && key[k] <= thr_pos;
+    fn[k] = kls[k] == 0 && take_neg > 0 && key[k] <= thr_neg;
+    cp += fp[k];
+    cn += fn[k];
+  }
+  int pv = (cp << 16) | cn, incl = pv;             // inclusive warp scan of the packed counts
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((t & 31) >= o) incl += u;
+  }
+  if ((t & 31) == 31) s_warp[t >> 5] = incl;
+  __syncthreads();
+  if (t < 32) {
+    int w = s_warp[t], wi = w;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, wi, o);
+      if (t >= o) wi += u;
+    }
+    s_warp[t] = wi - w;                            // exclusive prefix of the warp totals
+  }
+  __syncthreads();
+  const int excl = incl - pv + s_warp[t >> 5];
+  int op = excl >> 16, on = take_pos + (excl & 0xffff);
+  long long* sel_i = sel + (long long)img * num;
+  float* ob = out_boxes + (long long)img * num * 4;
+  long long* og = out_gt + (long long)img * num;
+  unsigned char* oi = out_isgt + (long long)img * num;
+#pragma unroll
+  for (int k = 0; k < kSampPer; ++k) {
+    if (!(fp[k] || fn[k])) continue;
+    const int j = t * kSampPer + k;
+    const int o = fp[k] ? op++ : on++;
+    float4 b;
+    if (j < G) b = reinterpret_cast<const float4*>(gts)[g0 + j];
+    else {
+      const float* q = pr + (long long)(j - G) * prop_ld;
+      b = make_float4(q[0], q[1], q[2], q[3]);
+    }
+    sel_i[o] = j;
+    reinterpret_cast<float4*>(ob)[o] = b;
+    og[o] = fp[k] ? gti[k] - 1 : -1;
+    oi[o] = j < G ? 1 : 0;
+  }
+  if (t == 0) {
+    cnt[img * 2 + 0] = take_pos;
+    cnt[img * 2 + 1] = take_neg;
+  }
+}
+
 // ---------------------------------------------------------------- soft-NMS (linear), test time
 // mmcv.ops.soft_nms(method='linear') [mmcv-full 1.0.5, CPU-only there]: repeatedly select the
 // highest-scoring live box, decay every other live box j by (1 - iou) if iou > thr, drop boxes whose
@@ -870,6 +1047,33 @@ int loft_nms_segmented(const float* boxes, const int* seg_off, int L, const long
   nms_compact_kernel<<<B, 1024, 0, stream>>>(ws, stride_w, flag_off, order, n, max_keep, keep,
                                              num_keep);
   LOFT_CUDA_LAUNCH_CHECK("nms_compact");
+  return LOFT_OK;
+}
+
+// RoI sampling of the RCNN stage for a batch of images, one block each (see rcnn_sample_kernel).
+// props [B, K, prop_ld] (box in the first 4 columns), num_valid [B] (rows >= it are padding; NULL =
+// all K), prop_gt_inds [B, K] from loft_iou_assign on the proposals, gts = all images' gt boxes
+// [sum G, 4] with gt_off [B+1].  Outputs per image, `num` slots: sel (candidate index: gt boxes
+// first, then proposals), out_boxes, out_gt (assigned gt index or -1), out_isgt, cnt [B,2] =
+// (#positives, #negatives) -- positives first, each group in ascending candidate order.
+int loft_rcnn_sample(const float* props, long long prop_stride, int K, int prop_ld,
+                     const int* num_valid, const long long* prop_gt_inds, const float* gts,
+                     const int* gt_off, int B, int max_gt, int num, int num_pos_max,
+                     unsigned long long seed, long long* sel, float* out_boxes, long long* out_gt,
+                     unsigned char* out_isgt, int* cnt, cudaStream_t stream) {
+  LOFT_CHECK_ARG(props && prop_gt_inds && gt_off && sel && out_boxes && out_gt && out_isgt && cnt,
+                 "rcnn_sample: null pointer");
+  LOFT_CHECK_SHAPE(B >= 0 && K >= 0 && max_gt >= 0 && K + max_gt <= kSampThreads * kSampPer &&
+                       num > 0 && num <= kSampMaxOut && num_pos_max >= 0 && num_pos_max <= num,
+                   "rcnn_sample: bad sizes B=%d K=%d max_gt=%d num=%d (K + max_gt <= %d)", B, K,
+                   max_gt, num, kSampThreads * kSampPer);
+  LOFT_CHECK_ARG(max_gt == 0 || (gts && (reinterpret_cast<uintptr_t>(gts) & 15) == 0),
+                 "rcnn_sample: gt boxes must be 16-byte aligned");
+  if (B == 0) return LOFT_OK;
+  rcnn_sample_kernel<<<B, kSampThreads, 0, stream>>>(props, prop_stride, K, prop_ld, num_valid,
+                                                     prop_gt_inds, gts, gt_off, num, num_pos_max,
+                                                     seed, sel, out_boxes, out_gt, out_isgt, cnt);
+  LOFT_CUDA_LAUNCH_CHECK("rcnn_sample");
   return LOFT_OK;
 }
 

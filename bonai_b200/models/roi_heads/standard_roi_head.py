@@ -1,5 +1,6 @@
 """BaseRoIHead / StandardRoIHead (mmdet/models/roi_heads/base_roi_head.py:8-154,
 standard_roi_head.py:10-290): assign + sample per image, bbox branch, mask branch."""
+import os
 from abc import ABCMeta
 
 import torch
@@ -79,6 +80,8 @@ class StandardRoIHead(BaseRoIHead):
             gt_bboxes_ignore = [None for _ in range(num_imgs)]
         from ...core.bbox import RandomSampler
         if type(self.bbox_sampler) is RandomSampler and self.bbox_sampler.neg_pos_ub < 0:
+            if self._fused_sampling_ok(proposal_list, gt_bboxes, gt_bboxes_ignore):
+                return self._assign_and_sample_fused(proposal_list, gt_bboxes, gt_labels)
             return self._assign_and_sample_batched(proposal_list, gt_bboxes, gt_labels,
                                                    gt_bboxes_ignore)
         sampling_results = []
@@ -88,6 +91,83 @@ class StandardRoIHead(BaseRoIHead):
             sampling_results.append(self.bbox_sampler.sample(
                 assign_result, proposal_list[i], gt_bboxes[i], gt_labels[i]))
         return sampling_results
+
+    def _fused_sampling_ok(self, proposal_list, gt_bboxes, gt_bboxes_ignore):
+        """The one-launch sampler covers the LOFT configuration: MaxIoUAssigner without ignore
+        regions, RandomSampler(add_gt_as_proposals) whose `random_choice` has not been replaced
+        (parity tests inject the oracle's draws through it), equally sized proposal blocks."""
+        from ...core.bbox import MaxIoUAssigner
+        smp = self.bbox_sampler
+        if os.environ.get('LOFT_FUSED_SAMPLER', '1') == '0' or 'random_choice' in vars(smp):
+            return False
+        if type(self.bbox_assigner) is not MaxIoUAssigner or not smp.add_gt_as_proposals:
+            return False
+        if any(g is not None and g.numel() > 0 for g in gt_bboxes_ignore):
+            return False
+        K = proposal_list[0].shape[0]
+        if any(p.shape[0] != K or not p.is_cuda for p in proposal_list):
+            return False
+        return K + max(int(g.shape[0]) for g in gt_bboxes) <= 4096 and smp.num <= 1024
+
+    def _assign_and_sample_fused(self, proposal_list, gt_bboxes, gt_labels):
+        """assign + RandomSampler.sample for every image in three launches per image + one for
+        the batch (`loft_iou_assign`, `loft_rcnn_sample`) and ONE host read-back (the per-image
+        positive / negative counts); same candidate sets and sampling law as the reference
+        (base_sampler.py:34-101, random_sampler.py:31-75), own random stream."""
+        import ctypes
+        from ... import _lib as L
+        from ...core.bbox import SamplingResult
+        i32 = ctypes.c_int
+        asg, smp = self.bbox_assigner, self.bbox_sampler
+        n_img = len(proposal_list)
+        dev = proposal_list[0].device
+        K, ld = int(proposal_list[0].shape[0]), int(proposal_list[0].shape[1])
+        base = proposal_list[0]
+        step = K * ld * base.element_size()
+        if all(p.is_contiguous() and p.data_ptr() == base.data_ptr() + i * step
+               for i, p in enumerate(proposal_list)):
+            props_ptr = L.ptr(base)                      # slices of one [B,K,5] block: no copy
+        else:
+            stacked = torch.stack([p.contiguous() for p in proposal_list])
+            props_ptr = L.ptr(stacked)
+        nvs = [getattr(p, '_loft_num_valid', None) for p in proposal_list]
+        nv = torch.stack([v.reshape(()) for v in nvs]).to(torch.int32) \
+            if all(v is not None for v in nvs) else None
+        gts = [g[:, :4].contiguous().float() for g in gt_bboxes]
+        Gs = [int(g.shape[0]) for g in gts]
+        gt_all = torch.cat(gts) if sum(Gs) else torch.zeros((1, 4), device=dev)
+        offs = [0]
+        for g in Gs:
+            offs.append(offs[-1] + g)
+        gt_off = torch.tensor(offs, dtype=torch.int32).to(dev, non_blocking=True)
+        gt_inds = torch.empty((n_img, K), dtype=torch.long, device=dev)
+        max_ov = torch.empty((n_img, K), dtype=torch.float32, device=dev)
+        for i in range(n_img):
+            if Gs[i] == 0 or K == 0:
+                continue
+            boxes = proposal_list[i][:, :4].contiguous()
+            ws_bytes = int(L.lib().loft_iou_assign_workspace(L.ll(K), i32(Gs[i])))
+            ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+            L.call('iou_assign', L.ptr(boxes), L.ll(K), L.ptr(gts[i]), i32(Gs[i]),
+                   L.f32(asg.pos_iou_thr), L.f32(asg.neg_iou_thr), L.f32(asg.min_pos_iou),
+                   i32(asg.match_low_quality), L.ptr(gt_inds[i]), L.ptr(max_ov[i]), L.ptr(ws),
+                   ctypes.c_size_t(ws_bytes), L.stream())
+        num = int(smp.num)
+        sel = torch.empty((n_img, num), dtype=torch.long, device=dev)
+        out_boxes = torch.empty((n_img, num, 4), dtype=torch.float32, device=dev)
+        out_gt = torch.empty((n_img, num), dtype=torch.long, device=dev)
+        out_isgt = torch.empty((n_img, num), dtype=torch.uint8, device=dev)
+        cnt = torch.empty((n_img, 2), dtype=torch.int32, device=dev)
+        self._sample_calls = getattr(self, '_sample_calls', 0) + 1
+        seed = (int(torch.initial_seed()) * 1000003 + self._sample_calls) & ((1 << 64) - 1)
+        L.call('rcnn_sample', props_ptr, L.ll(K * ld), i32(K), i32(ld), L.ptr(nv), L.ptr(gt_inds),
+               L.ptr(gt_all), L.ptr(gt_off), i32(n_img), i32(max(Gs)), i32(num),
+               i32(int(smp.num * smp.pos_fraction)), ctypes.c_ulonglong(seed), L.ptr(sel),
+               L.ptr(out_boxes), L.ptr(out_gt), L.ptr(out_isgt), L.ptr(cnt), L.stream())
+        counts = cnt.tolist()                                                  # the only sync
+        return [SamplingResult.from_fused(sel[i], out_boxes[i], out_gt[i], out_isgt[i],
+                                          counts[i][0], counts[i][1], gt_bboxes[i], gt_labels[i])
+                for i in range(n_img)]
 
     def _assign_and_sample_batched(self, proposal_list, gt_bboxes, gt_labels, gt_bboxes_ignore):
         """Same result as assign + RandomSampler.sample per image (base_sampler.py:34-101), but

@@ -171,6 +171,18 @@ int loft_rpn_decode(const float* head_out, int ld, int reg_off, const long long*
                     int fw, int A, const float* base_anchors, float stride, float max_ratio,
                     float img_h, float img_w, float* boxes_out, int batch, long long head_stride,
                     long long idx_stride, long long out_stride, cudaStream_t stream);
+/* RCNN RoI sampling: BaseSampler.sample + RandomSampler (samplers/base_sampler.py:34-101,
+ * random_sampler.py:31-75) with add_gt_as_proposals, one block per image, after loft_iou_assign.
+ * Candidates = [gt boxes, proposals]; up to num_pos_max positives, then negatives up to `num` in
+ * total, each drawn uniformly without replacement (counter-based hash of `seed`), emitted in
+ * ascending candidate order, positives first.  props [B,K,prop_ld], num_valid [B] or NULL,
+ * prop_gt_inds [B,K], gts [sum G,4] + gt_off [B+1] (device), max_gt = largest G (host).  Outputs:
+ * sel / out_gt [B,num] i64, out_boxes [B,num,4], out_isgt [B,num] u8, cnt [B,2] i32. */
+int loft_rcnn_sample(const float* props, long long prop_stride, int K, int prop_ld,
+                     const int* num_valid, const long long* prop_gt_inds, const float* gts,
+                     const int* gt_off, int B, int max_gt, int num, int num_pos_max,
+                     unsigned long long seed, long long* sel, float* out_boxes, long long* out_gt,
+                     unsigned char* out_isgt, int* cnt, cudaStream_t stream);
 size_t loft_nms_workspace(int n);
 int loft_nms_sorted(const float* boxes, const long long* idxs, int B, int n, float iou_thr,
                     int max_keep, long long* keep, int* num_keep, void* workspace, size_t ws_bytes,
