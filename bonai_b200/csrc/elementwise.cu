@@ -308,6 +308,39 @@ __global__ void im2col_nchw_kernel(const float* __restrict__ x, float* __restric
   }
 }
 
+// Operand of the direct 7x7/2 stem conv (loft_stem_conv7x7): the NCHW fp32 image as a zero-padded
+// NHWC4 tensor, TF32-rounded, with its rows split into an even and an odd plane:
+//   xp[n][par][hh][wp][4],  padded row 2*hh + par = iy + 3,  padded column wp = ix + 3,
+//   Hh = ceil((H + 6) / 2),  Wp = W + 8.
+// For one kernel row the 8 taps x 4 channels an output pixel reads (tap 7 and channel 3 carry zero
+// weights) are then 128 contiguous bytes that start every 32 bytes along the row: a TMA view with
+// overlapping strides delivers the im2col rows without materialising them (the im2col matrix of
+// the 1024^2 stem was 310 MB written and read back per step, 0.36 ms for the write alone).
+__global__ void stem_pack_kernel(const float* __restrict__ x, float4* __restrict__ xp, int N, int H,
+                                 int W, int C, int Hh, int Wp) {
+  const long long total = (long long)N * 2 * Hh * Wp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int wp = (int)(i % Wp);
+    long long t = i / Wp;
+    const int hh = (int)(t % Hh);
+    t /= Hh;
+    const int par = (int)(t & 1);
+    const int n = (int)(t >> 1);
+    const int iy = 2 * hh + par - 3, ix = wp - 3;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+      const float* src = x + ((long long)n * C * H + iy) * W + ix;
+      const long long plane = (long long)H * W;
+      v.x = tf32_rna(src[0]);
+      if (C > 1) v.y = tf32_rna(src[plane]);
+      if (C > 2) v.z = tf32_rna(src[2 * plane]);
+      if (C > 3) v.w = tf32_rna(src[3 * plane]);
+    }
+    xp[i] = v;
+  }
+}
+
 // dx[n,h,w,c] = sum over taps of dcol[(n,ho,wo),(r,s,c)] (gather form, no atomics), float4 over c
 __global__ void col2im_v4_kernel(const float4* __restrict__ dcol, float4* __restrict__ dx,
                                  const float4* __restrict__ mask, int N, int H, int W, int C4, int kh,
@@ -653,6 +686,18 @@ int loft_im2col(const float* x, float* col, int N, int H, int W, int C, int kh, 
         stride, pad, Ho, Wo, kh * kw * C / 4, Kpad / 4);
   }
   LOFT_CUDA_LAUNCH_CHECK("im2col");
+  return LOFT_OK;
+}
+
+int loft_stem_pack(const float* x, float* xp, int N, int H, int W, int C, cudaStream_t stream) {
+  LOFT_CHECK_ARG(x && xp, "stem_pack: null pointer");
+  LOFT_CHECK_SHAPE(C >= 1 && C <= 4, "stem_pack: C=%d must be 1..4", C);
+  const int Hh = (H + 7) / 2, Wp = W + 8;
+  const long long total = (long long)N * 2 * Hh * Wp;
+  if (total == 0) return LOFT_OK;
+  stem_pack_kernel<<<grid_for(total, kT, 148 * 32), kT, 0, stream>>>(
+      x, reinterpret_cast<float4*>(xp), N, H, W, C, Hh, Wp);
+  LOFT_CUDA_LAUNCH_CHECK("stem_pack");
   return LOFT_OK;
 }
 

@@ -64,6 +64,8 @@ struct GemmParams {
   int tn, th, tw;   // pixel tile (conv modes)
   int tiles_h, tiles_w;
   int cchunks;      // Cin/32 (FPROP_CONV) or Cout/32 (DGRAD_CONV): k-chunks per tap
+  int stem;         // FPROP_CONV over the packed stem image (loft_stem_conv7x7): k-block = kernel
+                    // row kh, read from plane 2n + (kh & 1) at half-row h + (kh >> 1)
   int ntaps;        // 9 or 1
   int P;            // total pixels (2D modes)
   int Cm;           // number of valid channels on the M side (Cout for fprop, Cin for dgrad)
@@ -290,7 +292,10 @@ loft_gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a,
                 if (!(p.dbg_skip & 2)) tma_load_2d<kPair>(sb, &tmap_b, fb, kb * kKB, pt * p.n_half);
               } else if constexpr (kM == FPROP_CONV) {
                 tma_load_3d<kPair>(sa, &tmap_a, fb, kb * kKB, ct * kBlockC, grp);
-                tma_load_4d<kPair>(sb, &tmap_b, fb, ch * kKB, w0 + dw, h0 + dh, n0);
+                if (p.stem)
+                  tma_load_4d<kPair>(sb, &tmap_b, fb, 0, w0, h0 + (tp >> 1), 2 * n0 + (tp & 1));
+                else
+                  tma_load_4d<kPair>(sb, &tmap_b, fb, ch * kKB, w0 + dw, h0 + dh, n0);
               } else if constexpr (kM == DGRAD_2D) {
                 // A view: (32 cin, Cout rows, Cin/32 chunks); k-block = 32 cout rows
                 tma_load_3d<kPair>(sa, &tmap_a, fb, 0, kb * kKB, ct * (kBlockC / 32));
@@ -1541,6 +1546,67 @@ int loft_conv3x3_fprop_grouped(const float* x, const float* w, float* y, int N, 
     uint64_t s[3] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4};
     uint32_t b[4] = {kKB, (uint32_t)p.tw, (uint32_t)p.th, (uint32_t)p.tn};
     int r = make_tmap(&tb, 4, x, d, s, b);
+    if (r) return r;
+  }
+  return launch(ta, tb, p, stream);
+}
+
+// 7x7 / stride 2 / pad 3 conv of an image of <= 4 channels (the ResNet stem, resnet.py:525-571)
+// WITHOUT an im2col matrix.  xp is the packed image of loft_stem_pack (zero-padded NHWC4, even and
+// odd rows in separate planes); w is [Cout][7][8][4] (kernel row, tap padded 7 -> 8, channel
+// padded to 4; the pads are zero).  For kernel row kh the 32 k-elements (8 taps x 4 channels) of
+// output pixel (oy, ox) are the 128 contiguous bytes at padded row 2*oy + kh, column 2*ox: the B
+// operand is a 4-D tensor map (32 floats, ox with a 32-byte stride, half-row, plane) whose second
+// stride OVERLAPS the first extent -- a sliding window the TMA delivers straight into the swizzled
+// operand stage (tools/probes/tma_overlap_probe.cu: accepted by cuTensorMapEncodeTiled and exact).
+// 7 k-blocks per tile; fused epilogue as everywhere else.
+int loft_stem_conv7x7(const float* xp, const float* w, float* y, int N, int H, int W, int Cout,
+                      const loft_epilogue_t* epi, cudaStream_t stream) {
+  LOFT_CHECK_ARG(xp && w && y, "stem_conv7x7: null pointer");
+  LOFT_CHECK_SHAPE(N >= 0 && H >= 1 && W >= 1 && Cout >= 1, "stem_conv7x7: bad shape");
+  if (N == 0) return LOFT_OK;
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const int Hh = (H + 7) / 2, Wp = W + 8;
+  GemmParams p{};
+  p.mode = FPROP_CONV;
+  p.stem = 1;
+  p.groups = 1;
+  p.group_n = N;
+  p.splits = 1;
+  p.nct = loft_cdiv(Cout, kBlockC);
+  // one image per tile (the planes of consecutive images are not consecutive rows of the view)
+  p.tn = 1;
+  p.tw = Wo < kMaxN ? Wo : kMaxN;
+  p.th = kMaxN / p.tw < Ho ? kMaxN / p.tw : Ho;
+  p.n_mma = round16(p.th * p.tw);
+  p.tiles_w = loft_cdiv(Wo, p.tw);
+  p.tiles_h = loft_cdiv(Ho, p.th);
+  p.npt = p.tiles_w * p.tiles_h * N;
+  p.num_tiles = p.nct * p.npt;
+  p.tx_bytes = kABytes + p.th * p.tw * kKB * 4;
+  p.cchunks = 1;
+  p.ntaps = 7;
+  p.num_kb = 7;
+  p.kb_per_split = p.num_kb;
+  p.N = N;
+  p.H = Ho;
+  p.W = Wo;
+  p.Cm = Cout;
+  fill_descs(p, false, false);
+  set_epilogue(p, epi, y, Cout);
+  CUtensorMap ta, tb;
+  {
+    uint64_t d[3] = {(uint64_t)7 * kKB, (uint64_t)Cout, 1};
+    uint64_t s[2] = {(uint64_t)7 * kKB * 4, (uint64_t)7 * kKB * 4 * Cout};
+    uint32_t b[3] = {kKB, kBlockC, 1};
+    int r = make_tmap(&ta, 3, w, d, s, b);
+    if (r) return r;
+  }
+  {
+    uint64_t d[4] = {kKB, (uint64_t)Wo, (uint64_t)Hh, (uint64_t)2 * N};
+    uint64_t s[3] = {32, (uint64_t)Wp * 16, (uint64_t)Hh * Wp * 16};
+    uint32_t b[4] = {kKB, (uint32_t)p.tw, (uint32_t)p.th, 1};
+    int r = make_tmap(&tb, 4, xp, d, s, b);
     if (r) return r;
   }
   return launch(ta, tb, p, stream);

@@ -206,13 +206,12 @@ class ResNet(nn.Module):
         import ctypes
         w = self.conv1.weight                          # [64,3,7,7], physically [64,7,7,3]
         store.fold_bn(w, self.bn1)
-        K = w.shape[1] * 49
-        self._kpad = (K + 3) // 4 * 4
-        self._stem_w = torch.zeros((w.shape[0], self._kpad), device=store.device)
+        assert w.shape[1] <= 4, 'the direct stem conv packs the image as NHWC4'
+        self._stem_w = torch.zeros((w.shape[0], M.STEM_K), device=store.device)
 
         def build():
-            L.call('copy2d', L.ptr(w._loft.w), L.ll(K), L.ptr(self._stem_w), L.ll(self._kpad),
-                   L.ll(w.shape[0]), ctypes.c_int(K), ctypes.c_int(0), ctypes.c_int(1), L.stream())
+            # the TF32 copy is logically [Cout,C,7,7] over [Cout,7,7,C] memory (engine.ParamStore)
+            M.pack_stem_weight(w._loft.w.permute(0, 2, 3, 1), self._stem_w)
 
         from ...engine import Packed
         store.add_packed(Packed(self._stem_w, None, None, None, build, lambda: None))
@@ -220,7 +219,7 @@ class ResNet(nn.Module):
     def forward(self, x):
         bn = self.bn1._loft_bn
         with torch.no_grad():
-            x = M.stem_conv(x, self._stem_w, self._kpad, None, bn.shift)
+            x = M.stem_conv(x, self._stem_w, None, bn.shift)
             x = M.maxpool3x3s2(x)
         outs = []
         for i, name in enumerate(self.res_layers):

@@ -21,22 +21,41 @@ def maxpool3x3s2(x):
     return y
 
 
-def stem_conv(img, w_packed, kpad, scale, shift):
-    """7x7/2 pad-3 conv (3->64) + BN-eval + ReLU of the frozen stem (resnet.py:525-571): im2col
-    straight from the NCHW fp32 image, then one tcgen05 GEMM with the affine+ReLU epilogue."""
+STEM_K = 7 * 8 * 4          # k extent of the packed stem weight: 7 kernel rows x (8 taps x 4 channels)
+
+
+def pack_stem_weight(w_khwc, out=None):
+    """[Cout,7,7,C<=4] (kernel row, tap, channel) -> [Cout, 224] = [Cout][7][8][4], zero pads: the
+    K layout loft_stem_conv7x7 reads (one 32-float k-block per kernel row)."""
+    Co, kh, kw, C = w_khwc.shape
+    assert kh == 7 and kw == 7 and C <= 4
+    if out is None:
+        out = torch.zeros((Co, STEM_K), device=w_khwc.device, dtype=torch.float32)
+    out.view(Co, 7, 8, 4)[:, :, :7, :C].copy_(w_khwc)
+    return out
+
+
+def stem_packed_shape(N, H, W):
+    """Shape of the packed stem image loft_stem_pack writes (see include/loft_b200.h)."""
+    return (N, 2, (H + 7) // 2, W + 8, 4)
+
+
+def stem_conv(img, w_packed, scale, shift, xp=None):
+    """7x7/2 pad-3 conv (3->64) + BN-eval + ReLU of the frozen stem (resnet.py:525-571), direct:
+    the NCHW fp32 image is packed once (zero-padded NHWC4, TF32-rounded) and one tcgen05 GEMM
+    reads its sliding windows through an overlapping-stride tensor map -- no im2col matrix."""
     N, C, H, W = img.shape
-    Ho, Wo = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
     img = img.contiguous().float()
-    col = torch.empty((N * Ho * Wo, kpad), device=img.device, dtype=torch.float32)
+    if xp is None:
+        xp = torch.empty(stem_packed_shape(N, H, W), device=img.device, dtype=torch.float32)
     st = L.stream()
-    L.call('im2col', L.ptr(img), L.ptr(col), i32(N), i32(H), i32(W), i32(C), i32(7), i32(7), i32(2),
-           i32(3), i32(kpad), i32(1), st)
+    L.call('stem_pack', L.ptr(img), L.ptr(xp), i32(N), i32(H), i32(W), i32(C), st)
     Cout = w_packed.shape[0]
     y = new_nhwc(N, Cout, Ho, Wo, img.device)
     e = L.make_epilogue(scale=scale, shift=shift, relu=True, round_out=True)
-    L.call('gemm_fprop', L.ptr(col), L.ptr(w_packed), L.ptr(y.permute(0, 2, 3, 1)),
-           L.ll(N * Ho * Wo), i32(kpad), i32(Cout), L.ll(kpad), L.ll(kpad), L.ll(Cout), i32(Ho),
-           i32(Wo), ctypes.byref(e), st)
+    L.call('stem_conv7x7', L.ptr(xp), L.ptr(w_packed), L.ptr(y.permute(0, 2, 3, 1)), i32(N), i32(H),
+           i32(W), i32(Cout), ctypes.byref(e), st)
     return y
 
 

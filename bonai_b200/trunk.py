@@ -21,6 +21,7 @@ import torch
 from torch.autograd import Function
 
 from . import _lib as L
+from .ops.misc import stem_packed_shape
 
 i32 = ctypes.c_int
 
@@ -182,15 +183,15 @@ class _Program:
         bb, neck, rpn = m.backbone, m.neck, m.rpn_head
         N, H, W = self.N, self.H, self.W
         with self.fwd:
-            # frozen stem: im2col from the NCHW image + GEMM (+folded BN, ReLU) + 3x3/2 max-pool
-            Ho, Wo = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
-            kpad = bb._kpad
-            col = self.buf(N * Ho * Wo, kpad)
-            L.call('im2col', L.ptr(self.img), L.ptr(col), i32(N), i32(H), i32(W), i32(3), i32(7),
-                   i32(7), i32(2), i32(3), i32(kpad), i32(1), L.stream())
+            # frozen stem: pack the NCHW image (padded NHWC4) + direct 7x7/2 conv GEMM (+folded BN,
+            # ReLU) over its sliding windows + 3x3/2 max-pool
+            Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+            xp = self.buf(*stem_packed_shape(N, H, W))
+            L.call('stem_pack', L.ptr(self.img), L.ptr(xp), i32(N), i32(H), i32(W), i32(3), L.stream())
             c1 = self.buf(N, Ho, Wo, bb._stem_w.shape[0])
-            self.gemm_f(col, bb._stem_w, c1, N * Ho * Wo, kpad, c1.shape[-1], Ho, Wo,
-                        shift=bb.bn1._loft_bn.shift, relu=True, round_out=True)
+            L.call('stem_conv7x7', L.ptr(xp), L.ptr(bb._stem_w), L.ptr(c1), i32(N), i32(H), i32(W),
+                   i32(c1.shape[-1]),
+                   _epi(shift=bb.bn1._loft_bn.shift, relu=True, round_out=True), L.stream())
             Hp, Wp = (Ho - 1) // 2 + 1, (Wo - 1) // 2 + 1
             x = self.buf(N, Hp, Wp, c1.shape[-1])
             L.call('maxpool3x3s2', L.ptr(c1), L.ptr(x), i32(N), i32(Ho), i32(Wo),

@@ -129,6 +129,14 @@ int loft_act_bwd(const float* dy, const float* y, const float* z, const float* s
                  float* dbeta, long long P, int C, int relu, cudaStream_t stream);
 int loft_im2col(const float* x, float* col, int N, int H, int W, int C, int kh, int kw, int stride,
                 int pad, int Kpad, int nchw_input, cudaStream_t stream);
+/* direct 7x7/2 stem conv (replaces nn.Conv2d(3, 64, 7, 2, 3) + eval BN + ReLU of
+ * mmdet/models/backbones/resnet.py:525-571,623-630 with no im2col matrix):
+ * loft_stem_pack writes the NCHW fp32 image as xp[N][2][(H+7)/2][W+8][4] (zero-padded NHWC4,
+ * TF32-rounded, even / odd padded rows in separate planes); loft_stem_conv7x7 reads it through an
+ * overlapping-stride tensor map; w is [Cout][7][8][4] with zero pads, y is NHWC [N][Ho][Wo][Cout] */
+int loft_stem_pack(const float* x, float* xp, int N, int H, int W, int C, cudaStream_t stream);
+int loft_stem_conv7x7(const float* xp, const float* w, float* y, int N, int H, int W, int Cout,
+                      const loft_epilogue_t* epi, cudaStream_t stream);
 int loft_col2im(const float* dcol, float* dx, const float* mask, int N, int H, int W, int C, int kh,
                 int kw, int stride, int pad, int Kpad, cudaStream_t stream);
 int loft_maxpool3x3s2(const float* x, float* y, int N, int H, int W, int C, cudaStream_t stream);

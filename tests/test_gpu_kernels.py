@@ -225,18 +225,23 @@ def test_deconv2x2():
     assert rel(gb, br.grad) < GRAD_TOL
 
 
-def test_stem_and_maxpool():
+@pytest.mark.parametrize('hw', [(64, 64), (70, 90), (256, 320), (33, 1100)])
+def test_stem_and_maxpool(hw):
+    """Direct 7x7/2 stem (packed NHWC4 image read through an overlapping-stride tensor map) against
+    torch fp32 conv2d; even / odd sizes, rows wider than one 256-column tile."""
     from bonai_b200.ops import misc as M
-    img = rnd(2, 3, 64, 64, seed=1)
+    img = rnd(2, 3, *hw, seed=1)
     w = rnd(64, 3, 7, 7, seed=2, scale=0.1)
     scale, shift = rnd(64, seed=3).abs() + 0.5, rnd(64, seed=4) * 0.1
-    K, kpad = 147, 148
-    wp = torch.zeros(64, kpad, device='cuda')
-    wp[:, :K] = tf32_round(w.permute(0, 2, 3, 1).reshape(64, K))
-    y = M.stem_conv(img, wp, kpad, scale, shift)
-    yr = F.relu(F.conv2d(img, w, stride=2, padding=3) * scale.view(1, -1, 1, 1) +
-                shift.view(1, -1, 1, 1))
+    wp = M.pack_stem_weight(tf32_round(w.permute(0, 2, 3, 1).contiguous()))
+    y = M.stem_conv(img, wp, scale, shift)
+    yr = F.relu(F.conv2d(tf32_round(img), tf32_round(w), stride=2, padding=3) *
+                scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    assert y.shape == yr.shape
     assert rel(y, yr) < TF32_TOL
+    # the border rows / columns read the zero padding of the packed image
+    assert rel(y[:, :, :2], yr[:, :, :2]) < TF32_TOL and rel(y[:, :, -2:], yr[:, :, -2:]) < TF32_TOL
+    assert rel(y[..., :2], yr[..., :2]) < TF32_TOL and rel(y[..., -2:], yr[..., -2:]) < TF32_TOL
     p = M.maxpool3x3s2(y)
     assert torch.equal(p, F.max_pool2d(y, 3, 2, 1))
 
