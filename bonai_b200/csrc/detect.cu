@@ -599,6 +599,219 @@ rcnn_sample_kernel(const float* __restrict__ props, long long prop_stride, int K
   }
 }
 
+// ---------------------------------------------------------------- RPN sampling + targets
+// AnchorHead._get_targets_single after the assigner (anchor_head.py:206-278, allowed_border -1,
+// sampling on) + RandomSampler (random_sampler.py:31-75, add_gt_as_proposals off) + images_to_levels
+// (anchor_head.py:363-380) for the whole batch in three wide launches and NO host read-back: up to
+// num_pos_max positives (assigned gt > 0), then num - (#positives taken) negatives (assigned gt ==
+// 0) are drawn uniformly without replacement over the ~262 k anchors of each image, and labels /
+// label weights / box targets / box weights are written directly in the per-level (n, h, w, a)
+// order the loss kernel reads.  The reference path is ~80 small ATen launches and three host
+// syncs per step (nonzero / randperm / index_put per image, the sample count for the loss scale).
+// A uniform subset of size m = the m smallest of unique pseudo-random 64-bit keys (hash(seed, img,
+// j) << 32 | j):  (1) histogram of the keys' top 12 bits per (image, class);  (2) every block
+// derives the bin holding the m-th smallest key and appends that bin's keys (~64 of them) to a
+// list;  (3) every block ranks the list to find the exact m-th key and writes the targets of its
+// anchors.  The total sample count (the loss' avg_factor) is left on the device.
+constexpr int kRpnBins = 4096;
+constexpr int kRpnListCap = 2048;
+constexpr int kRpnThreads = 1024;
+
+struct RpnMeta {            // per image
+  int tot[2];               // candidates of class 0 (negative) / 1 (positive)
+  int take[2];              // how many of them are sampled
+  int bin[2];               // top-12-bit bin of the take-th smallest key (-1: take everything)
+  int want[2];              // rank of that key within its bin (1-based)
+};
+
+struct RpnTargetArgs {
+  const float* anchors;               // [A, 4], level-major
+  const long long* gt_inds;           // [B, A]
+  const float* gts;                   // [sum G, 4]
+  const int* gt_off;                  // [B + 1]
+  long long lvl_off[kMaxRpnLevels + 1];   // anchor offsets of the levels
+  int n_levels, B;
+  long long A;
+  int num, num_pos_max;
+  unsigned long long seed;
+  float s0, s1, s2, s3, pos_weight;
+  // workspace
+  unsigned* hist;                     // [B][2][kRpnBins]
+  unsigned long long* list;           // [B][2][kRpnListCap]
+  int* list_n;                        // [B][2]
+  RpnMeta* meta;                      // [B]
+  int* err;                           // != 0: a list overflowed
+  // outputs: level l occupies [B * lvl_off[l], B * lvl_off[l + 1]) in (image, anchor) order
+  float *labels, *label_w, *bbox_t, *bbox_w;
+  float* total;                       // [1]: sum over images of max(#pos, 1) + max(#neg, 1)
+};
+
+__device__ __forceinline__ unsigned long long rpn_key(unsigned long long seed, int img, long long j) {
+  return ((unsigned long long)samp_hash(seed + (unsigned long long)img * 0x100000001B3ull,
+                                        (unsigned)j) << 32) | (unsigned)j;
+}
+
+__global__ void __launch_bounds__(kRpnThreads) rpn_hist_kernel(const RpnTargetArgs a) {
+  __shared__ unsigned s_hist[2 * kRpnBins];
+  const int img = blockIdx.y, t = threadIdx.x;
+  for (int i = t; i < 2 * kRpnBins; i += kRpnThreads) s_hist[i] = 0u;
+  __syncthreads();
+  const long long* gi = a.gt_inds + (long long)img * a.A;
+  for (long long j = (long long)blockIdx.x * kRpnThreads + t; j < a.A;
+       j += (long long)gridDim.x * kRpnThreads) {
+    const long long g = gi[j];
+    if (g < 0) continue;
+    const int cls = g > 0 ? 1 : 0;
+    atomicAdd(&s_hist[cls * kRpnBins + (unsigned)(rpn_key(a.seed, img, j) >> 52)], 1u);
+  }
+  __syncthreads();
+  unsigned* gh = a.hist + (size_t)img * 2 * kRpnBins;
+  for (int i = t; i < 2 * kRpnBins; i += kRpnThreads)
+    if (s_hist[i]) atomicAdd(&gh[i], s_hist[i]);
+}
+
+// per (image, class): totals, how many to take, and the (bin, rank in bin) of the take-th key
+__device__ void rpn_plan(const RpnTargetArgs& a, int img, unsigned* s_scan, int* s_warp,
+                         RpnMeta* s_meta) {
+  const int t = threadIdx.x;
+  const unsigned* gh = a.hist + (size_t)img * 2 * kRpnBins;
+  constexpr int kPer = kRpnBins / kRpnThreads;   // 4 bins per thread
+  for (int cls = 1; cls >= 0; --cls) {           // positives first: they fix the negatives' quota
+    unsigned v[kPer], sum = 0;
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+      v[k] = gh[cls * kRpnBins + t * kPer + k];
+      sum += v[k];
+    }
+    unsigned incl = sum;
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned u = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((t & 31) >= o) incl += u;
+    }
+    if ((t & 31) == 31) s_warp[t >> 5] = (int)incl;
+    __syncthreads();
+    if (t < 32) {
+      int w = s_warp[t], wi = w;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, wi, o);
+        if (t >= o) wi += u;
+      }
+      s_warp[t] = wi - w;
+      if (t == 31) s_meta->tot[cls] = wi;
+    }
+    __syncthreads();
+    unsigned excl = incl - sum + (unsigned)s_warp[t >> 5];   // candidates in bins before mine
+    if (t == 0) {
+      const int tot = s_meta->tot[cls];
+      const int quota = cls == 1 ? a.num_pos_max : a.num - s_meta->take[1];
+      s_meta->take[cls] = tot < quota ? tot : (quota > 0 ? quota : 0);
+      s_meta->bin[cls] = -1;
+      s_meta->want[cls] = 0;
+    }
+    __syncthreads();
+    const int take = s_meta->take[cls];
+    if (take > 0 && take < s_meta->tot[cls]) {
+#pragma unroll
+      for (int k = 0; k < kPer; ++k) {
+        if ((int)excl < take && (int)(excl + v[k]) >= take) {   // exactly one bin satisfies this
+          s_meta->bin[cls] = t * kPer + k;
+          s_meta->want[cls] = take - (int)excl;
+        }
+        excl += v[k];
+      }
+    }
+    __syncthreads();
+  }
+  (void)s_scan;
+}
+
+__global__ void __launch_bounds__(kRpnThreads) rpn_gather_kernel(const RpnTargetArgs a) {
+  __shared__ int s_warp[32];
+  __shared__ RpnMeta s_meta;
+  const int img = blockIdx.y, t = threadIdx.x;
+  rpn_plan(a, img, nullptr, s_warp, &s_meta);
+  if (blockIdx.x == 0 && t == 0) {
+    a.meta[img] = s_meta;
+    atomicAdd(a.total, (float)((s_meta.take[1] > 1 ? s_meta.take[1] : 1) +
+                               (s_meta.take[0] > 1 ? s_meta.take[0] : 1)));
+  }
+  const int bin0 = s_meta.bin[0], bin1 = s_meta.bin[1];
+  if (bin0 < 0 && bin1 < 0) return;
+  const long long* gi = a.gt_inds + (long long)img * a.A;
+  for (long long j = (long long)blockIdx.x * kRpnThreads + t; j < a.A;
+       j += (long long)gridDim.x * kRpnThreads) {
+    const long long g = gi[j];
+    if (g < 0) continue;
+    const int cls = g > 0 ? 1 : 0;
+    const int want_bin = cls ? bin1 : bin0;
+    if (want_bin < 0) continue;
+    const unsigned long long key = rpn_key(a.seed, img, j);
+    if ((int)(key >> 52) != want_bin) continue;
+    const int slot = atomicAdd(&a.list_n[img * 2 + cls], 1);
+    if (slot < kRpnListCap) a.list[((size_t)img * 2 + cls) * kRpnListCap + slot] = key;
+    else *a.err = 1;
+  }
+}
+
+__global__ void __launch_bounds__(kRpnThreads) rpn_write_kernel(const RpnTargetArgs a) {
+  __shared__ unsigned long long s_list[kRpnListCap];
+  __shared__ unsigned long long s_thr[2];
+  const int img = blockIdx.y, t = threadIdx.x;
+  const RpnMeta m = a.meta[img];
+  if (t < 2) s_thr[t] = ~0ull;                       // take every candidate of the class
+  __syncthreads();
+  for (int cls = 0; cls < 2; ++cls) {
+    if (m.bin[cls] < 0) continue;
+    const int n = min(a.list_n[img * 2 + cls], kRpnListCap);
+    const unsigned long long* gl = a.list + ((size_t)img * 2 + cls) * kRpnListCap;
+    for (int i = t; i < n; i += kRpnThreads) s_list[i] = gl[i];
+    __syncthreads();
+    for (int i = t; i < n; i += kRpnThreads) {       // the key of rank want-1 is the threshold
+      const unsigned long long k = s_list[i];
+      int r = 0;
+      for (int q = 0; q < n; ++q) r += s_list[q] < k;
+      if (r == m.want[cls] - 1) s_thr[cls] = k;
+    }
+    __syncthreads();
+  }
+  const unsigned long long thr0 = s_thr[0], thr1 = s_thr[1];
+  const long long* gi = a.gt_inds + (long long)img * a.A;
+  const float4* anc = reinterpret_cast<const float4*>(a.anchors);
+  const float4* gtb = reinterpret_cast<const float4*>(a.gts) + a.gt_off[img];
+  int lvl = 0;
+  for (long long j = (long long)blockIdx.x * kRpnThreads + t; j < a.A;
+       j += (long long)gridDim.x * kRpnThreads) {
+    while (j >= a.lvl_off[lvl + 1]) ++lvl;           // j only grows
+    const long long nl = a.lvl_off[lvl + 1] - a.lvl_off[lvl];
+    const long long o = (long long)a.B * a.lvl_off[lvl] + (long long)img * nl + (j - a.lvl_off[lvl]);
+    const long long g = gi[j];
+    bool pos = false, neg = false;
+    if (g >= 0) {
+      const unsigned long long key = rpn_key(a.seed, img, j);
+      if (g > 0) pos = m.take[1] > 0 && key <= thr1;
+      else neg = m.take[0] > 0 && key <= thr0;
+    }
+    float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pos) {
+      const float4 p = anc[j];
+      const float4 q = gtb[g - 1];
+      const float px = __fmul_rn(__fadd_rn(p.x, p.z), 0.5f), py = __fmul_rn(__fadd_rn(p.y, p.w), 0.5f);
+      const float pw = __fsub_rn(p.z, p.x), ph = __fsub_rn(p.w, p.y);
+      const float gx = __fmul_rn(__fadd_rn(q.x, q.z), 0.5f), gy = __fmul_rn(__fadd_rn(q.y, q.w), 0.5f);
+      const float gw = __fsub_rn(q.z, q.x), gh = __fsub_rn(q.w, q.y);
+      d.x = __fdiv_rn(__fdiv_rn(__fsub_rn(gx, px), pw), a.s0);
+      d.y = __fdiv_rn(__fdiv_rn(__fsub_rn(gy, py), ph), a.s1);
+      d.z = __fdiv_rn(logf(__fdiv_rn(gw, pw)), a.s2);
+      d.w = __fdiv_rn(logf(__fdiv_rn(gh, ph)), a.s3);
+    }
+    const float bw = pos ? 1.f : 0.f;
+    a.labels[o] = pos ? 1.f : 0.f;
+    a.label_w[o] = pos ? a.pos_weight : (neg ? 1.f : 0.f);
+    reinterpret_cast<float4*>(a.bbox_t)[o] = d;
+    reinterpret_cast<float4*>(a.bbox_w)[o] = make_float4(bw, bw, bw, bw);
+  }
+}
+
 // ---------------------------------------------------------------- soft-NMS (linear), test time
 // mmcv.ops.soft_nms(method='linear') [mmcv-full 1.0.5, CPU-only there]: repeatedly select the
 // highest-scoring live box, decay every other live box j by (1 - iou) if iou > thr, drop boxes whose
@@ -921,6 +1134,92 @@ int loft_iou_assign(const float* boxes, long long n, const float* gts, int G, fl
                                                       gt_inds);
   LOFT_CUDA_LAUNCH_CHECK("iou_assign");
   return LOFT_OK;
+}
+
+size_t loft_rpn_targets_workspace(int B) {
+  size_t b = 64;                                             // total (float), err (int)
+  b += (size_t)B * 2 * kRpnBins * sizeof(unsigned);          // hist
+  b += (size_t)B * 2 * sizeof(int) + 64;                     // list_n
+  b += (size_t)B * sizeof(RpnMeta) + 64;                     // meta
+  b += (size_t)B * 2 * kRpnListCap * sizeof(unsigned long long);
+  return b;
+}
+
+// RPN sampling + target construction for a batch (see rpn_hist_kernel).  gt_inds [B, A] is the
+// assigner's output per image; lvl_off[n_levels + 1] are the anchor offsets of the pyramid levels;
+// outputs are flat buffers of B*A (labels, label_w) and B*A*4 (bbox_t, bbox_w) floats in which
+// level l occupies [B*lvl_off[l], B*lvl_off[l+1]) in (image, anchor) order; total[0] receives the
+// loss' avg_factor (anchor_head.py:441-449).  Asynchronous; nothing is read back.
+int loft_rpn_targets(const float* anchors, const long long* gt_inds, const float* gts,
+                     const int* gt_off, const long long* lvl_off, int n_levels, int B, long long A,
+                     int num, int num_pos_max, unsigned long long seed, float s0, float s1,
+                     float s2, float s3, float pos_weight, float* labels, float* label_w,
+                     float* bbox_t, float* bbox_w, float* total, void* workspace, size_t ws_bytes,
+                     cudaStream_t stream) {
+  LOFT_CHECK_ARG(anchors && gt_inds && gts && gt_off && lvl_off && labels && label_w && bbox_t &&
+                     bbox_w && total && workspace,
+                 "rpn_targets: null pointer");
+  LOFT_CHECK_SHAPE(n_levels >= 1 && n_levels <= kMaxRpnLevels && B >= 1 && A >= 1 &&
+                       A < (1ll << 32) && num >= 1 && num_pos_max >= 0 && lvl_off[n_levels] == A,
+                   "rpn_targets: bad sizes levels=%d B=%d A=%lld num=%d", n_levels, B, A, num);
+  LOFT_CHECK_ARG(ws_bytes >= loft_rpn_targets_workspace(B), "rpn_targets: workspace too small");
+  LOFT_CHECK_ARG((reinterpret_cast<uintptr_t>(anchors) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(gts) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(bbox_t) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(bbox_w) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(workspace) & 15) == 0,
+                 "rpn_targets: buffers must be 16-byte aligned");
+  RpnTargetArgs a{};
+  a.anchors = anchors;
+  a.gt_inds = gt_inds;
+  a.gts = gts;
+  a.gt_off = gt_off;
+  for (int l = 0; l <= n_levels; ++l) a.lvl_off[l] = lvl_off[l];
+  a.n_levels = n_levels;
+  a.B = B;
+  a.A = A;
+  a.num = num;
+  a.num_pos_max = num_pos_max;
+  a.seed = seed;
+  a.s0 = s0; a.s1 = s1; a.s2 = s2; a.s3 = s3;
+  a.pos_weight = pos_weight;
+  unsigned char* w = reinterpret_cast<unsigned char*>(workspace);
+  a.err = reinterpret_cast<int*>(w + 16);
+  size_t o = 64;
+  a.hist = reinterpret_cast<unsigned*>(w + o);
+  o += (size_t)B * 2 * kRpnBins * sizeof(unsigned);
+  a.list_n = reinterpret_cast<int*>(w + o);
+  o += ((size_t)B * 2 * sizeof(int) + 63) / 64 * 64;
+  const size_t zero_bytes = o;                               // err, hist, list_n start at zero
+  a.meta = reinterpret_cast<RpnMeta*>(w + o);
+  o += ((size_t)B * sizeof(RpnMeta) + 63) / 64 * 64;
+  a.list = reinterpret_cast<unsigned long long*>(w + o);
+  a.labels = labels;
+  a.label_w = label_w;
+  a.bbox_t = bbox_t;
+  a.bbox_w = bbox_w;
+  a.total = total;
+  cudaMemsetAsync(w, 0, zero_bytes, stream);
+  cudaMemsetAsync(total, 0, sizeof(float), stream);
+  const int per_img = (int)((A + 8 * kRpnThreads - 1) / (8 * kRpnThreads));   // ~8 anchors / thread
+  dim3 grid(per_img < 1 ? 1 : (per_img > 64 ? 64 : per_img), B);
+  rpn_hist_kernel<<<grid, kRpnThreads, 0, stream>>>(a);
+  LOFT_CUDA_LAUNCH_CHECK("rpn_hist");
+  rpn_gather_kernel<<<grid, kRpnThreads, 0, stream>>>(a);
+  LOFT_CUDA_LAUNCH_CHECK("rpn_gather");
+  rpn_write_kernel<<<grid, kRpnThreads, 0, stream>>>(a);
+  LOFT_CUDA_LAUNCH_CHECK("rpn_write");
+  return LOFT_OK;
+}
+
+// 1 if a candidate list of the last loft_rpn_targets call on this workspace overflowed (the
+// sample is then short); a device -> host read, for tests.
+int loft_rpn_targets_overflowed(const void* workspace, cudaStream_t stream) {
+  int e = 0;
+  cudaMemcpyAsync(&e, reinterpret_cast<const unsigned char*>(workspace) + 16, sizeof(int),
+                  cudaMemcpyDeviceToHost, stream);
+  cudaStreamSynchronize(stream);
+  return e;
 }
 
 int loft_rpn_decode(const float* head_out, int ld, int reg_off, const long long* topk_idx, int k,

@@ -341,6 +341,33 @@ __global__ void stem_pack_kernel(const float* __restrict__ x, float4* __restrict
   }
 }
 
+// dst[r, :] = src[idx[r], :] (gather) or dst[idx[r], :] += src[r, :] (scatter-add; idx unique),
+// rows of `cols4` float4.  Lets the FOA head read the positives' rows of the bbox head's RoI
+// features instead of a third RoIAlign over the same RoIs, and add its gradient back into the
+// same rows of the bbox features' gradient.
+template <bool kScatterAdd>
+__global__ void rows_kernel(const float4* __restrict__ src, const long long* __restrict__ idx,
+                            float4* __restrict__ dst, long long rows, int cols4) {
+  const long long total = rows * cols4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols4;
+    const int c = (int)(i - r * cols4);
+    const long long j = idx[r];
+    if (kScatterAdd) {
+      float4 a = dst[j * cols4 + c];
+      const float4 b = src[i];
+      a.x += b.x;
+      a.y += b.y;
+      a.z += b.z;
+      a.w += b.w;
+      dst[j * cols4 + c] = a;
+    } else {
+      dst[i] = src[j * cols4 + c];
+    }
+  }
+}
+
 // dx[n,h,w,c] = sum over taps of dcol[(n,ho,wo),(r,s,c)] (gather form, no atomics), float4 over c
 __global__ void col2im_v4_kernel(const float4* __restrict__ dcol, float4* __restrict__ dx,
                                  const float4* __restrict__ mask, int N, int H, int W, int C4, int kh,
@@ -698,6 +725,28 @@ int loft_stem_pack(const float* x, float* xp, int N, int H, int W, int C, cudaSt
   stem_pack_kernel<<<grid_for(total, kT, 148 * 32), kT, 0, stream>>>(
       x, reinterpret_cast<float4*>(xp), N, H, W, C, Hh, Wp);
   LOFT_CUDA_LAUNCH_CHECK("stem_pack");
+  return LOFT_OK;
+}
+
+int loft_gather_rows(const float* src, const long long* idx, float* dst, long long rows,
+                     long long cols, cudaStream_t stream) {
+  LOFT_CHECK_ARG(src && idx && dst, "gather_rows: null pointer");
+  LOFT_CHECK_SHAPE(cols % 4 == 0 && cols / 4 < (1ll << 31), "gather_rows: cols=%lld must be a multiple of 4", cols);
+  if (rows * cols == 0) return LOFT_OK;
+  rows_kernel<false><<<grid_for(rows * (cols / 4), kT, 148 * 16), kT, 0, stream>>>(
+      reinterpret_cast<const float4*>(src), idx, reinterpret_cast<float4*>(dst), rows, (int)(cols / 4));
+  LOFT_CUDA_LAUNCH_CHECK("gather_rows");
+  return LOFT_OK;
+}
+
+int loft_scatter_add_rows(const float* src, const long long* idx, float* dst, long long rows,
+                          long long cols, cudaStream_t stream) {
+  LOFT_CHECK_ARG(src && idx && dst, "scatter_add_rows: null pointer");
+  LOFT_CHECK_SHAPE(cols % 4 == 0 && cols / 4 < (1ll << 31), "scatter_add_rows: cols=%lld must be a multiple of 4", cols);
+  if (rows * cols == 0) return LOFT_OK;
+  rows_kernel<true><<<grid_for(rows * (cols / 4), kT, 148 * 16), kT, 0, stream>>>(
+      reinterpret_cast<const float4*>(src), idx, reinterpret_cast<float4*>(dst), rows, (int)(cols / 4));
+  LOFT_CUDA_LAUNCH_CHECK("scatter_add_rows");
   return LOFT_OK;
 }
 

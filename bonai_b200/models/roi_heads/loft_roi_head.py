@@ -1,5 +1,7 @@
 """LoftRoIHead (mmdet/models/roi_heads/loft_roi_head.py:22-227): StandardRoIHead + the
 roof-to-footprint offset branch."""
+import os
+
 import torch
 
 from .builder_alias import HEADS, build_head, build_roi_extractor
@@ -48,7 +50,8 @@ class LoftRoIHead(StandardRoIHead):
         if self.with_offset:
             offset_results = self._offset_forward_train(x, sampling_results,
                                                         bbox_results['bbox_feats'], gt_offsets,
-                                                        img_metas)
+                                                        img_metas,
+                                                        offset_feats=bbox_results.get('offset_feats'))
             if offset_results['loss_offset'] is not None:
                 losses.update(offset_results['loss_offset'])
         return losses
@@ -63,9 +66,55 @@ class LoftRoIHead(StandardRoIHead):
         mask_results.update(loss_mask=loss_mask, mask_targets=mask_targets)
         return mask_results
 
-    def _offset_forward_train(self, x, sampling_results, bbox_feats, gt_offsets, img_metas):
-        pos_rois = bbox2roi([res.pos_bboxes for res in sampling_results])
-        offset_results = self._offset_forward(x, pos_rois)
+    def _shares_bbox_rois(self):
+        """True when the offset extractor is the same RoIAlign as the bbox extractor (it is in
+        every LOFT config: bonai_loft_foa_r50_fpn_basic.py:37-42,69-74), so that the offset
+        features of the positive RoIs ARE the positives' rows of the bbox features."""
+        a, b = self.bbox_roi_extractor, self.offset_roi_extractor
+        if os.environ.get('LOFT_SHARE_OFFSET_ROI', '1') == '0' or self.with_shared_head:
+            return False
+        if type(a) is not type(b) or len(a.roi_layers) != len(b.roi_layers):
+            return False
+        return (repr(a.roi_layers) == repr(b.roi_layers) and
+                list(a.featmap_strides) == list(b.featmap_strides) and
+                a.out_channels == b.out_channels and
+                getattr(a, 'finest_scale', None) == getattr(b, 'finest_scale', None))
+
+    def _bbox_forward_train(self, x, sampling_results, gt_bboxes, gt_labels, img_metas):
+        """StandardRoIHead._bbox_forward_train (standard_roi_head.py:111-124); additionally hands
+        the positives' rows of the RoI features to the offset branch (`_TakeRows`) instead of
+        running the offset extractor over the same RoIs again."""
+        if not (self.with_offset and torch.is_grad_enabled() and self._shares_bbox_rois()):
+            return super()._bbox_forward_train(x, sampling_results, gt_bboxes, gt_labels, img_metas)
+        from ...ops.roi import take_rows
+        rois = bbox2roi([res.bboxes for res in sampling_results])
+        bbox_feats = self.bbox_roi_extractor(x[:self.bbox_roi_extractor.num_inputs], rois)
+        rows, off = [], 0
+        for res in sampling_results:          # per image: positives first, then negatives
+            n_pos, n_all = int(res.pos_bboxes.shape[0]), int(res.bboxes.shape[0])
+            rows.append(torch.arange(off, off + n_pos, device=rois.device))
+            off += n_all
+        rows = torch.cat(rows)
+        offset_feats = None
+        if rows.numel() > 0:
+            bbox_feats, offset_feats = take_rows(bbox_feats, rows)
+        cls_score, bbox_pred = self.bbox_head(bbox_feats)
+        bbox_results = dict(cls_score=cls_score, bbox_pred=bbox_pred, bbox_feats=bbox_feats,
+                            offset_feats=offset_feats)
+        bbox_targets = self.bbox_head.get_targets(sampling_results, gt_bboxes, gt_labels,
+                                                  self.train_cfg)
+        loss_bbox = self.bbox_head.loss(cls_score, bbox_pred, rois, *bbox_targets)
+        bbox_results.update(loss_bbox=loss_bbox)
+        return bbox_results
+
+    def _offset_forward_train(self, x, sampling_results, bbox_feats, gt_offsets, img_metas,
+                              offset_feats=None):
+        if offset_feats is not None:
+            offset_results = dict(offset_pred=self.offset_head(offset_feats),
+                                  offset_feats=offset_feats)
+        else:
+            pos_rois = bbox2roi([res.pos_bboxes for res in sampling_results])
+            offset_results = self._offset_forward(x, pos_rois)
         offset_targets = self.offset_head.get_targets(sampling_results, gt_offsets, self.train_cfg)
         loss_offset = self.offset_head.loss(offset_results['offset_pred'], offset_targets)
         offset_results.update(loss_offset=loss_offset, offset_targets=offset_targets)

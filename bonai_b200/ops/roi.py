@@ -74,6 +74,49 @@ def multilevel_roi_align(feats, rois, out_size, strides, finest_scale=56):
                                      float(finest_scale), sinks, *feats)
 
 
+class _TakeRows(Function):
+    """feats [K,C,S,S] -> (feats, feats[rows]): a second consumer reads a subset of the rows (the
+    FOA head reads the positives' rows of the bbox head's RoI features -- both extractors are the
+    same 7x7 RoIAlign over the same pyramid, loft_roi_head.py:118-120).  The backward adds the
+    subset's gradient into the same rows of the full gradient IN PLACE: no zero-filled [K,C,S,S]
+    temporary, no full-size add, one RoIAlign backward for both heads."""
+
+    @staticmethod
+    def forward(ctx, feats, rows):
+        ctx.set_materialize_grads(False)
+        fn = nhwc(feats)
+        K, S, S2, C = fn.shape
+        P = int(rows.numel())
+        out = new_nhwc(P, C, S, S2, feats.device)
+        rows = rows.contiguous().long()
+        L.call('gather_rows', L.ptr(fn), L.ptr(rows), L.ptr(out.permute(0, 2, 3, 1)), L.ll(P),
+               L.ll(S * S2 * C), L.stream())
+        ctx.save_for_backward(rows)
+        ctx.full_shape = tuple(feats.shape)
+        return feats, out
+
+    @staticmethod
+    def backward(ctx, g_full, g_rows):
+        (rows,) = ctx.saved_tensors
+        if g_rows is None:
+            return g_full, None
+        K, C, S, S2 = ctx.full_shape
+        if g_full is None:
+            g_full = new_nhwc(K, C, S, S2, g_rows.device).zero_()
+        gf = g_full.permute(0, 2, 3, 1)
+        if not gf.is_contiguous():
+            gf = gf.contiguous()
+            g_full = gf.permute(0, 3, 1, 2)
+        L.call('scatter_add_rows', L.ptr(nhwc(g_rows)), L.ptr(rows), L.ptr(gf), L.ll(rows.numel()),
+               L.ll(S * S2 * C), L.stream())
+        return g_full, None
+
+
+def take_rows(feats, rows):
+    """(feats, feats[rows]) with the shared-gradient backward of `_TakeRows`; `rows` unique."""
+    return _TakeRows.apply(feats, rows)
+
+
 def roi_align(input, rois, output_size, spatial_scale=1.0, sampling_ratio=0, pool_mode='avg',
               aligned=True):
     """Functional single-level form with the mmcv signature (structures.py:286-287)."""

@@ -137,6 +137,14 @@ int loft_im2col(const float* x, float* col, int N, int H, int W, int C, int kh, 
 int loft_stem_pack(const float* x, float* xp, int N, int H, int W, int C, cudaStream_t stream);
 int loft_stem_conv7x7(const float* xp, const float* w, float* y, int N, int H, int W, int Cout,
                       const loft_epilogue_t* epi, cudaStream_t stream);
+/* rows of a [*, cols] fp32 matrix by index (cols % 4 == 0): dst[r] = src[idx[r]] and
+ * dst[idx[r]] += src[r] (idx unique).  Replaces the offset branch's own RoIAlign over the positive
+ * RoIs (mmdet/models/roi_heads/loft_roi_head.py:118-120: offset_roi_extractor == bbox_roi_extractor,
+ * bonai_loft_foa_r50_fpn_basic.py:37-42,69-74) by the positives' rows of bbox_feats */
+int loft_gather_rows(const float* src, const long long* idx, float* dst, long long rows,
+                     long long cols, cudaStream_t stream);
+int loft_scatter_add_rows(const float* src, const long long* idx, float* dst, long long rows,
+                          long long cols, cudaStream_t stream);
 int loft_col2im(const float* dcol, float* dx, const float* mask, int N, int H, int W, int C, int kh,
                 int kw, int stride, int pad, int Kpad, cudaStream_t stream);
 int loft_maxpool3x3s2(const float* x, float* y, int N, int H, int W, int C, cudaStream_t stream);

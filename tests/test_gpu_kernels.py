@@ -520,3 +520,26 @@ def test_grouped_conv3x3_matches_per_group():
         assert rel(xg.grad[g * Pg:(g + 1) * Pg], xr.grad) < GRAD_TOL
         assert rel(wrefs[g].grad, wr.grad) < GRAD_TOL
         assert rel(bgrads[g], br.grad) < GRAD_TOL
+
+
+def test_take_rows_shares_the_gradient():
+    """_TakeRows: (feats, feats[rows]) with the subset's gradient added in place into the rows of
+    the full gradient == autograd over plain indexing."""
+    from bonai_b200.ops.roi import take_rows
+    K, C, S = 37, 8, 7
+    x = rnd(K, C, S, S, seed=1).contiguous(memory_format=torch.channels_last).requires_grad_()
+    xr = x.detach().clone().requires_grad_()
+    rows = torch.tensor([0, 3, 4, 17, 36], device='cuda')
+    full, sub = take_rows(x, rows)
+    assert torch.equal(full, x) and torch.equal(sub, x[rows])
+    wf, ws = rnd(K, C, S, S, seed=2), rnd(5, C, S, S, seed=3)
+    ((full * wf).sum() + (sub * ws).sum()).backward()
+    ((xr * wf).sum() + (xr[rows] * ws).sum()).backward()
+    assert torch.allclose(x.grad, xr.grad, rtol=0, atol=1e-6)
+    # only the subset is differentiated
+    x.grad = None
+    full, sub = take_rows(x, rows)
+    (sub * ws).sum().backward()
+    ref = torch.zeros_like(xr)
+    ref[rows] = ws
+    assert torch.allclose(x.grad, ref, rtol=0, atol=1e-6)

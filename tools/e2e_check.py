@@ -122,7 +122,10 @@ def run(size=256, n_img=1, num_gt=10, seed=0, force_proposals=True, verbose=True
         model.roi_head.offset_head.register_forward_hook(cap('offset_pred'))
         model.roi_head.bbox_head.register_forward_hook(cap('bbox_out'))
     # inputs of the FOA head and its targets, for the TF32-emulated head oracle below
-    model.roi_head.offset_roi_extractor.register_forward_hook(cap('offset_feats'))
+    # (the head's INPUT: in training the offset features are the positives' rows of the bbox
+    # features, the offset extractor itself is not called)
+    model.roi_head.offset_head.register_forward_pre_hook(
+        lambda mod, inp: caps.__setitem__('offset_feats', inp[0]))
     oh = model.roi_head.offset_head
     get_targets = oh.get_targets
 
