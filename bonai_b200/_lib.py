@@ -71,7 +71,7 @@ def f32(v):
 
 
 LAUNCHES = [0]          # kernels launched through this binding (bench.py reads / resets it)
-_KERNELS_PER_CALL = {'iou_assign': 2, 'grad_sqnorm': 1, 'poly_rasterize': 2}
+_KERNELS_PER_CALL = {'iou_assign': 2, 'grad_sqnorm': 1, 'poly_rasterize': 2, 'rpn_targets': 3}
 
 
 RECORD = None           # set to a list to record (fn, args) of every call (trunk.Tape)

@@ -613,6 +613,7 @@ rcnn_sample_kernel(const float* __restrict__ props, long long prop_stride, int K
 // derives the bin holding the m-th smallest key and appends that bin's keys (~64 of them) to a
 // list;  (3) every block ranks the list to find the exact m-th key and writes the targets of its
 // anchors.  The total sample count (the loss' avg_factor) is left on the device.
+constexpr int kMaxRpnLevels = 8;                 // as in loss.cu (rpn_loss_fused)
 constexpr int kRpnBins = 4096;
 constexpr int kRpnListCap = 2048;
 constexpr int kRpnThreads = 1024;

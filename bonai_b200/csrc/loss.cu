@@ -175,6 +175,7 @@ struct RpnLossArgs {
   long long row_end[kMaxRpnLevels];   // prefix sums of rows
   int n_levels, A, ld, mode_bbox;
   float beta, cls_scale, bbox_scale;
+  const float* inv_denom;   // optional device scalar: both scales are divided by it (avg_factor)
 };
 
 __global__ void rpn_loss_fused_kernel(const RpnLossArgs a, float* __restrict__ sums) {
@@ -183,6 +184,8 @@ __global__ void rpn_loss_fused_kernel(const RpnLossArgs a, float* __restrict__ s
   __syncthreads();
   const long long total = a.row_end[a.n_levels - 1] * a.ld;
   const int A = a.A, ld = a.ld;
+  const float inv = a.inv_denom ? 1.f / fmaxf(*a.inv_denom, 1.f) : 1.f;
+  const float cls_scale = a.cls_scale * inv, bbox_scale = a.bbox_scale * inv;
   int cur = -1;
   float acc_c = 0.f, acc_b = 0.f;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
@@ -207,7 +210,7 @@ __global__ void rpn_loss_fused_kernel(const RpnLossArgs a, float* __restrict__ s
       const long long ti = row * A + col;
       const float t = L.labels[ti], w = L.label_w[ti];
       acc_c += bce_logits(x, t) * w;
-      g = (1.f / (1.f + expf(-x)) - t) * w * a.cls_scale;
+      g = (1.f / (1.f + expf(-x)) - t) * w * cls_scale;
     } else if (col < 5 * A) {
       const long long ti = row * 4 * A + (col - A);
       const float t = L.bbox_t[ti], w = L.bbox_w[ti];
@@ -220,7 +223,7 @@ __global__ void rpn_loss_fused_kernel(const RpnLossArgs a, float* __restrict__ s
         acc_b += (ad < a.beta ? 0.5f * d * d / a.beta : ad - 0.5f * a.beta) * w;
         gd = (ad < a.beta) ? d / a.beta : (d > 0.f ? 1.f : -1.f);
       }
-      g = gd * w * a.bbox_scale;
+      g = gd * w * bbox_scale;
     }
     if (L.grad != nullptr) L.grad[row * ld + col] = g;
   }
@@ -231,7 +234,7 @@ __global__ void rpn_loss_fused_kernel(const RpnLossArgs a, float* __restrict__ s
   __syncthreads();
   if (threadIdx.x < 2 * a.n_levels) {
     const int l = threadIdx.x >> 1, which = threadIdx.x & 1;
-    const float v = s_acc[threadIdx.x] * (which ? a.bbox_scale : a.cls_scale);
+    const float v = s_acc[threadIdx.x] * (which ? bbox_scale : cls_scale);
     if (v != 0.f) atomicAdd(&sums[which * a.n_levels + l], v);
   }
 }
@@ -241,8 +244,8 @@ __global__ void rpn_loss_fused_kernel(const RpnLossArgs a, float* __restrict__ s
 extern "C" {
 
 int loft_rpn_loss_fused(const loft_rpn_level_t* levels, int n_levels, int A, int ld, int mode_bbox,
-                        float beta, float cls_scale, float bbox_scale, float* sums,
-                        cudaStream_t stream) {
+                        float beta, float cls_scale, float bbox_scale, const float* denom,
+                        float* sums, cudaStream_t stream) {
   LOFT_CHECK_ARG(levels && sums, "rpn_loss_fused: null pointer");
   LOFT_CHECK_SHAPE(n_levels >= 1 && n_levels <= kMaxRpnLevels && 5 * A <= ld,
                    "rpn_loss_fused: n_levels=%d A=%d ld=%d", n_levels, A, ld);
@@ -265,6 +268,7 @@ int loft_rpn_loss_fused(const loft_rpn_level_t* levels, int n_levels, int A, int
   a.beta = beta;
   a.cls_scale = cls_scale;
   a.bbox_scale = bbox_scale;
+  a.inv_denom = denom;
   cudaMemsetAsync(sums, 0, sizeof(float) * 2 * n_levels, stream);
   if (rows == 0) return LOFT_OK;
   rpn_loss_fused_kernel<<<blocks_for(rows * ld), kT, 0, stream>>>(a, sums);

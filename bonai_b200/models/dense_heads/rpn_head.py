@@ -8,6 +8,7 @@ output already has the `(n, h, w, a)` order that the reference obtains with
 the fused IoU+assign kernel, the losses from fused BCE/L1 reductions, proposals from the
 top-k decode + bitmask-NMS kernels."""
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -191,9 +192,92 @@ class RPNHead(nn.Module):
             label_weights[neg_inds] = 1.0
         return labels, label_weights, bbox_targets, bbox_weights, pos_inds, neg_inds
 
+    def _fused_targets_ok(self, gt_bboxes):
+        """The no-read-back path covers the LOFT configuration: MaxIoUAssigner without ignore
+        regions, a plain RandomSampler (no gt boxes added, no neg_pos_ub) whose `random_choice`
+        has not been replaced (parity tests inject the oracle's draws through it)."""
+        from ...core.bbox import MaxIoUAssigner, RandomSampler
+        smp = self.sampler
+        if os.environ.get('LOFT_FUSED_RPN_TARGETS', '1') == '0' or 'random_choice' in vars(smp):
+            return False
+        if type(self.assigner) is not MaxIoUAssigner or type(smp) is not RandomSampler:
+            return False
+        if smp.add_gt_as_proposals or smp.neg_pos_ub >= 0 or self.train_cfg.allowed_border >= 0:
+            return False
+        if any(float(m) != 0.0 for m in self.bbox_coder.means):
+            return False
+        return all(g.is_cuda for g in gt_bboxes)
+
+    def _build_targets_fused(self, featmap_sizes, gt_bboxes, img_metas, device):
+        """Same targets as `_build_targets` (own random stream) from `loft_iou_assign` per image +
+        ONE `loft_rpn_targets` call for the batch; the sample count stays on the device (returned
+        as a 1-element tensor), nothing synchronises the host."""
+        import ctypes
+        i32 = ctypes.c_int
+        flat = self._flat_anchors(featmap_sizes, device)
+        A_tot = int(flat.shape[0])
+        B = len(img_metas)
+        num_lvl = [int(h) * int(w) * self.num_anchors for h, w in featmap_sizes]
+        offs = [0]
+        for n in num_lvl:
+            offs.append(offs[-1] + n)
+        asg, smp = self.assigner, self.sampler
+        gts = [g[:, :4].contiguous().float() for g in gt_bboxes]
+        Gs = [int(g.shape[0]) for g in gts]
+        gt_all = torch.cat(gts) if sum(Gs) else torch.zeros((1, 4), device=device)
+        goff = [0]
+        for g in Gs:
+            goff.append(goff[-1] + g)
+        cache = self.__dict__.setdefault('_fused_tables', {})
+        key = (tuple(offs), tuple(goff), str(device))
+        if key not in cache:
+            if len(cache) > 64:
+                cache.clear()
+            cache[key] = torch.tensor(goff, dtype=torch.int32).to(device)
+        gt_off = cache[key]
+        gt_inds = torch.empty((B, A_tot), dtype=torch.long, device=device)
+        max_ov = torch.empty((A_tot,), dtype=torch.float32, device=device)
+        for i in range(B):
+            if Gs[i] == 0:
+                gt_inds[i].zero_()
+                continue
+            ws_bytes = int(L.lib().loft_iou_assign_workspace(L.ll(A_tot), i32(Gs[i])))
+            ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=device)
+            L.call('iou_assign', L.ptr(flat), L.ll(A_tot), L.ptr(gts[i]), i32(Gs[i]),
+                   L.f32(asg.pos_iou_thr), L.f32(asg.neg_iou_thr), L.f32(asg.min_pos_iou),
+                   i32(asg.match_low_quality), L.ptr(gt_inds[i]), L.ptr(max_ov), L.ptr(ws),
+                   ctypes.c_size_t(ws_bytes), L.stream())
+        lab = torch.empty((B * A_tot,), dtype=torch.float32, device=device)
+        lw = torch.empty((B * A_tot,), dtype=torch.float32, device=device)
+        bt = torch.empty((B * A_tot * 4,), dtype=torch.float32, device=device)
+        bw = torch.empty((B * A_tot * 4,), dtype=torch.float32, device=device)
+        total = torch.empty((1,), dtype=torch.float32, device=device)
+        fn = L.lib().loft_rpn_targets_workspace
+        fn.restype = ctypes.c_size_t
+        ws_bytes = int(fn(i32(B)))
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=device)
+        self._target_calls = getattr(self, '_target_calls', 0) + 1
+        seed = (int(torch.initial_seed()) * 1000003 + 7919 * self._target_calls) & ((1 << 64) - 1)
+        lvl_off = (ctypes.c_longlong * len(offs))(*offs)
+        stds = [float(v) for v in self.bbox_coder.stds]
+        pos_w = 1.0 if self.train_cfg.pos_weight <= 0 else float(self.train_cfg.pos_weight)
+        L.call('rpn_targets', L.ptr(flat), L.ptr(gt_inds), L.ptr(gt_all), L.ptr(gt_off), lvl_off,
+               i32(len(num_lvl)), i32(B), L.ll(A_tot), i32(int(smp.num)),
+               i32(int(smp.num * smp.pos_fraction)), ctypes.c_ulonglong(seed), L.f32(stds[0]),
+               L.f32(stds[1]), L.f32(stds[2]), L.f32(stds[3]), L.f32(pos_w), L.ptr(lab), L.ptr(lw),
+               L.ptr(bt), L.ptr(bw), L.ptr(total), L.ptr(ws), ctypes.c_size_t(ws_bytes), L.stream())
+        self._last_target_ws = ws
+        per_level = [(lab[B * offs[l]:B * offs[l + 1]], lw[B * offs[l]:B * offs[l + 1]],
+                      bt[4 * B * offs[l]:4 * B * offs[l + 1]], bw[4 * B * offs[l]:4 * B * offs[l + 1]])
+                     for l in range(len(num_lvl))]
+        return per_level, total
+
     def _build_targets(self, featmap_sizes, gt_bboxes, img_metas, device):
         """get_targets (anchor_head.py:280-380) for all images, regrouped per level and flattened
-        in the (n, h, w, a) order of the fused head output."""
+        in the (n, h, w, a) order of the fused head output.  Returns (per_level, num_total_samples);
+        the count is a 1-element device tensor on the fused path, a Python int otherwise."""
+        if self._fused_targets_ok(gt_bboxes):
+            return self._build_targets_fused(featmap_sizes, gt_bboxes, img_metas, device)
         flat = self._flat_anchors(featmap_sizes, device)
         num_lvl = [int(h) * int(w) * self.num_anchors for h, w in featmap_sizes]
         lab, lw, bt, bw = [], [], [], []
@@ -242,6 +326,8 @@ class RPNHead(nn.Module):
         for tup in per_level:
             for t in tup:
                 t.record_stream(main)
+        if isinstance(num_total, torch.Tensor):
+            num_total.record_stream(main)
         # a small FIFO: the next batch's targets are usually prefetched while the current
         # batch's are still waiting to be consumed by loss()
         slots = self.__dict__.setdefault('_prefetched', [])
@@ -290,13 +376,21 @@ class RPNHead(nn.Module):
         if grad_out is not None and all(getattr(cs, '_loft_fused', None) is not None
                                         for cs in cls_scores):
             outs2d = [cs._loft_fused.permute(0, 2, 3, 1).reshape(-1, _FUSED_W) for cs in cls_scores]
-            sums = K.rpn_loss_fused(outs2d, per_level, A, mode, beta,
-                                    self.loss_cls.loss_weight / num_total_samples,
-                                    self.loss_bbox.loss_weight / num_total_samples,
-                                    grads=[g.view(-1, _FUSED_W) for g in grad_out])
+            if isinstance(num_total_samples, torch.Tensor):      # count left on the device
+                sums = K.rpn_loss_fused(outs2d, per_level, A, mode, beta,
+                                        self.loss_cls.loss_weight, self.loss_bbox.loss_weight,
+                                        grads=[g.view(-1, _FUSED_W) for g in grad_out],
+                                        denom=num_total_samples)
+            else:
+                sums = K.rpn_loss_fused(outs2d, per_level, A, mode, beta,
+                                        self.loss_cls.loss_weight / num_total_samples,
+                                        self.loss_bbox.loss_weight / num_total_samples,
+                                        grads=[g.view(-1, _FUSED_W) for g in grad_out])
             n = len(cls_scores)
             return dict(loss_rpn_cls=[sums[l:l + 1] for l in range(n)],
                         loss_rpn_bbox=[sums[n + l:n + l + 1] for l in range(n)])
+        if isinstance(num_total_samples, torch.Tensor):          # module path: needs the number
+            num_total_samples = float(num_total_samples.item())
         loss_cls, loss_bbox = [], []
         for l, cs in enumerate(cls_scores):
             fused = getattr(cs, '_loft_fused', None)

@@ -61,13 +61,15 @@ class RpnLevel(ctypes.Structure):
 
 
 def rpn_loss_fused(outs2d, targets, num_anchors, mode_bbox, beta, cls_scale, bbox_scale,
-                   grads=None):
+                   grads=None, denom=None):
     """AnchorHead.loss over all levels in ONE launch (anchor_head.py:382-497).  outs2d: per level
     the fused head output [rows, ld]; targets: per level (labels, label_weights, bbox_targets,
     bbox_weights) flat; grads: per level a buffer shaped like the output that receives
     d(sum of all RPN loss terms)/d(output) in full (the total loss is the plain sum of its terms,
     detectors/base.py:175-208), or None.  Returns a [2 * n_levels] tensor: per-level cls sums, then
-    per-level bbox sums (already scaled).  No autograd: the caller owns the backward."""
+    per-level bbox sums (already scaled).  `denom`: optional 1-element device tensor both scales
+    are divided by (the avg_factor `rpn_targets` leaves on the device).  No autograd: the caller
+    owns the backward."""
     n = len(outs2d)
     ld = outs2d[0].shape[1]
     arr = (RpnLevel * n)()
@@ -86,7 +88,7 @@ def rpn_loss_fused(outs2d, targets, num_anchors, mode_bbox, beta, cls_scale, bbo
         arr[l].rows = o.shape[0]
     sums = torch.empty(2 * n, device=outs2d[0].device, dtype=torch.float32)
     L.call('rpn_loss_fused', arr, i32(n), i32(num_anchors), i32(ld), i32(mode_bbox), L.f32(beta),
-           L.f32(cls_scale), L.f32(bbox_scale), L.ptr(sums), L.stream())
+           L.f32(cls_scale), L.f32(bbox_scale), L.ptr(denom), L.ptr(sums), L.stream())
     return sums
 
 

@@ -286,9 +286,26 @@ typedef struct {
   float* grad;
   long long rows;
 } loft_rpn_level_t;
+/* denom: optional device scalar (the avg_factor loft_rpn_targets leaves on the device); both
+ * scales are divided by max(*denom, 1) */
 int loft_rpn_loss_fused(const loft_rpn_level_t* levels, int n_levels, int A, int ld, int mode_bbox,
-                        float beta, float cls_scale, float bbox_scale, float* sums,
-                        cudaStream_t stream);
+                        float beta, float cls_scale, float bbox_scale, const float* denom,
+                        float* sums, cudaStream_t stream);
+/* RPN sampling + targets of a batch without a host read-back: replaces
+ * AnchorHead._get_targets_single after the assigner + RandomSampler.sample + images_to_levels
+ * (mmdet/models/dense_heads/anchor_head.py:206-278,363-380, core/bbox/samplers/random_sampler.py:31-75).
+ * gt_inds [B, A]: MaxIoUAssigner output per image; lvl_off[n_levels+1]: anchor offsets of the
+ * levels; outputs: flat B*A (labels, label_w) / B*A*4 (bbox_t, bbox_w) floats, level l at
+ * [B*lvl_off[l], B*lvl_off[l+1]) in (image, anchor) order; total[0] = sum over images of
+ * max(#pos,1) + max(#neg,1) */
+size_t loft_rpn_targets_workspace(int B);
+int loft_rpn_targets(const float* anchors, const long long* gt_inds, const float* gts,
+                     const int* gt_off, const long long* lvl_off, int n_levels, int B, long long A,
+                     int num, int num_pos_max, unsigned long long seed, float s0, float s1,
+                     float s2, float s3, float pos_weight, float* labels, float* label_w,
+                     float* bbox_t, float* bbox_w, float* total, void* workspace, size_t ws_bytes,
+                     cudaStream_t stream);
+int loft_rpn_targets_overflowed(const void* workspace, cudaStream_t stream);
 int loft_elem_loss_fwd(int mode, const float* pred, long long ld, int col_off, int ncols,
                        long long rows, const float* target, const float* weight, float beta,
                        float scale, float* out_sum, cudaStream_t stream);
