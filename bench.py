@@ -481,14 +481,26 @@ def main():
     h2d_total = trainer.staged_bytes
     torch.cuda.synchronize()
     e0.record()
+    e2e_marks, host_t = [], []
     for j in range(args.steps):
+        host_t.append(time.perf_counter())
         nxt = trainer.stage(host_batches[(j + 1) % N_ROTATE])    # next batch's copies overlap
         h2d_total += trainer.staged_bytes if j + 1 < args.steps else 0
         trainer.train_step(cur, read_logs='async', prefetch=nxt)   # D2H of every step's loss
         cur = nxt                                # vector, read one step late
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        e2e_marks.append(ev)
     out = trainer.flush_logs()                   # the last step's losses, inside the timed region
     e1.record()
+    host_t.append(time.perf_counter())
     sync_all()
+    e2e_seq = [a.elapsed_time(b) for a, b in zip([e0] + e2e_marks[:-1], e2e_marks)]
+    e2e_host = sorted((b - a) * 1e3 for a, b in zip(host_t[:-1], host_t[1:]))
+    if os.environ.get('LOFT_STEP_TIMES'):
+        print(f'[rank {rank}] e2e per-step ms in order: ' + ' '.join(f'{t:.1f}' for t in e2e_seq),
+              file=sys.stderr)
+    e2e_sorted = sorted(e2e_seq)
     h2d_bytes = h2d_total // args.steps
     t = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
     if world > 1:
@@ -540,6 +552,10 @@ def main():
         'cpu_baseline': cpu,
         'e2e': {'value': round(e2e_value, 3), 'unit': 'img/s', 'h2d_bytes_per_step': h2d_bytes,
                 'd2h_bytes_per_step': 4 * len(out), 'ms_per_step': round(e2e_ms / args.steps, 3),
+                'step_ms': {'p50': round(e2e_sorted[len(e2e_sorted) // 2], 3),
+                            'max': round(e2e_sorted[-1], 3), 'min': round(e2e_sorted[0], 3),
+                            'host_p50': round(e2e_host[len(e2e_host) // 2], 3),
+                            'host_max': round(e2e_host[-1], 3)},
                 'note': 'inputs staged from pinned host memory on a copy stream (prefetch of the '
                         'next batch overlaps the step); every step\'s loss vector is copied to '
                         'pinned host memory asynchronously and read one step later, the last one '

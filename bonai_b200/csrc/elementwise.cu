@@ -368,6 +368,78 @@ __global__ void rows_kernel(const float4* __restrict__ src, const long long* __r
   }
 }
 
+// FOA input assembly (offset_head_expand_feature.py:163-196,198-214) fused with the row gather:
+//   y[b*P + p][i][j][:] = x[idx[p]][rot_kb(i, j)][:]   for the nb branches (rotation kb * 90 deg),
+// i.e. gather_rows + one rot90 per branch + torch.cat in one launch; and its backward
+//   gx[idx[p]][s][:] += sum_b gy[b*P + p][rot_kb^-1(s)][:]
+// (the branches' gradients summed and added into the rows of the bbox features' gradient).
+struct Rot4 {
+  int k[4];
+  int nb;
+};
+
+__device__ __forceinline__ void rot_src(int k, int S, int i, int j, int& si, int& sj) {
+  switch (k & 3) {           // as rot90_kernel: y[i][j] = x[si][sj]
+    case 0: si = i; sj = j; break;
+    case 1: si = j; sj = S - 1 - i; break;
+    case 2: si = S - 1 - i; sj = S - 1 - j; break;
+    default: si = S - 1 - j; sj = i; break;
+  }
+}
+
+__global__ void gather_rot_kernel(const float4* __restrict__ x, const long long* __restrict__ idx,
+                                  float4* __restrict__ y, long long P, int S, int C4, Rot4 r) {
+  const long long per = (long long)S * S * C4;
+  const long long total = (long long)r.nb * P * per;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(e % C4);
+    long long t = e / C4;
+    const int j = (int)(t % S);
+    t /= S;
+    const int i = (int)(t % S);
+    t /= S;
+    const long long p = t % P;
+    const int b = (int)(t / P);
+    int si, sj;
+    rot_src(r.k[b], S, i, j, si, sj);
+    y[e] = x[(idx[p] * S + si) * (long long)S * C4 + (long long)sj * C4 + c];
+  }
+}
+
+__global__ void scatter_rot_add_kernel(const float4* __restrict__ gy,
+                                       const long long* __restrict__ idx, float4* __restrict__ gx,
+                                       long long P, int S, int C4, Rot4 r) {
+  const long long per = (long long)S * S * C4;
+  const long long total = P * per;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(e % C4);
+    long long t = e / C4;
+    const int j = (int)(t % S);
+    t /= S;
+    const int i = (int)(t % S);
+    const long long p = t / S;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int b = 0; b < r.nb; ++b) {
+      int si, sj;
+      rot_src(-r.k[b], S, i, j, si, sj);      // gx[i][j] collects gy_b at the inverse rotation
+      const float4 v = gy[((b * P + p) * S + si) * (long long)S * C4 + (long long)sj * C4 + c];
+      acc.x += v.x;
+      acc.y += v.y;
+      acc.z += v.z;
+      acc.w += v.w;
+    }
+    float4* d = gx + (idx[p] * S + i) * (long long)S * C4 + (long long)j * C4 + c;
+    float4 a = *d;
+    a.x += acc.x;
+    a.y += acc.y;
+    a.z += acc.z;
+    a.w += acc.w;
+    *d = a;
+  }
+}
+
 // dx[n,h,w,c] = sum over taps of dcol[(n,ho,wo),(r,s,c)] (gather form, no atomics), float4 over c
 __global__ void col2im_v4_kernel(const float4* __restrict__ dcol, float4* __restrict__ dx,
                                  const float4* __restrict__ mask, int N, int H, int W, int C4, int kh,
@@ -747,6 +819,34 @@ int loft_scatter_add_rows(const float* src, const long long* idx, float* dst, lo
   rows_kernel<true><<<grid_for(rows * (cols / 4), kT, 148 * 16), kT, 0, stream>>>(
       reinterpret_cast<const float4*>(src), idx, reinterpret_cast<float4*>(dst), rows, (int)(cols / 4));
   LOFT_CUDA_LAUNCH_CHECK("scatter_add_rows");
+  return LOFT_OK;
+}
+
+int loft_gather_rot(const float* x, const long long* idx, float* y, long long P, int S, int C,
+                    const int* k, int nb, cudaStream_t stream) {
+  LOFT_CHECK_ARG(x && idx && y && k, "gather_rot: null pointer");
+  LOFT_CHECK_SHAPE(C % 4 == 0 && nb >= 1 && nb <= 4 && S >= 1, "gather_rot: C=%d nb=%d S=%d", C, nb, S);
+  if (P == 0) return LOFT_OK;
+  Rot4 r{};
+  r.nb = nb;
+  for (int b = 0; b < nb; ++b) r.k[b] = ((k[b] % 4) + 4) % 4;
+  gather_rot_kernel<<<grid_for((long long)nb * P * S * S * (C / 4), kT, 148 * 16), kT, 0, stream>>>(
+      reinterpret_cast<const float4*>(x), idx, reinterpret_cast<float4*>(y), P, S, C / 4, r);
+  LOFT_CUDA_LAUNCH_CHECK("gather_rot");
+  return LOFT_OK;
+}
+
+int loft_scatter_rot_add(const float* gy, const long long* idx, float* gx, long long P, int S, int C,
+                         const int* k, int nb, cudaStream_t stream) {
+  LOFT_CHECK_ARG(gy && idx && gx && k, "scatter_rot_add: null pointer");
+  LOFT_CHECK_SHAPE(C % 4 == 0 && nb >= 1 && nb <= 4 && S >= 1, "scatter_rot_add: C=%d nb=%d S=%d", C, nb, S);
+  if (P == 0) return LOFT_OK;
+  Rot4 r{};
+  r.nb = nb;
+  for (int b = 0; b < nb; ++b) r.k[b] = ((k[b] % 4) + 4) % 4;
+  scatter_rot_add_kernel<<<grid_for(P * S * S * (C / 4), kT, 148 * 16), kT, 0, stream>>>(
+      reinterpret_cast<const float4*>(gy), idx, reinterpret_cast<float4*>(gx), P, S, C / 4, r);
+  LOFT_CUDA_LAUNCH_CHECK("scatter_rot_add");
   return LOFT_OK;
 }
 

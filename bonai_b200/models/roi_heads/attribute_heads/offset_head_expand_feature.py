@@ -121,12 +121,23 @@ class OffsetHeadExpandFeature(nn.Module):
             raise NotImplementedError
         return M.rot90(feature, self.rotations[operation_idx] // 90)
 
-    def forward(self, x):
+    def branch_rotations(self):
+        """Quarter turns of the branches if `forward(x, expanded=...)` can take the branch-major
+        rotated batch [nb*P, C, S, S] from the caller (ops.roi.take_rows_rot assembles it straight
+        from the bbox head's RoI features); None if the head is not on the grouped path."""
+        rots = list(self.rotations)[:self.expand_feature_num]
+        if self._group_specs is None or self.expand_feature_num > 4 or not rots or rots[0] != 0 or \
+                any(r % 90 for r in rots):
+            return None
+        return [r // 90 for r in rots]
+
+    def forward(self, x, expanded=None):
         if x.size(0) == 0:
             return x.new_empty(x.size(0), 2 * self.expand_feature_num)
         if self._group_specs is not None:
             # branch-major batch [4P, C, 7, 7]; each layer of the 4 branches is ONE launch
-            y = torch.cat([self.expand_feature(x, idx) for idx in range(self.expand_feature_num)], 0)
+            y = expanded if expanded is not None else \
+                torch.cat([self.expand_feature(x, idx) for idx in range(self.expand_feature_num)], 0)
             for i, gspec in enumerate(self._group_specs):
                 trig = tuple(self.expand_convs[b][i].weight for b in range(self.expand_feature_num))
                 y = D.grouped_conv3x3(y, gspec, triggers=trig)

@@ -51,7 +51,9 @@ class LoftRoIHead(StandardRoIHead):
             offset_results = self._offset_forward_train(x, sampling_results,
                                                         bbox_results['bbox_feats'], gt_offsets,
                                                         img_metas,
-                                                        offset_feats=bbox_results.get('offset_feats'))
+                                                        offset_feats=bbox_results.get('offset_feats'),
+                                                        offset_expanded=bbox_results.get(
+                                                            'offset_expanded'))
             if offset_results['loss_offset'] is not None:
                 losses.update(offset_results['loss_offset'])
         return losses
@@ -86,7 +88,7 @@ class LoftRoIHead(StandardRoIHead):
         running the offset extractor over the same RoIs again."""
         if not (self.with_offset and torch.is_grad_enabled() and self._shares_bbox_rois()):
             return super()._bbox_forward_train(x, sampling_results, gt_bboxes, gt_labels, img_metas)
-        from ...ops.roi import take_rows
+        from ...ops.roi import take_rows, take_rows_rot
         rois = bbox2roi([res.bboxes for res in sampling_results])
         bbox_feats = self.bbox_roi_extractor(x[:self.bbox_roi_extractor.num_inputs], rois)
         rows, off = [], 0
@@ -95,12 +97,19 @@ class LoftRoIHead(StandardRoIHead):
             rows.append(torch.arange(off, off + n_pos, device=rois.device))
             off += n_all
         rows = torch.cat(rows)
-        offset_feats = None
+        offset_feats = offset_expanded = None
         if rows.numel() > 0:
-            bbox_feats, offset_feats = take_rows(bbox_feats, rows)
+            ks = getattr(self.offset_head, 'branch_rotations', lambda: None)()
+            if ks is not None:
+                # gather + the FOA branch rotations + their concatenation in one launch; branch 0
+                # is the identity, so the un-rotated features are its first P rows
+                bbox_feats, offset_expanded = take_rows_rot(bbox_feats, rows, ks)
+                offset_feats = offset_expanded[:rows.numel()]
+            else:
+                bbox_feats, offset_feats = take_rows(bbox_feats, rows)
         cls_score, bbox_pred = self.bbox_head(bbox_feats)
         bbox_results = dict(cls_score=cls_score, bbox_pred=bbox_pred, bbox_feats=bbox_feats,
-                            offset_feats=offset_feats)
+                            offset_feats=offset_feats, offset_expanded=offset_expanded)
         bbox_targets = self.bbox_head.get_targets(sampling_results, gt_bboxes, gt_labels,
                                                   self.train_cfg)
         loss_bbox = self.bbox_head.loss(cls_score, bbox_pred, rois, *bbox_targets)
@@ -108,8 +117,12 @@ class LoftRoIHead(StandardRoIHead):
         return bbox_results
 
     def _offset_forward_train(self, x, sampling_results, bbox_feats, gt_offsets, img_metas,
-                              offset_feats=None):
-        if offset_feats is not None:
+                              offset_feats=None, offset_expanded=None):
+        if offset_expanded is not None:
+            offset_results = dict(offset_pred=self.offset_head(offset_feats,
+                                                               expanded=offset_expanded),
+                                  offset_feats=offset_feats)
+        elif offset_feats is not None:
             offset_results = dict(offset_pred=self.offset_head(offset_feats),
                                   offset_feats=offset_feats)
         else:

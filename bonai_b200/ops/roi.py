@@ -112,6 +112,51 @@ class _TakeRows(Function):
         return g_full, None
 
 
+class _TakeRowsRot(Function):
+    """feats [K,C,S,S] -> (feats, y [nb*P,C,S,S]) with y[b*P + p] = rot90(feats[rows[p]], ks[b]):
+    `_TakeRows` fused with the FOA branch rotations and their concatenation (one launch instead of
+    gather + one rot90 per branch + cat); the backward sums the branches' un-rotated gradients
+    into the rows of the full gradient in place."""
+
+    @staticmethod
+    def forward(ctx, feats, rows, ks):
+        ctx.set_materialize_grads(False)
+        fn = nhwc(feats)
+        K, S, S2, C = fn.shape
+        assert S == S2
+        P = int(rows.numel())
+        nb = len(ks)
+        out = new_nhwc(nb * P, C, S, S, feats.device)
+        rows = rows.contiguous().long()
+        karr = (ctypes.c_int * nb)(*[int(k) for k in ks])
+        L.call('gather_rot', L.ptr(fn), L.ptr(rows), L.ptr(out.permute(0, 2, 3, 1)), L.ll(P), i32(S),
+               i32(C), karr, i32(nb), L.stream())
+        ctx.save_for_backward(rows)
+        ctx.meta = (tuple(feats.shape), karr, nb)
+        return feats, out
+
+    @staticmethod
+    def backward(ctx, g_full, g_y):
+        (rows,) = ctx.saved_tensors
+        (K, C, S, S2), karr, nb = ctx.meta
+        if g_y is None:
+            return g_full, None, None
+        if g_full is None:
+            g_full = new_nhwc(K, C, S, S2, g_y.device).zero_()
+        gf = g_full.permute(0, 2, 3, 1)
+        if not gf.is_contiguous():
+            gf = gf.contiguous()
+            g_full = gf.permute(0, 3, 1, 2)
+        L.call('scatter_rot_add', L.ptr(nhwc(g_y)), L.ptr(rows), L.ptr(gf), L.ll(rows.numel()),
+               i32(S), i32(C), karr, i32(nb), L.stream())
+        return g_full, None, None
+
+
+def take_rows_rot(feats, rows, ks):
+    """(feats, cat_b rot90(feats[rows], ks[b])) with the shared-gradient backward; rows unique."""
+    return _TakeRowsRot.apply(feats, rows, tuple(ks))
+
+
 def take_rows(feats, rows):
     """(feats, feats[rows]) with the shared-gradient backward of `_TakeRows`; `rows` unique."""
     return _TakeRows.apply(feats, rows)

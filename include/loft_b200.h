@@ -145,6 +145,14 @@ int loft_gather_rows(const float* src, const long long* idx, float* dst, long lo
                      long long cols, cudaStream_t stream);
 int loft_scatter_add_rows(const float* src, const long long* idx, float* dst, long long rows,
                           long long cols, cudaStream_t stream);
+/* FOA input assembly fused with the row gather (offset_head_expand_feature.py:163-214: one
+ * affine_grid + grid_sample rotation per branch, == rot90 for multiples of 90 degrees):
+ * y[b*P + p] = rot90(x[idx[p]], k[b]) for nb <= 4 branches, x / y NHWC [*, S, S, C];
+ * backward: gx[idx[p]] += sum_b rot90(gy[b*P + p], -k[b]) (idx unique) */
+int loft_gather_rot(const float* x, const long long* idx, float* y, long long P, int S, int C,
+                    const int* k, int nb, cudaStream_t stream);
+int loft_scatter_rot_add(const float* gy, const long long* idx, float* gx, long long P, int S, int C,
+                         const int* k, int nb, cudaStream_t stream);
 int loft_col2im(const float* dcol, float* dx, const float* mask, int N, int H, int W, int C, int kh,
                 int kw, int stride, int pad, int Kpad, cudaStream_t stream);
 int loft_maxpool3x3s2(const float* x, float* y, int N, int H, int W, int C, cudaStream_t stream);

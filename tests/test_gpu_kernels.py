@@ -543,3 +543,20 @@ def test_take_rows_shares_the_gradient():
     ref = torch.zeros_like(xr)
     ref[rows] = ws
     assert torch.allclose(x.grad, ref, rtol=0, atol=1e-6)
+
+
+def test_take_rows_rot_equals_gather_rot90_cat():
+    """_TakeRowsRot == (feats, cat_b rot90(feats[rows], k_b)) forward and backward."""
+    from bonai_b200.ops.roi import take_rows_rot
+    K, C, S = 23, 8, 7
+    x = rnd(K, C, S, S, seed=1).contiguous(memory_format=torch.channels_last).requires_grad_()
+    xr = x.detach().clone().requires_grad_()
+    rows = torch.tensor([1, 2, 9, 22], device='cuda')
+    ks = (0, 1, 2, 3)
+    full, y = take_rows_rot(x, rows, ks)
+    yr = torch.cat([torch.rot90(xr[rows], k, dims=(2, 3)) for k in ks], 0)
+    assert torch.equal(full, x) and torch.equal(y, yr)
+    wf, wy = rnd(K, C, S, S, seed=2), rnd(4 * rows.numel(), C, S, S, seed=3)
+    ((full * wf).sum() + (y * wy).sum()).backward()
+    ((xr * wf).sum() + (yr * wy).sum()).backward()
+    assert torch.allclose(x.grad, xr.grad, rtol=0, atol=1e-5)
