@@ -471,8 +471,10 @@ def main():
     host_batches = [to_model_inputs(make_batch(seed=rank * 100 + i, pinned=True, num_gt=gts[i]))
                     for i in range(N_ROTATE)]
     cur = trainer.stage(host_batches[0])
-    for j in range(3):                          # first use of the staging path (pinned copies,
-        nxt = trainer.stage(host_batches[(j + 1) % N_ROTATE])    # events, log buffers)
+    e2e_warm = max(args.warmup, N_ROTATE + 1)   # first use of the staging path (pinned copies,
+    for j in range(e2e_warm):                   # events, log buffers) and one full rotation of the
+        nxt = trainer.stage(host_batches[(j + 1) % N_ROTATE])    # batches: their tensors differ in
+                                                # size, the caching allocator grows until it has seen all
         trainer.train_step(cur, read_logs='async', prefetch=nxt)
         cur = nxt
     trainer.flush_logs()
@@ -556,6 +558,7 @@ def main():
                             'max': round(e2e_sorted[-1], 3), 'min': round(e2e_sorted[0], 3),
                             'host_p50': round(e2e_host[len(e2e_host) // 2], 3),
                             'host_max': round(e2e_host[-1], 3)},
+                'warmup': e2e_warm,
                 'note': 'inputs staged from pinned host memory on a copy stream (prefetch of the '
                         'next batch overlaps the step); every step\'s loss vector is copied to '
                         'pinned host memory asynchronously and read one step later, the last one '

@@ -4,6 +4,7 @@ There is deliberately no fallback: if the shared library is missing, or a call i
 CUDA device, the product path raises.  Build with ``python -c "import __graft_entry__ as g;
 g.build()"`` or ``make -C bonai_b200/csrc``.
 """
+import contextlib
 import ctypes
 import os
 
@@ -74,6 +75,40 @@ LAUNCHES = [0]          # kernels launched through this binding (bench.py reads 
 _KERNELS_PER_CALL = {'iou_assign': 2, 'grad_sqnorm': 1, 'poly_rasterize': 2, 'rpn_targets': 3}
 
 
+class Copy2D(ctypes.Structure):
+    """Mirror of ``loft_copy2d_t``."""
+    _fields_ = [('src', ctypes.c_void_p), ('lds', ctypes.c_longlong), ('dst', ctypes.c_void_p),
+                ('ldd', ctypes.c_longlong), ('rows', ctypes.c_longlong), ('cols', ctypes.c_int),
+                ('accumulate', ctypes.c_int), ('round_tf32', ctypes.c_int)]
+
+
+BATCH = None            # inside `batched_copies()`: the copy2d calls collected so far
+
+
+@contextlib.contextmanager
+def batched_copies():
+    """Collect every ``call('copy2d', ...)`` issued inside the block and run them as ONE
+    ``loft_copy2d_multi`` launch at its end.  Only for copies that are independent of each other
+    and of every other kernel launched inside the block (weight re-packs, gradient scatters)."""
+    global BATCH
+    if BATCH is not None or RECORD is not None:          # nested, or a launch program is recording
+        yield
+        return
+    BATCH = []
+    try:
+        yield
+    finally:
+        items, BATCH = BATCH, None
+        if items:
+            arr = (Copy2D * len(items))()
+            for a, (src, lds, dst, ldd, rows, cols, acc, rnd, st) in zip(arr, items):
+                a.src, a.lds, a.dst, a.ldd = src.value, lds.value, dst.value, ldd.value
+                a.rows, a.cols, a.accumulate, a.round_tf32 = rows.value, cols.value, acc.value, \
+                    rnd.value
+                assert st.value == items[0][-1].value, 'batched copies must share one stream'
+            call('copy2d_multi', arr, ctypes.c_int(len(items)), items[0][-1])
+
+
 RECORD = None           # set to a list to record (fn, args) of every call (trunk.Tape)
 TRACE = None            # set to a list to record (name, int args, start event, end event) per call
 
@@ -88,6 +123,9 @@ def _arg_summary(args):
 
 def call(name, *args):
     """Call ``loft_<name>`` and raise LoftError on a non-zero return code."""
+    if BATCH is not None and name == 'copy2d':
+        BATCH.append(args)
+        return
     fn = getattr(lib(), 'loft_' + name)
     if RECORD is not None:
         RECORD.append((name, fn, args))

@@ -40,6 +40,28 @@ __global__ void copy2d_kernel(const float* __restrict__ src, long long lds, floa
   }
 }
 
+// Up to kMaxCopies independent copy2d jobs in ONE launch (blockIdx.y = job): the per-step refresh of
+// the fused / padded head weights and the scatter of their gradients were ~40 launches of a few
+// hundred elements each, back to back on the critical path between the optimizer and the forward.
+constexpr int kMaxCopies = 48;
+struct CopyJobs {
+  loft_copy2d_t job[kMaxCopies];
+};
+
+__global__ void copy2d_multi_kernel(const CopyJobs jobs) {
+  const loft_copy2d_t& j = jobs.job[blockIdx.y];
+  const long long n = j.rows * j.cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / j.cols;
+    const int c = (int)(i - r * j.cols);
+    float v = j.src[r * j.lds + c];
+    if (j.round_tf32) v = tf32_rna(v);
+    float* d = j.dst + r * j.ldd + c;
+    *d = j.accumulate ? (*d + v) : v;
+  }
+}
+
 // Generic 3-axis permute of a [A][B][C] tensor into [A][C][B] (dst) or back, with optional TF32
 // rounding / accumulation.  Covers fc (C,HW)->(HW,C) weight repacks and their gradient un-packs.
 __global__ void permute_acb_kernel(const float* __restrict__ src, float* __restrict__ dst, int A,
@@ -683,6 +705,27 @@ int loft_copy2d(const float* src, long long lds, float* dst, long long ldd, long
   copy2d_kernel<<<grid_for(rows * cols), kT, 0, stream>>>(src, lds, dst, ldd, rows, cols,
                                                            accumulate, round_tf32);
   LOFT_CUDA_LAUNCH_CHECK("copy2d");
+  return LOFT_OK;
+}
+
+int loft_copy2d_multi(const loft_copy2d_t* items, int n, cudaStream_t stream) {
+  LOFT_CHECK_ARG(items || n == 0, "copy2d_multi: null pointer");
+  for (int o = 0; o < n; o += kMaxCopies) {
+    const int m = n - o < kMaxCopies ? n - o : kMaxCopies;
+    CopyJobs jobs{};
+    long long big = 0;
+    for (int i = 0; i < m; ++i) {
+      jobs.job[i] = items[o + i];
+      LOFT_CHECK_ARG((jobs.job[i].src && jobs.job[i].dst) || jobs.job[i].rows * jobs.job[i].cols == 0,
+                     "copy2d_multi: null pointer in job %d", o + i);
+      const long long e = jobs.job[i].rows * jobs.job[i].cols;
+      big = e > big ? e : big;
+    }
+    if (big == 0) continue;
+    dim3 grid(grid_for(big, kT, 64), m);
+    copy2d_multi_kernel<<<grid, kT, 0, stream>>>(jobs);
+    LOFT_CUDA_LAUNCH_CHECK("copy2d_multi");
+  }
   return LOFT_OK;
 }
 

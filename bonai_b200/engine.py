@@ -275,10 +275,11 @@ class ParamStore:
         their packed-weight gradients into the parameter gradients now and tell the listeners."""
         if not self.heads_done_hooks:
             return
-        for pk in self.packed:
-            if pk.owner.startswith('roi_head') and not pk.scattered:
-                pk.scatter()
-                pk.scattered = True
+        with L.batched_copies():
+            for pk in self.packed:
+                if pk.owner.startswith('roi_head') and not pk.scattered:
+                    pk.scatter()
+                    pk.scattered = True
         for fn in self.heads_done_hooks:
             fn()
 
@@ -322,8 +323,9 @@ class ParamStore:
                    L.ptr(g['shift']), L.ptr(g['rstd']), ctypes.c_int(g['C']), L.stream())
             self._fold_weights(gi)
         self._frozen_ready = True
-        for pk in self.packed:
-            pk.build()
+        with L.batched_copies():            # the builds' small copies: one launch
+            for pk in self.packed:
+                pk.build()
 
     def begin_step(self):
         """Zero the gradient buffers (weight-gradient kernels accumulate atomically)."""
@@ -369,10 +371,11 @@ class ParamStore:
         self.join_wgrad_stream()
         # packed gradients first: a packed weight may belong to a BN-folded conv (HRNet stem),
         # whose gamma gradient bn_finalize derives from the un-packed weight gradient
-        for pk in self.packed:
-            if not pk.scattered:
-                pk.scatter()
-                pk.scattered = True
+        with L.batched_copies():
+            for pk in self.packed:
+                if not pk.scattered:
+                    pk.scatter()
+                    pk.scattered = True
         self._bn_finalize()
         for p, g in self._grad_views:
             if g is not None and p.grad is not g:

@@ -108,6 +108,19 @@ void loft_debug_set_trace(unsigned long long* buf);
  * (affine_grid+grid_sample == rot90); optimizer: mmcv OptimizerHook(grad_clip) +
  * torch.optim.SGD as configured by configs/_base_/schedules/schedule_2x_bonai.py:2-3. */
 int loft_fill(float* p, long long n, float v, cudaStream_t stream);
+/* several independent loft_copy2d jobs in one launch (the per-step refresh of fused / padded head
+ * weights and the scatter of their gradients) */
+typedef struct {
+  const float* src;
+  long long lds;
+  float* dst;
+  long long ldd;
+  long long rows;
+  int cols;
+  int accumulate;
+  int round_tf32;
+} loft_copy2d_t;
+int loft_copy2d_multi(const loft_copy2d_t* items, int n, cudaStream_t stream);
 int loft_copy2d(const float* src, long long lds, float* dst, long long ldd, long long rows, int cols,
                 int accumulate, int round_tf32, cudaStream_t stream);
 int loft_permute_acb(const float* src, float* dst, int A, int B, int C, int accumulate,
