@@ -119,7 +119,10 @@ class FCNMaskHead(nn.Module):
         for cm, spec in zip(self.convs, self._conv_specs):
             x = D.conv(x, spec, triggers=(cm.conv.weight, cm.conv.bias))
         x = D.deconv2x2(x, self._up_spec, triggers=(self.upsample.weight, self.upsample.bias))
-        fused = D.conv(x, self._logit_spec, triggers=(self.conv_logits.weight,))
+        if D.narrow_head_ok(self._logit_spec, x):       # 256 -> 1 channel: HBM-bound, no GEMM tile
+            fused = D.narrow_head(x, self._logit_spec, triggers=(self.conv_logits.weight,))
+        else:
+            fused = D.conv(x, self._logit_spec, triggers=(self.conv_logits.weight,))
         mask_pred = fused[:, :self._n_out]
         mask_pred._loft_fused = fused
         return mask_pred

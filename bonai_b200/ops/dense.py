@@ -9,6 +9,7 @@ weight gradients afterwards, engine._bn_finalize); the Functions return ``None``
 model does not go through these Functions in training -- see bonai_b200/trunk.py.
 """
 import ctypes
+import os
 
 import torch
 from torch.autograd import Function
@@ -284,6 +285,57 @@ def conv(x, spec, residual=None, triggers=()):
         return x.new_zeros((0, spec.cout or spec.wref.w.shape[0], (H + 2 * pad - k) // s + 1,
                             (W + 2 * pad - k) // s + 1))
     return _ConvFn.apply(x, residual, spec, *triggers)
+
+
+class _NarrowHeadFn(Function):
+    """1x1 conv with <= 4 (padded) output channels and no activation as HBM-bound warp-per-pixel
+    kernels (`loft_narrow_head_fwd/bwd`) instead of a 128-row tensor-core tile that is almost
+    entirely padding: same ConvSpec protocol as `_ConvFn` (premask_in, in_colsum, bias_grad)."""
+
+    @staticmethod
+    def forward(ctx, x, spec, *triggers):
+        N, C, H, W = x.shape
+        xn = nhwc(x)
+        w = spec.wref.w
+        y = new_nhwc(N, w.shape[0], H, W, x.device)
+        L.call('narrow_head_fwd', L.ptr(xn), L.ptr(w), L.ptr(spec.bias), L.ptr(y.permute(0, 2, 3, 1)),
+               L.ll(N * H * W), i32(C), L.stream())
+        ctx.spec = spec
+        ctx.save_for_backward(xn)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        spec = ctx.spec
+        (xn,) = ctx.saved_tensors
+        _queue_finalize(spec.store)
+        N, H, W, C = xn.shape
+        dyn = nhwc(dy)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = new_nhwc(N, C, H, W, dy.device)
+        L.call('narrow_head_bwd', L.ptr(dyn), L.ptr(xn), L.ptr(spec.wref.w),
+               L.ptr(dx.permute(0, 2, 3, 1)) if dx is not None else None, L.ptr(spec.wref.grad),
+               L.ptr(spec.bias_grad) if not spec.bias_by_consumer else None,
+               L.ptr(spec.in_colsum) if dx is not None else None, L.ll(N * H * W), i32(C),
+               i32(1 if spec.premask_in else 0), L.stream())
+        return (dx, None) + (None,) * (len(ctx.needs_input_grad) - 2)
+
+
+def narrow_head_ok(spec, x):
+    """`conv(x, spec)` can run as `_NarrowHeadFn`: 1x1/s1, <= 4 padded outputs, no activation,
+    no output rounding, 128 / 256 / 512 input channels."""
+    return (os.environ.get('LOFT_NARROW_HEAD', '1') != '0' and spec.ksize == 1 and
+            spec.stride == 1 and spec.padding == 0 and not spec.relu and spec.bn is None and
+            not spec.round_out and spec.wref.w.dim() == 2 and spec.wref.w.shape[0] == 4 and
+            x.dim() == 4 and x.shape[1] in (128, 256, 512) and spec.wref.w.shape[1] == x.shape[1])
+
+
+def narrow_head(x, spec, triggers=()):
+    if x.shape[0] == 0:
+        N, _, H, W = x.shape
+        return x.new_zeros((0, spec.wref.w.shape[0], H, W))
+    return _NarrowHeadFn.apply(x, spec, *triggers)
 
 
 def conv_nograd(x, spec, residual=None):
