@@ -470,57 +470,72 @@ __global__ void scatter_rot_add_kernel(const float4* __restrict__ gy,
 // time per pass over x.  Here one warp owns a pixel row (16-byte loads, shuffle reduction) and the
 // backward is ONE pass: dx = mask(x > 0) * (dy . w) rounded to TF32, dW += dy^T x, db += sum dy and
 // the per-channel sum of dx (the bias gradient of the producing layer) from the same read of x.
+template <int NOUT>    // real output channels (1..4); the padded rows of w are not touched
 __global__ void __launch_bounds__(256)
 narrow_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ w,
                   const float* __restrict__ b, float4* __restrict__ y, long long P, int C4) {
-  extern __shared__ float4 sw[];                    // [4][C4]
-  for (int i = threadIdx.x; i < 4 * C4; i += blockDim.x) sw[i] = w[i];
+  extern __shared__ float4 sw[];                    // [NOUT][C4]
+  for (int i = threadIdx.x; i < NOUT * C4; i += blockDim.x) sw[i] = w[i];
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarp = (long long)gridDim.x * (blockDim.x >> 5);
-  float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (b) bias = make_float4(b[0], b[1], b[2], b[3]);
-  for (long long p = warp; p < P; p += nwarp) {
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    const float4* xr = x + p * C4;
+  float bias[4] = {0.f, 0.f, 0.f, 0.f};
+  if (b)
+    for (int j = 0; j < 4; ++j) bias[j] = b[j];
+  // two pixel rows per iteration: twice the loads in flight per warp
+  for (long long p = 2 * warp; p < P; p += 2 * nwarp) {
+    const bool two = p + 1 < P;
+    float a[2][NOUT];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int j = 0; j < NOUT; ++j) a[r][j] = 0.f;
+    const float4* x0 = x + p * C4;
+    const float4* x1 = x0 + (two ? C4 : 0);
     for (int i = lane; i < C4; i += 32) {
-      const float4 v = xr[i];
-      const float4 w0 = sw[i], w1 = sw[C4 + i], w2 = sw[2 * C4 + i], w3 = sw[3 * C4 + i];
-      a0 += v.x * w0.x + v.y * w0.y + v.z * w0.z + v.w * w0.w;
-      a1 += v.x * w1.x + v.y * w1.y + v.z * w1.z + v.w * w1.w;
-      a2 += v.x * w2.x + v.y * w2.y + v.z * w2.z + v.w * w2.w;
-      a3 += v.x * w3.x + v.y * w3.y + v.z * w3.z + v.w * w3.w;
+      const float4 v0 = x0[i], v1 = x1[i];
+#pragma unroll
+      for (int j = 0; j < NOUT; ++j) {
+        const float4 wj = sw[j * C4 + i];
+        a[0][j] += v0.x * wj.x + v0.y * wj.y + v0.z * wj.z + v0.w * wj.w;
+        a[1][j] += v1.x * wj.x + v1.y * wj.y + v1.z * wj.z + v1.w * wj.w;
+      }
     }
-    for (int o = 16; o > 0; o >>= 1) {
-      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-      a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int j = 0; j < NOUT; ++j)
+        for (int o = 16; o > 0; o >>= 1) a[r][j] += __shfl_xor_sync(0xffffffffu, a[r][j], o);
+    if (lane < 2 && (lane == 0 || two)) {
+      float o4[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o4[j] = (j < NOUT ? a[lane][j] : 0.f) + bias[j];
+      y[p + lane] = make_float4(o4[0], o4[1], o4[2], o4[3]);
     }
-    if (lane == 0) y[p] = make_float4(a0 + bias.x, a1 + bias.y, a2 + bias.z, a3 + bias.w);
   }
 }
 
-template <int T>       // float4 columns per lane: C = 128 * T
+template <int T, int NOUT>       // float4 columns per lane (C = 128 * T), real output channels
 __global__ void __launch_bounds__(256)
 narrow_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ x,
                   const float4* __restrict__ w, float4* __restrict__ dx, float* __restrict__ dw,
                   float* __restrict__ db, float* __restrict__ colsum, long long P, int premask) {
   constexpr int C4 = 32 * T;
-  __shared__ float s_red[5 * C4 * 4 + 4];           // dW [4][C], colsum [C], db [4]
-  for (int i = threadIdx.x; i < 5 * C4 * 4 + 4; i += blockDim.x) s_red[i] = 0.f;
+  constexpr int C = 4 * C4;
+  __shared__ float s_red[(NOUT + 1) * C + 4];       // dW [NOUT][C], colsum [C], db [4]
+  for (int i = threadIdx.x; i < (NOUT + 1) * C + 4; i += blockDim.x) s_red[i] = 0.f;
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarp = (long long)gridDim.x * (blockDim.x >> 5);
-  float4 wr[4][T], gw[4][T], cs[T];
-  float4 gb = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 wr[NOUT][T], gw[NOUT][T], cs[T];
+  float gb[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int t = 0; t < T; ++t) {
     cs[t] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NOUT; ++j) {
       wr[j][t] = w[j * C4 + lane + 32 * t];
       gw[j][t] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
@@ -528,14 +543,15 @@ narrow_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ x,
   for (long long p = warp; p < P; p += nwarp) {
     const float4 d = dy[p];
     const float dj[4] = {d.x, d.y, d.z, d.w};
-    gb.x += d.x; gb.y += d.y; gb.z += d.z; gb.w += d.w;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) gb[j] += dj[j];
 #pragma unroll
     for (int t = 0; t < T; ++t) {
       const long long o = p * C4 + lane + 32 * t;
       const float4 xv = x[o];
       float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < NOUT; ++j) {
         g.x += dj[j] * wr[j][t].x; g.y += dj[j] * wr[j][t].y;
         g.z += dj[j] * wr[j][t].z; g.w += dj[j] * wr[j][t].w;
         gw[j][t].x += dj[j] * xv.x; gw[j][t].y += dj[j] * xv.y;
@@ -555,35 +571,43 @@ narrow_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ x,
   for (int t = 0; t < T; ++t) {
     const int c = (lane + 32 * t) * 4;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      atomicAdd(&s_red[j * C4 * 4 + c + 0], gw[j][t].x);
-      atomicAdd(&s_red[j * C4 * 4 + c + 1], gw[j][t].y);
-      atomicAdd(&s_red[j * C4 * 4 + c + 2], gw[j][t].z);
-      atomicAdd(&s_red[j * C4 * 4 + c + 3], gw[j][t].w);
+    for (int j = 0; j < NOUT; ++j) {
+      atomicAdd(&s_red[j * C + c + 0], gw[j][t].x);
+      atomicAdd(&s_red[j * C + c + 1], gw[j][t].y);
+      atomicAdd(&s_red[j * C + c + 2], gw[j][t].z);
+      atomicAdd(&s_red[j * C + c + 3], gw[j][t].w);
     }
-    atomicAdd(&s_red[4 * C4 * 4 + c + 0], cs[t].x);
-    atomicAdd(&s_red[4 * C4 * 4 + c + 1], cs[t].y);
-    atomicAdd(&s_red[4 * C4 * 4 + c + 2], cs[t].z);
-    atomicAdd(&s_red[4 * C4 * 4 + c + 3], cs[t].w);
+    atomicAdd(&s_red[NOUT * C + c + 0], cs[t].x);
+    atomicAdd(&s_red[NOUT * C + c + 1], cs[t].y);
+    atomicAdd(&s_red[NOUT * C + c + 2], cs[t].z);
+    atomicAdd(&s_red[NOUT * C + c + 3], cs[t].w);
   }
-  if (lane == 0) {                                  // every lane saw the same dy rows
-    atomicAdd(&s_red[5 * C4 * 4 + 0], gb.x);
-    atomicAdd(&s_red[5 * C4 * 4 + 1], gb.y);
-    atomicAdd(&s_red[5 * C4 * 4 + 2], gb.z);
-    atomicAdd(&s_red[5 * C4 * 4 + 3], gb.w);
-  }
+  if (lane == 0)                                    // every lane saw the same dy rows
+    for (int j = 0; j < 4; ++j) atomicAdd(&s_red[(NOUT + 1) * C + j], gb[j]);
   __syncthreads();
-  for (int i = threadIdx.x; i < 5 * C4 * 4 + 4; i += blockDim.x) {
+  for (int i = threadIdx.x; i < (NOUT + 1) * C + 4; i += blockDim.x) {
     const float v = s_red[i];
     if (v == 0.f) continue;
-    if (i < 4 * C4 * 4) {
+    if (i < NOUT * C) {
       if (dw) atomicAdd(&dw[i], v);
-    } else if (i < 5 * C4 * 4) {
-      if (colsum) atomicAdd(&colsum[i - 4 * C4 * 4], v);
+    } else if (i < (NOUT + 1) * C) {
+      if (colsum) atomicAdd(&colsum[i - NOUT * C], v);
     } else if (db) {
-      atomicAdd(&db[i - 5 * C4 * 4], v);
+      atomicAdd(&db[i - (NOUT + 1) * C], v);
     }
   }
+}
+
+template <int NOUT>
+static void narrow_bwd_launch(int grid, cudaStream_t stream, int C, const float4* dy,
+                              const float4* x, const float4* w, float4* dx, float* dw, float* db,
+                              float* colsum, long long P, int premask) {
+  if (C == 128)
+    narrow_bwd_kernel<1, NOUT><<<grid, 256, 0, stream>>>(dy, x, w, dx, dw, db, colsum, P, premask);
+  else if (C == 256)
+    narrow_bwd_kernel<2, NOUT><<<grid, 256, 0, stream>>>(dy, x, w, dx, dw, db, colsum, P, premask);
+  else
+    narrow_bwd_kernel<4, NOUT><<<grid, 256, 0, stream>>>(dy, x, w, dx, dw, db, colsum, P, premask);
 }
 
 // dx[n,h,w,c] = sum over taps of dcol[(n,ho,wo),(r,s,c)] (gather form, no atomics), float4 over c
@@ -1018,24 +1042,33 @@ int loft_scatter_rot_add(const float* gy, const long long* idx, float* gx, long 
 }
 
 int loft_narrow_head_fwd(const float* x, const float* w, const float* b, float* y, long long P,
-                         int C, cudaStream_t stream) {
+                         int C, int n_out, cudaStream_t stream) {
   LOFT_CHECK_ARG(x && w && y, "narrow_head_fwd: null pointer");
-  LOFT_CHECK_SHAPE(C % 4 == 0 && C >= 4 && C <= 2048, "narrow_head_fwd: C=%d", C);
+  LOFT_CHECK_SHAPE(C % 4 == 0 && C >= 4 && C <= 2048 && n_out >= 1 && n_out <= 4,
+                   "narrow_head_fwd: C=%d n_out=%d", C, n_out);
   if (P == 0) return LOFT_OK;
-  const long long blocks = (P + 7) / 8;
+  const long long blocks = (P + 15) / 16;
   const int grid = (int)(blocks < 148 * 8 ? blocks : 148 * 8);
-  narrow_fwd_kernel<<<grid, 256, (size_t)4 * C * sizeof(float), stream>>>(
-      reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(w), b,
-      reinterpret_cast<float4*>(y), P, C / 4);
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  const float4* w4 = reinterpret_cast<const float4*>(w);
+  float4* y4 = reinterpret_cast<float4*>(y);
+  const size_t smem = (size_t)n_out * C * sizeof(float);
+  switch (n_out) {
+    case 1: narrow_fwd_kernel<1><<<grid, 256, smem, stream>>>(x4, w4, b, y4, P, C / 4); break;
+    case 2: narrow_fwd_kernel<2><<<grid, 256, smem, stream>>>(x4, w4, b, y4, P, C / 4); break;
+    case 3: narrow_fwd_kernel<3><<<grid, 256, smem, stream>>>(x4, w4, b, y4, P, C / 4); break;
+    default: narrow_fwd_kernel<4><<<grid, 256, smem, stream>>>(x4, w4, b, y4, P, C / 4); break;
+  }
   LOFT_CUDA_LAUNCH_CHECK("narrow_head_fwd");
   return LOFT_OK;
 }
 
 int loft_narrow_head_bwd(const float* dy, const float* x, const float* w, float* dx, float* dw,
-                         float* db, float* colsum, long long P, int C, int premask,
+                         float* db, float* colsum, long long P, int C, int n_out, int premask,
                          cudaStream_t stream) {
   LOFT_CHECK_ARG(dy && x && w, "narrow_head_bwd: null pointer");
-  LOFT_CHECK_SHAPE(C == 128 || C == 256 || C == 512, "narrow_head_bwd: C=%d must be 128, 256 or 512", C);
+  LOFT_CHECK_SHAPE((C == 128 || C == 256 || C == 512) && n_out >= 1 && n_out <= 4,
+                   "narrow_head_bwd: C=%d must be 128, 256 or 512, n_out=%d in 1..4", C, n_out);
   if (P == 0) return LOFT_OK;
   const long long blocks = (P + 7) / 8;
   const int grid = (int)(blocks < 148 * 4 ? blocks : 148 * 4);
@@ -1043,12 +1076,12 @@ int loft_narrow_head_bwd(const float* dy, const float* x, const float* w, float*
   const float4* x4 = reinterpret_cast<const float4*>(x);
   const float4* w4 = reinterpret_cast<const float4*>(w);
   float4* dx4 = reinterpret_cast<float4*>(dx);
-  if (C == 128)
-    narrow_bwd_kernel<1><<<grid, 256, 0, stream>>>(dy4, x4, w4, dx4, dw, db, colsum, P, premask);
-  else if (C == 256)
-    narrow_bwd_kernel<2><<<grid, 256, 0, stream>>>(dy4, x4, w4, dx4, dw, db, colsum, P, premask);
+  if (n_out == 1)
+    narrow_bwd_launch<1>(grid, stream, C, dy4, x4, w4, dx4, dw, db, colsum, P, premask);
+  else if (n_out == 2)
+    narrow_bwd_launch<2>(grid, stream, C, dy4, x4, w4, dx4, dw, db, colsum, P, premask);
   else
-    narrow_bwd_kernel<4><<<grid, 256, 0, stream>>>(dy4, x4, w4, dx4, dw, db, colsum, P, premask);
+    narrow_bwd_launch<4>(grid, stream, C, dy4, x4, w4, dx4, dw, db, colsum, P, premask);
   LOFT_CUDA_LAUNCH_CHECK("narrow_head_bwd");
   return LOFT_OK;
 }

@@ -113,6 +113,7 @@ class FCNMaskHead(nn.Module):
         self._logit_spec = D.ConvSpec(WeightRef(lw, lgw), ksize=1, bias=lb, bias_grad=lgb,
                                       round_out=False, store=store, premask_in=True)
         self._n_out = n_out
+        self._logit_spec.n_out = n_out
         D.link_chain(self._conv_specs + [self._up_spec, self._logit_spec])
 
     def forward(self, x):

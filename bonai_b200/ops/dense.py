@@ -91,6 +91,7 @@ class ConvSpec:
         # ReLU mask of its INPUT (x > 0) in its dgrad epilogue, so the producer of x (which sets
         # grad_premasked) receives an already-masked gradient and skips its own masking pass.
         self.premask_in = premask_in
+        self.n_out = None          # real rows of a zero-padded narrow head weight (narrow_head)
         self.grad_premasked = grad_premasked
 
 
@@ -299,7 +300,7 @@ class _NarrowHeadFn(Function):
         w = spec.wref.w
         y = new_nhwc(N, w.shape[0], H, W, x.device)
         L.call('narrow_head_fwd', L.ptr(xn), L.ptr(w), L.ptr(spec.bias), L.ptr(y.permute(0, 2, 3, 1)),
-               L.ll(N * H * W), i32(C), L.stream())
+               L.ll(N * H * W), i32(C), i32(spec.n_out or 4), L.stream())
         ctx.spec = spec
         ctx.save_for_backward(xn)
         return y
@@ -318,7 +319,7 @@ class _NarrowHeadFn(Function):
                L.ptr(dx.permute(0, 2, 3, 1)) if dx is not None else None, L.ptr(spec.wref.grad),
                L.ptr(spec.bias_grad) if not spec.bias_by_consumer else None,
                L.ptr(spec.in_colsum) if dx is not None else None, L.ll(N * H * W), i32(C),
-               i32(1 if spec.premask_in else 0), L.stream())
+               i32(spec.n_out or 4), i32(1 if spec.premask_in else 0), L.stream())
         return (dx, None) + (None,) * (len(ctx.needs_input_grad) - 2)
 
 

@@ -166,15 +166,16 @@ int loft_gather_rot(const float* x, const long long* idx, float* y, long long P,
                     const int* k, int nb, cudaStream_t stream);
 int loft_scatter_rot_add(const float* gy, const long long* idx, float* gx, long long P, int S, int C,
                          const int* k, int nb, cudaStream_t stream);
-/* 1x1 conv / linear head with at most 4 (padded) output channels over P rows of C channels, e.g.
- * the class-agnostic mask logits nn.Conv2d(256, 1, 1) (fcn_mask_head.py:118-126): w is [4][C] (rows
- * beyond the real outputs zero), y / dy are [P][4].  Backward in one pass over x: dx = (premask ?
- * x > 0 : 1) * (dy . w) rounded to TF32 (dx may be NULL), dw[4][C] += dy^T x, db[4] += sum dy,
- * colsum[C] += sum_p dx (bias gradient of the producing layer); C in {128, 256, 512} */
+/* 1x1 conv / linear head with at most 4 output channels over P rows of C channels, e.g. the
+ * class-agnostic mask logits nn.Conv2d(256, 1, 1) (fcn_mask_head.py:118-126): w is [4][C] of which
+ * the first n_out rows are real (the others zero, never read), y / dy are [P][4].  Backward in one
+ * pass over x: dx = (premask ? x > 0 : 1) * (dy . w) rounded to TF32 (dx may be NULL), dw[n_out][C]
+ * += dy^T x, db[4] += sum dy, colsum[C] += sum_p dx (bias gradient of the producing layer);
+ * C in {128, 256, 512} for the backward */
 int loft_narrow_head_fwd(const float* x, const float* w, const float* b, float* y, long long P,
-                         int C, cudaStream_t stream);
+                         int C, int n_out, cudaStream_t stream);
 int loft_narrow_head_bwd(const float* dy, const float* x, const float* w, float* dx, float* dw,
-                         float* db, float* colsum, long long P, int C, int premask,
+                         float* db, float* colsum, long long P, int C, int n_out, int premask,
                          cudaStream_t stream);
 int loft_col2im(const float* dcol, float* dx, const float* mask, int N, int H, int W, int C, int kh,
                 int kw, int stride, int pad, int Kpad, cudaStream_t stream);

@@ -562,22 +562,24 @@ def test_take_rows_rot_equals_gather_rot90_cat():
     assert torch.allclose(x.grad, xr.grad, rtol=0, atol=1e-5)
 
 
-@pytest.mark.parametrize('C', [128, 256, 512])
-def test_narrow_head_forward_backward(C):
+@pytest.mark.parametrize('C,n_out', [(128, 4), (256, 1), (256, 2), (512, 3)])
+def test_narrow_head_forward_backward(C, n_out):
     """loft_narrow_head_fwd/bwd (<= 4 output channels, warp per pixel) against fp32 autograd:
     outputs, data gradient with the ReLU mask of the input, weight / bias gradients and the
     per-channel sum of the data gradient (the producer's bias gradient), all from one pass."""
     from bonai_b200.engine import WeightRef
     from bonai_b200.ops import dense as D
-    N, H, W = 3, 28, 28
+    N, H, W = 3, 27, 27                               # odd row count: the 2-row loop tail
     x = tf32_round(rnd(N, C, H, W, seed=1)).contiguous(memory_format=torch.channels_last)
     x = x.requires_grad_()
     w = tf32_round(rnd(4, C, seed=2, scale=0.1))
+    w[n_out:] = 0                                     # padded rows
     b = rnd(4, seed=3)
     gw, gb, cs = torch.zeros_like(w), torch.zeros_like(b), torch.zeros(C, device='cuda')
     spec = D.ConvSpec(WeightRef(w, gw), ksize=1, bias=b, bias_grad=gb, round_out=False,
                       premask_in=True)
     spec.in_colsum = cs
+    spec.n_out = n_out
     assert D.narrow_head_ok(spec, x)
     y = D.narrow_head(x, spec)
     xr = x.detach().clone().requires_grad_()
@@ -585,9 +587,11 @@ def test_narrow_head_forward_backward(C):
     yr = F.conv2d(xr, wr[:, :, None, None], br)
     assert rel(y, yr) < 1e-5
     dy = rnd(N, 4, H, W, seed=4).contiguous(memory_format=torch.channels_last)
+    dy[:, n_out:] = 0              # the loss only differentiates the real outputs
     y.backward(dy)
     yr.backward(dy)
     dx_ref = xr.grad * (xr > 0)
     assert rel(x.grad, dx_ref) < TF32_TOL              # dx is rounded to TF32
-    assert rel(gw, wr.grad) < 1e-4 and rel(gb, br.grad) < 1e-4
+    assert rel(gw[:n_out], wr.grad[:n_out]) < 1e-4 and bool((gw[n_out:] == 0).all())
+    assert rel(gb, br.grad) < 1e-4
     assert rel(cs, x.grad.sum((0, 2, 3))) < 1e-4
