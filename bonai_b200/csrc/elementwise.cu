@@ -470,10 +470,24 @@ __global__ void scatter_rot_add_kernel(const float4* __restrict__ gy,
 // time per pass over x.  Here one warp owns a pixel row (16-byte loads, shuffle reduction) and the
 // backward is ONE pass: dx = mask(x > 0) * (dy . w) rounded to TF32, dW += dy^T x, db += sum dy and
 // the per-channel sum of dx (the bias gradient of the producing layer) from the same read of x.
+// Row r of a space-to-depth packed tensor [(n, h, w), (i, j)] (the un-shuffled output of a 2x2 /
+// stride-2 deconv GEMM) -> its pixel index in the [n, 2h + i, 2w + j] image; identity if sH == 0.
+__device__ __forceinline__ long long s2d_pixel(long long r, int sH, int sW) {
+  if (sH == 0) return r;
+  const int ij = (int)(r & 3);
+  long long t = r >> 2;
+  const int w = (int)(t % sW);
+  t /= sW;
+  const int h = (int)(t % sH);
+  const long long n = t / sH;
+  return (n * (2 * sH) + 2 * h + (ij >> 1)) * (2 * sW) + 2 * w + (ij & 1);
+}
+
 template <int NOUT>    // real output channels (1..4); the padded rows of w are not touched
 __global__ void __launch_bounds__(256)
 narrow_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ w,
-                  const float* __restrict__ b, float4* __restrict__ y, long long P, int C4) {
+                  const float* __restrict__ b, float4* __restrict__ y, long long P, int C4, int sH,
+                  int sW) {
   extern __shared__ float4 sw[];                    // [NOUT][C4]
   for (int i = threadIdx.x; i < NOUT * C4; i += blockDim.x) sw[i] = w[i];
   __syncthreads();
@@ -511,7 +525,7 @@ narrow_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ w,
       float o4[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) o4[j] = (j < NOUT ? a[lane][j] : 0.f) + bias[j];
-      y[p + lane] = make_float4(o4[0], o4[1], o4[2], o4[3]);
+      y[s2d_pixel(p + lane, sH, sW)] = make_float4(o4[0], o4[1], o4[2], o4[3]);
     }
   }
 }
@@ -520,7 +534,8 @@ template <int T, int NOUT>       // float4 columns per lane (C = 128 * T), real 
 __global__ void __launch_bounds__(256)
 narrow_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ x,
                   const float4* __restrict__ w, float4* __restrict__ dx, float* __restrict__ dw,
-                  float* __restrict__ db, float* __restrict__ colsum, long long P, int premask) {
+                  float* __restrict__ db, float* __restrict__ colsum, long long P, int premask,
+                  int sH, int sW) {
   constexpr int C4 = 32 * T;
   constexpr int C = 4 * C4;
   __shared__ float s_red[(NOUT + 1) * C + 4];       // dW [NOUT][C], colsum [C], db [4]
@@ -541,7 +556,7 @@ narrow_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ x,
     }
   }
   for (long long p = warp; p < P; p += nwarp) {
-    const float4 d = dy[p];
+    const float4 d = dy[s2d_pixel(p, sH, sW)];
     const float dj[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) gb[j] += dj[j];
@@ -601,13 +616,16 @@ narrow_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ x,
 template <int NOUT>
 static void narrow_bwd_launch(int grid, cudaStream_t stream, int C, const float4* dy,
                               const float4* x, const float4* w, float4* dx, float* dw, float* db,
-                              float* colsum, long long P, int premask) {
+                              float* colsum, long long P, int premask, int sH, int sW) {
   if (C == 128)
-    narrow_bwd_kernel<1, NOUT><<<grid, 256, 0, stream>>>(dy, x, w, dx, dw, db, colsum, P, premask);
+    narrow_bwd_kernel<1, NOUT><<<grid, 256, 0, stream>>>(dy, x, w, dx, dw, db, colsum, P, premask,
+                                                         sH, sW);
   else if (C == 256)
-    narrow_bwd_kernel<2, NOUT><<<grid, 256, 0, stream>>>(dy, x, w, dx, dw, db, colsum, P, premask);
+    narrow_bwd_kernel<2, NOUT><<<grid, 256, 0, stream>>>(dy, x, w, dx, dw, db, colsum, P, premask,
+                                                         sH, sW);
   else
-    narrow_bwd_kernel<4, NOUT><<<grid, 256, 0, stream>>>(dy, x, w, dx, dw, db, colsum, P, premask);
+    narrow_bwd_kernel<4, NOUT><<<grid, 256, 0, stream>>>(dy, x, w, dx, dw, db, colsum, P, premask,
+                                                         sH, sW);
 }
 
 // dx[n,h,w,c] = sum over taps of dcol[(n,ho,wo),(r,s,c)] (gather form, no atomics), float4 over c
@@ -1042,10 +1060,12 @@ int loft_scatter_rot_add(const float* gy, const long long* idx, float* gx, long 
 }
 
 int loft_narrow_head_fwd(const float* x, const float* w, const float* b, float* y, long long P,
-                         int C, int n_out, cudaStream_t stream) {
+                         int C, int n_out, int s2d_h, int s2d_w, cudaStream_t stream) {
   LOFT_CHECK_ARG(x && w && y, "narrow_head_fwd: null pointer");
   LOFT_CHECK_SHAPE(C % 4 == 0 && C >= 4 && C <= 2048 && n_out >= 1 && n_out <= 4,
                    "narrow_head_fwd: C=%d n_out=%d", C, n_out);
+  LOFT_CHECK_SHAPE(s2d_h == 0 || (s2d_h > 0 && s2d_w > 0 && P % (4ll * s2d_h * s2d_w) == 0),
+                   "narrow_head_fwd: rows do not tile %d x %d x 4 sub-pixels", s2d_h, s2d_w);
   if (P == 0) return LOFT_OK;
   const long long blocks = (P + 15) / 16;
   const int grid = (int)(blocks < 148 * 8 ? blocks : 148 * 8);
@@ -1054,10 +1074,10 @@ int loft_narrow_head_fwd(const float* x, const float* w, const float* b, float* 
   float4* y4 = reinterpret_cast<float4*>(y);
   const size_t smem = (size_t)n_out * C * sizeof(float);
   switch (n_out) {
-    case 1: narrow_fwd_kernel<1><<<grid, 256, smem, stream>>>(x4, w4, b, y4, P, C / 4); break;
-    case 2: narrow_fwd_kernel<2><<<grid, 256, smem, stream>>>(x4, w4, b, y4, P, C / 4); break;
-    case 3: narrow_fwd_kernel<3><<<grid, 256, smem, stream>>>(x4, w4, b, y4, P, C / 4); break;
-    default: narrow_fwd_kernel<4><<<grid, 256, smem, stream>>>(x4, w4, b, y4, P, C / 4); break;
+    case 1: narrow_fwd_kernel<1><<<grid, 256, smem, stream>>>(x4, w4, b, y4, P, C / 4, s2d_h, s2d_w); break;
+    case 2: narrow_fwd_kernel<2><<<grid, 256, smem, stream>>>(x4, w4, b, y4, P, C / 4, s2d_h, s2d_w); break;
+    case 3: narrow_fwd_kernel<3><<<grid, 256, smem, stream>>>(x4, w4, b, y4, P, C / 4, s2d_h, s2d_w); break;
+    default: narrow_fwd_kernel<4><<<grid, 256, smem, stream>>>(x4, w4, b, y4, P, C / 4, s2d_h, s2d_w); break;
   }
   LOFT_CUDA_LAUNCH_CHECK("narrow_head_fwd");
   return LOFT_OK;
@@ -1065,10 +1085,12 @@ int loft_narrow_head_fwd(const float* x, const float* w, const float* b, float* 
 
 int loft_narrow_head_bwd(const float* dy, const float* x, const float* w, float* dx, float* dw,
                          float* db, float* colsum, long long P, int C, int n_out, int premask,
-                         cudaStream_t stream) {
+                         int s2d_h, int s2d_w, cudaStream_t stream) {
   LOFT_CHECK_ARG(dy && x && w, "narrow_head_bwd: null pointer");
   LOFT_CHECK_SHAPE((C == 128 || C == 256 || C == 512) && n_out >= 1 && n_out <= 4,
                    "narrow_head_bwd: C=%d must be 128, 256 or 512, n_out=%d in 1..4", C, n_out);
+  LOFT_CHECK_SHAPE(s2d_h == 0 || (s2d_h > 0 && s2d_w > 0 && P % (4ll * s2d_h * s2d_w) == 0),
+                   "narrow_head_bwd: rows do not tile %d x %d x 4 sub-pixels", s2d_h, s2d_w);
   if (P == 0) return LOFT_OK;
   const long long blocks = (P + 7) / 8;
   const int grid = (int)(blocks < 148 * 4 ? blocks : 148 * 4);
@@ -1077,11 +1099,14 @@ int loft_narrow_head_bwd(const float* dy, const float* x, const float* w, float*
   const float4* w4 = reinterpret_cast<const float4*>(w);
   float4* dx4 = reinterpret_cast<float4*>(dx);
   if (n_out == 1)
-    narrow_bwd_launch<1>(grid, stream, C, dy4, x4, w4, dx4, dw, db, colsum, P, premask);
+    narrow_bwd_launch<1>(grid, stream, C, dy4, x4, w4, dx4, dw, db, colsum, P, premask, s2d_h,
+                         s2d_w);
   else if (n_out == 2)
-    narrow_bwd_launch<2>(grid, stream, C, dy4, x4, w4, dx4, dw, db, colsum, P, premask);
+    narrow_bwd_launch<2>(grid, stream, C, dy4, x4, w4, dx4, dw, db, colsum, P, premask, s2d_h,
+                         s2d_w);
   else
-    narrow_bwd_launch<4>(grid, stream, C, dy4, x4, w4, dx4, dw, db, colsum, P, premask);
+    narrow_bwd_launch<4>(grid, stream, C, dy4, x4, w4, dx4, dw, db, colsum, P, premask, s2d_h,
+                         s2d_w);
   LOFT_CUDA_LAUNCH_CHECK("narrow_head_bwd");
   return LOFT_OK;
 }

@@ -119,11 +119,18 @@ class FCNMaskHead(nn.Module):
     def forward(self, x):
         for cm, spec in zip(self.convs, self._conv_specs):
             x = D.conv(x, spec, triggers=(cm.conv.weight, cm.conv.bias))
-        x = D.deconv2x2(x, self._up_spec, triggers=(self.upsample.weight, self.upsample.bias))
-        if D.narrow_head_ok(self._logit_spec, x):       # 256 -> 1 channel: HBM-bound, no GEMM tile
-            fused = D.narrow_head(x, self._logit_spec, triggers=(self.conv_logits.weight,))
+        if D.deconv_logits_ok(self._up_spec, self._logit_spec, x):
+            # upsample + logits with the deconv output left in its GEMM layout (no pixel-shuffle
+            # store, no space-to-depth copy of its gradient)
+            fused = D.deconv_logits(x, self._up_spec, self._logit_spec,
+                                    triggers=(self.upsample.weight, self.upsample.bias,
+                                              self.conv_logits.weight))
         else:
-            fused = D.conv(x, self._logit_spec, triggers=(self.conv_logits.weight,))
+            x = D.deconv2x2(x, self._up_spec, triggers=(self.upsample.weight, self.upsample.bias))
+            if D.narrow_head_ok(self._logit_spec, x):   # 256 -> 1 channel: HBM-bound, no GEMM tile
+                fused = D.narrow_head(x, self._logit_spec, triggers=(self.conv_logits.weight,))
+            else:
+                fused = D.conv(x, self._logit_spec, triggers=(self.conv_logits.weight,))
         mask_pred = fused[:, :self._n_out]
         mask_pred._loft_fused = fused
         return mask_pred

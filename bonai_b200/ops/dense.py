@@ -300,7 +300,7 @@ class _NarrowHeadFn(Function):
         w = spec.wref.w
         y = new_nhwc(N, w.shape[0], H, W, x.device)
         L.call('narrow_head_fwd', L.ptr(xn), L.ptr(w), L.ptr(spec.bias), L.ptr(y.permute(0, 2, 3, 1)),
-               L.ll(N * H * W), i32(C), i32(spec.n_out or 4), L.stream())
+               L.ll(N * H * W), i32(C), i32(spec.n_out or 4), i32(0), i32(0), L.stream())
         ctx.spec = spec
         ctx.save_for_backward(xn)
         return y
@@ -319,7 +319,7 @@ class _NarrowHeadFn(Function):
                L.ptr(dx.permute(0, 2, 3, 1)) if dx is not None else None, L.ptr(spec.wref.grad),
                L.ptr(spec.bias_grad) if not spec.bias_by_consumer else None,
                L.ptr(spec.in_colsum) if dx is not None else None, L.ll(N * H * W), i32(C),
-               i32(spec.n_out or 4), i32(1 if spec.premask_in else 0), L.stream())
+               i32(spec.n_out or 4), i32(1 if spec.premask_in else 0), i32(0), i32(0), L.stream())
         return (dx, None) + (None,) * (len(ctx.needs_input_grad) - 2)
 
 
@@ -480,6 +480,81 @@ class _Deconv2x2Fn(Function):
             L.call('gemm_dgrad', L.ptr(dzp), L.ptr(w), L.ptr(dx.permute(0, 2, 3, 1)), L.ll(P),
                    i32(Cin), i32(4 * Co), L.ll(4 * Co), L.ll(Cin), L.ll(Cin), ctypes.byref(e), st)
         return (dx, None) + (None,) * (len(ctx.needs_input_grad) - 2)
+
+
+class _DeconvLogitsFn(Function):
+    """ConvTranspose2d(k=2, s=2) + bias + ReLU followed by a narrow 1x1 head (the mask head's
+    upsample + conv_logits, fcn_mask_head.py:77-83,118-126) with the deconv output kept in the
+    UN-shuffled GEMM layout [(n, h, w), (i, j, co)]: the head is per pixel, so it reads those rows
+    as they are and only its 4-wide output / gradient rows are addressed in image order
+    (`s2d_*` of loft_narrow_head_*).  The backward's dz then already has the layout the deconv's
+    weight / data gradient GEMMs take -- the 160 MB space-to-depth copy of `_Deconv2x2Fn.backward`
+    (0.11 ms) and the pixel-shuffle store of its forward are gone."""
+
+    @staticmethod
+    def forward(ctx, x, up, lg, *triggers):
+        w = up.wref.w
+        N, Cin, H, W = x.shape
+        Co = w.shape[0] // 4
+        P = N * H * W
+        xn = nhwc(x)
+        yp = torch.empty((P, 4 * Co), device=x.device, dtype=torch.float32)
+        e = L.make_epilogue(shift=up.bias, relu=up.relu, round_out=up.round_out)
+        L.call('gemm_fprop', L.ptr(xn), L.ptr(w), L.ptr(yp), L.ll(P), i32(Cin), i32(4 * Co),
+               L.ll(Cin), L.ll(Cin), L.ll(4 * Co), i32(1), i32(P), ctypes.byref(e), L.stream())
+        out = new_nhwc(N, lg.wref.w.shape[0], 2 * H, 2 * W, x.device)
+        L.call('narrow_head_fwd', L.ptr(yp), L.ptr(lg.wref.w), L.ptr(lg.bias),
+               L.ptr(out.permute(0, 2, 3, 1)), L.ll(4 * P), i32(Co), i32(lg.n_out or 4), i32(H),
+               i32(W), L.stream())
+        ctx.specs = (up, lg)
+        ctx.save_for_backward(xn, yp)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        up, lg = ctx.specs
+        xn, yp = ctx.saved_tensors
+        _queue_finalize(up.store)
+        st = L.stream()
+        N, H, W, Cin = xn.shape
+        P = N * H * W
+        w = up.wref.w
+        Co = w.shape[0] // 4
+        dzp = torch.empty_like(yp)
+        # dz of the deconv (ReLU mask of its output applied, rounded), the head's weight / bias
+        # gradients and the deconv's bias gradient (per-channel sum of dz) in one pass over yp
+        L.call('narrow_head_bwd', L.ptr(nhwc(dy)), L.ptr(yp), L.ptr(lg.wref.w), L.ptr(dzp),
+               L.ptr(lg.wref.grad), L.ptr(lg.bias_grad), L.ptr(up.bias_grad), L.ll(4 * P), i32(Co),
+               i32(lg.n_out or 4), i32(1 if up.relu else 0), i32(H), i32(W), st)
+        if up.wref.grad is not None:
+            L.call('gemm_wgrad', L.ptr(dzp), L.ptr(xn), L.ptr(up.wref.grad), L.ll(P), i32(Cin),
+                   i32(4 * Co), L.ll(4 * Co), L.ll(Cin), L.ll(Cin), st)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = new_nhwc(N, Cin, H, W, dy.device)
+            e = L.make_epilogue(round_out=True, mask=xn if up.premask_in else None,
+                                colsum=up.in_colsum)
+            L.call('gemm_dgrad', L.ptr(dzp), L.ptr(w), L.ptr(dx.permute(0, 2, 3, 1)), L.ll(P),
+                   i32(Cin), i32(4 * Co), L.ll(4 * Co), L.ll(Cin), L.ll(Cin), ctypes.byref(e), st)
+        return (dx, None, None) + (None,) * (len(ctx.needs_input_grad) - 3)
+
+
+def deconv_logits_ok(up, lg, x):
+    """`deconv2x2(x, up)` followed by `conv(., lg)` can run as `_DeconvLogitsFn`."""
+    Co = up.wref.w.shape[0] // 4
+    return (os.environ.get('LOFT_NARROW_HEAD', '1') != '0' and
+            os.environ.get('LOFT_DECONV_LOGITS', '1') != '0' and lg.ksize == 1 and lg.stride == 1 and
+            lg.padding == 0 and not lg.relu and lg.bn is None and not lg.round_out and
+            lg.wref.w.dim() == 2 and lg.wref.w.shape[0] == 4 and lg.wref.w.shape[1] == Co and
+            Co in (128, 256, 512) and up.bn is None and lg.bias_grad is not None and
+            up.bias_grad is not None and x.dim() == 4)
+
+
+def deconv_logits(x, up, lg, triggers=()):
+    if x.shape[0] == 0:
+        N, _, H, W = x.shape
+        return x.new_zeros((0, lg.wref.w.shape[0], 2 * H, 2 * W))
+    return _DeconvLogitsFn.apply(x, up, lg, *triggers)
 
 
 def deconv2x2(x, spec, triggers=()):

@@ -171,12 +171,14 @@ int loft_scatter_rot_add(const float* gy, const long long* idx, float* gx, long 
  * the first n_out rows are real (the others zero, never read), y / dy are [P][4].  Backward in one
  * pass over x: dx = (premask ? x > 0 : 1) * (dy . w) rounded to TF32 (dx may be NULL), dw[n_out][C]
  * += dy^T x, db[4] += sum dy, colsum[C] += sum_p dx (bias gradient of the producing layer);
- * C in {128, 256, 512} for the backward */
+ * C in {128, 256, 512} for the backward.  s2d_h, s2d_w > 0: the rows of x / dx are the UN-shuffled
+ * output [(n, h, w), (i, j)] of a 2x2 / stride-2 deconv GEMM over an s2d_h x s2d_w grid (its
+ * gradient needs exactly that layout), while y / dy are in image order [n, 2h + i, 2w + j] */
 int loft_narrow_head_fwd(const float* x, const float* w, const float* b, float* y, long long P,
-                         int C, int n_out, cudaStream_t stream);
+                         int C, int n_out, int s2d_h, int s2d_w, cudaStream_t stream);
 int loft_narrow_head_bwd(const float* dy, const float* x, const float* w, float* dx, float* dw,
                          float* db, float* colsum, long long P, int C, int n_out, int premask,
-                         cudaStream_t stream);
+                         int s2d_h, int s2d_w, cudaStream_t stream);
 int loft_col2im(const float* dcol, float* dx, const float* mask, int N, int H, int W, int C, int kh,
                 int kw, int stride, int pad, int Kpad, cudaStream_t stream);
 int loft_maxpool3x3s2(const float* x, float* y, int N, int H, int W, int C, cudaStream_t stream);

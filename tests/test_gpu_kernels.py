@@ -595,3 +595,65 @@ def test_narrow_head_forward_backward(C, n_out):
     assert rel(gw[:n_out], wr.grad[:n_out]) < 1e-4 and bool((gw[n_out:] == 0).all())
     assert rel(gb, br.grad) < 1e-4
     assert rel(cs, x.grad.sum((0, 2, 3))) < 1e-4
+
+
+def test_deconv_logits_fused_equals_separate_layers():
+    """_DeconvLogitsFn (deconv output kept in its GEMM layout, narrow head addressed through the
+    space-to-depth row map) == deconv2x2 + narrow head / 1x1 conv as separate layers: logits and
+    every gradient."""
+    from bonai_b200.engine import WeightRef
+    from bonai_b200.ops import dense as D
+    N, Ci, Co, H, W = 5, 64, 128, 6, 7
+
+    def build():
+        wu = tf32_round(rnd(4 * Co, Ci, seed=2, scale=0.1))
+        bu = rnd(Co, seed=3, scale=0.1)
+        b4 = bu.repeat(4).contiguous()
+        wl = torch.zeros(4, Co, device='cuda')
+        wl[0] = tf32_round(rnd(Co, seed=4, scale=0.1))
+        bl = torch.zeros(4, device='cuda')
+        bl[0] = 0.3
+        g = dict(wu=torch.zeros_like(wu), bu=torch.zeros_like(bu), wl=torch.zeros_like(wl),
+                 bl=torch.zeros_like(bl))
+        up = D.ConvSpec(WeightRef(wu, g['wu']), relu=True, bias=b4, bias_grad=g['bu'],
+                        grad_premasked=True)
+        lg = D.ConvSpec(WeightRef(wl, g['wl']), ksize=1, bias=bl, bias_grad=g['bl'], round_out=False,
+                        premask_in=True)
+        lg.n_out = 1
+        D.link_chain([up, lg])
+        return up, lg, g
+
+    x0 = tf32_round(rnd(N, Ci, H, W, seed=1)).contiguous(memory_format=torch.channels_last)
+    dy = torch.zeros(N, 4, 2 * H, 2 * W, device='cuda').contiguous(memory_format=torch.channels_last)
+    dy[:, 0] = tf32_round(rnd(N, 2 * H, 2 * W, seed=5))     # on the TF32 grid: exact in both paths
+    up, lg, ga = build()
+    xa = x0.clone().requires_grad_()
+    assert D.deconv_logits_ok(up, lg, xa)
+    ya = D.deconv_logits(xa, up, lg)
+    ya.backward(dy)
+    # (a) the separate layers of the product
+    up2, lg2, gb = build()
+    xb = x0.clone().requires_grad_()
+    yb = D.conv(D.deconv2x2(xb, up2), lg2)
+    yb.backward(dy)
+    assert rel(ya[:, :1], yb[:, :1]) < 1e-5
+    assert rel(xa.grad, xb.grad) < TF32_TOL
+    for k in ('wu', 'bu', 'wl', 'bl'):
+        ref = gb[k][:1] if k in ('wl', 'bl') else gb[k]
+        got = ga[k][:1] if k in ('wl', 'bl') else ga[k]
+        assert rel(got, ref) < GRAD_TOL, k
+    # (b) torch fp32: ConvTranspose2d(2, 2) + ReLU (output rounded to TF32, straight through) + 1x1
+    wu, bu, wl, bl = up.wref.w, up.bias[:Co], lg.wref.w, lg.bias
+    wt = wu.view(2, 2, Co, Ci).permute(3, 2, 0, 1).contiguous().requires_grad_()   # [Ci,Co,i,j]
+    bt, wlt, blt = bu.clone().requires_grad_(), wl[:1].clone().requires_grad_(), \
+        bl[:1].clone().requires_grad_()
+    xr = x0.clone().requires_grad_()
+    h = F.relu(F.conv_transpose2d(xr, wt, bt, stride=2))
+    h = h + (tf32_round(h.detach()) - h.detach())
+    yr = F.conv2d(h, wlt[:, :, None, None], blt)
+    yr.backward(dy[:, :1])
+    assert rel(ya[:, :1], yr) < TF32_TOL
+    assert rel(xa.grad, xr.grad) < 2e-3               # dz is rounded to TF32 before the dgrad GEMM
+    assert rel(ga['wu'].view(2, 2, Co, Ci).permute(3, 2, 0, 1), wt.grad) < GRAD_TOL
+    assert rel(ga['bu'], bt.grad) < GRAD_TOL
+    assert rel(ga['wl'][:1], wlt.grad) < GRAD_TOL and rel(ga['bl'][:1], blt.grad) < GRAD_TOL
