@@ -325,15 +325,23 @@ __global__ void nms_mask_seg_kernel(const float* __restrict__ boxes, const float
   mask[(long long)i * nw + colb] = bits;
 }
 
-// One block per (image, segment): the chunked greedy scan of nms_scan_kernel over the segment's
-// own mask; kept boxes are flagged at their segment-major position.
+// One block per (image, segment): the greedy scan over the segment's own pair mask; kept boxes are
+// flagged at their segment-major position.  Same decisions as nms_scan_kernel, different data
+// flow: that kernel PULLS, per 64-box chunk, the mask words of every box kept so far (a gather
+// over up to 3000 rows behind two dependent loads: 7 us per chunk, 330 us for the 47 chunks of an
+// RPN level at random init, with 138 SMs idle behind it inside the forward graph); this one keeps
+// the "suppressed" bitmap of the whole segment in shared memory and PUSHES into it the mask rows
+// of the <= 64 boxes a chunk has just kept (independent loads, shared-memory atomicOr), while the
+// chunk itself is resolved by one thread over the 64 diagonal words held in registers.
+constexpr int kSegMaxWords = 2048;   // boxes per segment <= 131072
 __global__ void __launch_bounds__(kScanThreads)
 nms_scan_seg_kernel(unsigned long long* __restrict__ ws, long long ws_stride_words,
                     long long keep_off_words, long long flag_off_words, int n, int max_keep,
                     const SegTable tab) {
+  __shared__ unsigned long long removed[kSegMaxWords];
   __shared__ unsigned long long diag[64];
-  __shared__ unsigned long long warp_or[kScanThreads / 32];
-  __shared__ int s_count;
+  __shared__ int newkept[64];
+  __shared__ int s_count, s_new;
   const int s = blockIdx.x % tab.L, b = blockIdx.x / tab.L;
   const int ks = tab.off[s + 1] - tab.off[s];
   const int nw = (ks + 63) >> 6;
@@ -343,34 +351,45 @@ nms_scan_seg_kernel(unsigned long long* __restrict__ ws, long long ws_stride_wor
   unsigned char* flags = reinterpret_cast<unsigned char*>(wsb + flag_off_words) + tab.off[s];
   const int lim_keep = min(max_keep, ks);
   const int t = threadIdx.x;
+  for (int w = t; w < nw; w += kScanThreads) removed[w] = 0ull;
   if (t == 0) s_count = 0;
+  unsigned long long dnext = 0ull;                 // diagonal word of box c*64 + t, one chunk ahead
+  if (t < 64 && t < ks) dnext = mask[(long long)t * nw];
   __syncthreads();
   for (int c = 0; c < nw; ++c) {
-    const int cnt0 = s_count;
-    if (cnt0 >= lim_keep) break;
-    unsigned long long acc = 0ull;
-    for (int k = t; k < cnt0; k += kScanThreads) acc |= mask[(long long)keep[k] * nw + c];
-    if (t < 64) {
-      const int i = c * 64 + t;
-      diag[t] = (i < ks) ? mask[(long long)i * nw + c] : 0ull;
-    }
-    unsigned int lo = (unsigned int)acc, hi = (unsigned int)(acc >> 32);
-    lo = __reduce_or_sync(0xffffffffu, lo);
-    hi = __reduce_or_sync(0xffffffffu, hi);
-    if ((t & 31) == 0) warp_or[t >> 5] = ((unsigned long long)hi << 32) | lo;
+    if (s_count >= lim_keep) break;
+    if (t < 64) diag[t] = dnext;
     __syncthreads();
+    if (t < 64) {                                  // prefetch the next chunk's diagonal
+      const int i = (c + 1) * 64 + t;
+      dnext = (c + 1 < nw && i < ks) ? mask[(long long)i * nw + c + 1] : 0ull;
+    }
     if (t == 0) {
-      unsigned long long rem = 0ull;
-      for (int w = 0; w < kScanThreads / 32; ++w) rem |= warp_or[w];
-      int cnt = cnt0;
+      unsigned long long d[64];
+#pragma unroll
+      for (int bb = 0; bb < 64; ++bb) d[bb] = diag[bb];
+      unsigned long long rem = removed[c];
       const int lim = min(64, ks - c * 64);
-      for (int bb = 0; bb < lim && cnt < lim_keep; ++bb) {
-        if (!((rem >> bb) & 1ull)) {
+      if (lim < 64) rem |= ~0ull << lim;           // positions past the end of the segment
+      int cnt = s_count, nn = 0;
+#pragma unroll
+      for (int bb = 0; bb < 64; ++bb) {
+        if (!((rem >> bb) & 1ull) && cnt < lim_keep) {
           keep[cnt++] = c * 64 + bb;
-          rem |= diag[bb];
+          newkept[nn++] = c * 64 + bb;
+          rem |= d[bb];
         }
       }
       s_count = cnt;
+      s_new = nn;
+    }
+    __syncthreads();
+    const int nn = s_new, nrem = nw - (c + 1);
+    for (int idx = t; idx < nn * nrem; idx += kScanThreads) {
+      const int q = idx / nrem;
+      const int w = c + 1 + (idx - q * nrem);
+      const unsigned long long v = mask[(long long)newkept[q] * nw + w];
+      if (v) atomicOr(&removed[w], v);
     }
     __syncthreads();
   }
@@ -1328,6 +1347,8 @@ int loft_nms_segmented(const float* boxes, const int* seg_off, int L, const long
   int max_ks = 0;
   for (int s = 0; s < L; ++s) max_ks = max(max_ks, seg_off[s + 1] - seg_off[s]);
   const int max_nw = (max_ks + 63) / 64;
+  LOFT_CHECK_SHAPE(max_nw <= kSegMaxWords, "nms_segmented: at most %d boxes per segment, got %d",
+                   kSegMaxWords * 64, max_ks);
   for (int b = 0; b < B; ++b) {
     unsigned long long* wsb = ws + (long long)b * stride_w;
     float* maxc = reinterpret_cast<float*>(wsb + maxc_off);
