@@ -482,11 +482,13 @@ def main():
     cur = trainer.stage(host_batches[0])
     h2d_total = trainer.staged_bytes
     torch.cuda.synchronize()
+    ms0 = torch.cuda.memory_stats(device)
     e0.record()
-    e2e_marks, host_t = [], []
+    e2e_marks, host_t, stage_t = [], [], []
     for j in range(args.steps):
         host_t.append(time.perf_counter())
         nxt = trainer.stage(host_batches[(j + 1) % N_ROTATE])    # next batch's copies overlap
+        stage_t.append(time.perf_counter() - host_t[-1])
         h2d_total += trainer.staged_bytes if j + 1 < args.steps else 0
         trainer.train_step(cur, read_logs='async', prefetch=nxt)   # D2H of every step's loss
         cur = nxt                                # vector, read one step late
@@ -506,6 +508,12 @@ def main():
               ' '.join(f'{(b - a) * 1e3:.1f}' for a, b in zip(host_t[:-1], host_t[1:])),
               file=sys.stderr)
     e2e_sorted = sorted(e2e_seq)
+    ms1 = torch.cuda.memory_stats(device)
+    e2e_diag = {k: int(ms1.get(k, 0) - ms0.get(k, 0))
+                for k in ('num_device_alloc', 'num_device_free', 'num_alloc_retries',
+                          'num_sync_all_streams')}
+    e2e_diag['stage_host_ms_max'] = round(max(stage_t) * 1e3, 3)
+    e2e_diag['reserved_gb'] = round(ms1.get('reserved_bytes.all.current', 0) / 2 ** 30, 2)
     h2d_bytes = h2d_total // args.steps
     t = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
     if world > 1:
@@ -562,7 +570,7 @@ def main():
                             'max': round(e2e_sorted[-1], 3), 'min': round(e2e_sorted[0], 3),
                             'host_p50': round(e2e_host[len(e2e_host) // 2], 3),
                             'host_max': round(e2e_host[-1], 3)},
-                'warmup': e2e_warm,
+                'warmup': e2e_warm, 'allocator': e2e_diag,
                 'note': 'inputs staged from pinned host memory on a copy stream (prefetch of the '
                         'next batch overlaps the step); every step\'s loss vector is copied to '
                         'pinned host memory asynchronously and read one step later, the last one '

@@ -315,12 +315,20 @@ __global__ void nms_mask_seg_kernel(const float* __restrict__ boxes, const float
   unsigned long long bits = 0ull;
   const int jstart = (row == colb) ? t + 1 : 0;
   const int jend = min(64, ks - colb * 64);
+  // The decision is the reference's fl(inter / union) > thr.  The IEEE division is ~40
+  // instructions; a pair is only divided when inter is within 1e-4 (relative) of thr * union --
+  // outside that band the rounded quotient cannot land on the other side of thr.
+  const float thr_hi = thr * 1.0001f, thr_lo = thr * 0.9999f;
   for (int j = jstart; j < jend; ++j) {
     const float w = fmaxf(0.f, __fsub_rn(fminf(x2, sb[j][2]), fmaxf(x1, sb[j][0])));
     const float h = fmaxf(0.f, __fsub_rn(fminf(y2, sb[j][3]), fmaxf(y1, sb[j][1])));
     const float inter = __fmul_rn(w, h);
-    const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area, sb[j][4]), inter));
-    if (iou > thr) bits |= 1ull << j;
+    const float uni = __fsub_rn(__fadd_rn(area, sb[j][4]), inter);
+    bool over;
+    if (uni > 0.f && inter > thr_hi * uni) over = true;
+    else if (uni > 0.f && inter < thr_lo * uni) over = false;
+    else over = __fdiv_rn(inter, uni) > thr;
+    if (over) bits |= 1ull << j;
   }
   mask[(long long)i * nw + colb] = bits;
 }
