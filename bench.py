@@ -471,25 +471,23 @@ def main():
     host_batches = [to_model_inputs(make_batch(seed=rank * 100 + i, pinned=True, num_gt=gts[i]))
                     for i in range(N_ROTATE)]
     cur = trainer.stage(host_batches[0])
-    e2e_warm = max(args.warmup, N_ROTATE + 1)   # first use of the staging path (pinned copies,
-    for j in range(e2e_warm):                   # events, log buffers) and one full rotation of the
-        nxt = trainer.stage(host_batches[(j + 1) % N_ROTATE])    # batches: their tensors differ in
-                                                # size, the caching allocator grows until it has seen all
+    e2e_warm = max(args.warmup, N_ROTATE + 1)   # first use of the staging path (ring buffers, events,
+    for j in range(e2e_warm):                   # log buffers) and one full rotation of the batches
+        nxt = trainer.stage(host_batches[(j + 1) % N_ROTATE])
         trainer.train_step(cur, read_logs='async', prefetch=nxt)
         cur = nxt
     trainer.flush_logs()
     sync_all()
-    cur = trainer.stage(host_batches[0])
-    h2d_total = trainer.staged_bytes
-    torch.cuda.synchronize()
+    h2d_total = 0                               # `cur` (staged above) feeds the first timed step;
+    torch.cuda.synchronize()                    # every timed step stages exactly one batch
     ms0 = torch.cuda.memory_stats(device)
     e0.record()
     e2e_marks, host_t, stage_t = [], [], []
     for j in range(args.steps):
         host_t.append(time.perf_counter())
-        nxt = trainer.stage(host_batches[(j + 1) % N_ROTATE])    # next batch's copies overlap
+        nxt = trainer.stage(host_batches[(e2e_warm + j + 1) % N_ROTATE])   # overlaps this step
         stage_t.append(time.perf_counter() - host_t[-1])
-        h2d_total += trainer.staged_bytes if j + 1 < args.steps else 0
+        h2d_total += trainer.staged_bytes
         trainer.train_step(cur, read_logs='async', prefetch=nxt)   # D2H of every step's loss
         cur = nxt                                # vector, read one step late
         ev = torch.cuda.Event(enable_timing=True)

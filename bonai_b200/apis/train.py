@@ -284,39 +284,81 @@ class Trainer:
                        warmup_iters=c.get('warmup_iters', 0),
                        warmup_ratio=c.get('warmup_ratio', 0.1))
 
-    def stage(self, host_batch):
+    def stage(self, host_batch, slots=3):
         """Copy a (pinned) host batch to the device on a dedicated copy stream, like a prefetching
         data loader would: the copies overlap the previous step's backward and the returned batch
         carries the event the compute streams wait on.  Accepts the reference's input dict
-        (img, gt_bboxes, gt_labels, gt_masks, gt_offsets; lists of tensors or BitmapMasks)."""
+        (img, gt_bboxes, gt_labels, gt_masks, gt_offsets; lists of tensors or BitmapMasks).
+
+        The device side is a ring of `slots` persistent byte buffers (grown on demand, then
+        stable): the tensors of a staged batch are views into one of them, so the steady state
+        makes no allocator calls at all (fresh `Tensor.to()` allocations on the copy stream with
+        `record_stream` kept the caching allocator creating segments -- `cudaMalloc`, 10-100 ms on
+        the launch thread -- whenever the rotation's tensor sizes changed).  A slot is reused only
+        after the step that consumed it has finished (event recorded by `train_step`); a staged
+        batch that was never passed to `train_step` keeps its buffer and the slot gets a new one."""
         from ..core import BitmapMasks
         dev = self.store.device
         if not hasattr(self, '_copy_stream'):
             self._copy_stream = torch.cuda.Stream(device=dev)
-        out, nbytes = {}, 0
+        ring = self.__dict__.setdefault('_stage_ring', None)
+        if ring is None or len(ring['bufs']) != slots:
+            ring = self._stage_ring = dict(bufs=[None] * slots, done=[None] * slots,
+                                           pending=[False] * slots, i=0)
+        k = ring['i']
+        ring['i'] = (k + 1) % slots
+        # layout: every tensor at a 256-byte aligned offset of the slot's buffer
+        plan, off = [], 0
 
-        def mv(t):
-            nonlocal nbytes
+        def add(t):
+            nonlocal off
+            src = t
             if isinstance(t, BitmapMasks):
                 src = t._t if t._t is not None else torch.from_numpy(t._np)
-                nbytes += src.numel() * src.element_size()
-                return BitmapMasks(src.to(dev, non_blocking=True), t.height, t.width)
-            if isinstance(t, torch.Tensor):
-                nbytes += t.numel() * t.element_size()
-                return t.to(dev, non_blocking=True)
-            return t
+            if not isinstance(src, torch.Tensor):
+                return None
+            nb = src.numel() * src.element_size()
+            plan.append((src, off, nb))
+            off = (off + nb + 255) // 256 * 256
+            return len(plan) - 1
 
+        index = {}
+        for key, v in host_batch.items():
+            if key == 'img_metas':
+                continue
+            index[key] = [add(t) for t in v] if isinstance(v, (list, tuple)) else add(v)
+        nbytes = sum(p[2] for p in plan)
+        if ring['pending'][k]:              # staged but never consumed: leave its memory alone
+            ring['bufs'][k], ring['done'][k] = None, None
+        buf = ring['bufs'][k]
+        if buf is None or buf.numel() < off:
+            buf = ring['bufs'][k] = torch.empty(int(off * 1.25) + 256, dtype=torch.uint8, device=dev)
+            ring['done'][k] = None
+        views = []
         with torch.cuda.stream(self._copy_stream):
-            for k, v in host_batch.items():
-                out[k] = [mv(t) for t in v] if isinstance(v, (list, tuple)) and k != 'img_metas' \
-                    else mv(v)
-            out['ready_event'] = self._copy_stream.record_event()
-        main = torch.cuda.current_stream(dev)
-        for k, v in out.items():
-            for t in (v if isinstance(v, list) else [v]):
-                t = t._t if isinstance(t, BitmapMasks) else t
-                if isinstance(t, torch.Tensor):
-                    t.record_stream(main)
+            if ring['done'][k] is not None:
+                self._copy_stream.wait_event(ring['done'][k])
+            for src, o, nb in plan:
+                dst = buf[o:o + nb].view(src.dtype).view(src.shape)
+                dst.copy_(src, non_blocking=True)
+                views.append(dst)
+            ready = self._copy_stream.record_event()
+        out = {}
+        for key, v in host_batch.items():
+            if key == 'img_metas':
+                out[key] = v
+                continue
+            ix = index[key]
+
+            def get(i, t):
+                if i is None:
+                    return t
+                return BitmapMasks(views[i], t.height, t.width) if isinstance(t, BitmapMasks) \
+                    else views[i]
+            out[key] = [get(i, t) for i, t in zip(ix, v)] if isinstance(ix, list) else get(ix, v)
+        out['ready_event'] = ready
+        out['_stage_slot'] = k
+        ring['pending'][k] = True
         self.staged_bytes = nbytes
         return out
 
@@ -327,6 +369,10 @@ class Trainer:
         targets) is issued right after this step's optimizer launch, when the launch thread would
         otherwise wait for the GPU to finish the backward."""
         model = self.model
+        slot = None
+        if '_stage_slot' in data:                    # a batch from `stage`: its ring slot
+            data = dict(data)
+            slot = data.pop('_stage_slot')
         at_fwd = prefetch is not None and hasattr(model, 'prefetch') and \
             os.environ.get('LOFT_PREFETCH', '1') != '0' and \
             os.environ.get('LOFT_PREFETCH_AT', 'step_end') == 'forward'
@@ -361,6 +407,11 @@ class Trainer:
                 self._exchange_rest()
         self.store.sgd_step(self.current_lr(), self.momentum, self.weight_decay, self.max_norm,
                             grad_scale=1.0 / self.world)
+        if slot is not None and getattr(self, '_stage_ring', None) is not None and \
+                slot < len(self._stage_ring['done']):
+            # every reader of the staged tensors is ordered before this point of the main stream
+            self._stage_ring['done'][slot] = torch.cuda.current_stream().record_event()
+            self._stage_ring['pending'][slot] = False
         self.iter += 1
         self._gc_policy()
         if self.iters_per_epoch and self.iter % self.iters_per_epoch == 0:

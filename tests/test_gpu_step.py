@@ -409,3 +409,66 @@ def test_graph_captured_proposals_equal_eager(full_size):
         assert torch.equal(a, b)
         assert int(a._loft_num_valid) == int(b._loft_num_valid) == c.shape[0]
         assert torch.equal(a[:c.shape[0]], c)
+
+
+def test_stage_ring_keeps_unconsumed_batches_and_matches_resident_inputs():
+    """Trainer.stage: staged tensors are views into a ring of persistent device buffers.  A batch
+    that was never passed to train_step is not overwritten when its slot comes round again; a
+    consumed slot is reused (no new buffer); and a step on staged inputs gives the losses of the
+    same step on device-resident inputs."""
+    from bonai_b200 import Config
+    from bonai_b200.apis import Trainer
+    from bonai_b200.core import BitmapMasks
+    from bonai_b200.models import build_detector
+    from oracle import loft_cpu as O
+    cfg = Config.fromfile(os.path.join(ROOT, 'configs', 'loft', 'loft_foa_r50_fpn_2x_b200.py'))
+    metas = [dict(img_shape=(256, 256, 3), pad_shape=(256, 256, 3), scale_factor=1.0, flip=False)]
+
+    def host_batch(seed, g):
+        img, gb, gl, gm, go = O.make_inputs(seed, 1, 256, g)
+        pin = lambda t: t.contiguous().pin_memory()
+        return dict(img=pin(img), img_metas=metas, gt_bboxes=[pin(b) for b in gb],
+                    gt_labels=[pin(l) for l in gl],
+                    gt_masks=[BitmapMasks(pin(m), 256, 256) for m in gm],
+                    gt_offsets=[pin(o) for o in go])
+
+    def same(staged, host):
+        torch.cuda.synchronize()
+        ok = torch.equal(staged['img'].cpu(), host['img'])
+        for k in ('gt_bboxes', 'gt_labels', 'gt_offsets'):
+            ok = ok and all(torch.equal(a.cpu(), b) for a, b in zip(staged[k], host[k]))
+        return ok and all(torch.equal(a._t.cpu(), b._t) for a, b in
+                          zip(staged['gt_masks'], host['gt_masks']))
+
+    def make_trainer():
+        torch.manual_seed(0)
+        model = build_detector(cfg.model, train_cfg=cfg.train_cfg, test_cfg=cfg.test_cfg)
+        model.train()
+        return Trainer(model, cfg, torch.device('cuda:0'))
+
+    hosts = [host_batch(s, g) for s, g in ((0, 5), (1, 9), (2, 3), (3, 7), (4, 6))]
+    tr = make_trainer()
+    staged = [tr.stage(h) for h in hosts[:4]]        # 3 slots: the 4th call meets an unconsumed slot
+    assert all(same(s, h) for s, h in zip(staged, hosts))
+    logs_a = tr.train_step(staged[3], read_logs=True)            # consumes slot 0's new buffer
+    s4 = tr.stage(hosts[4])                                      # slot 1: still unconsumed -> new buffer
+    assert same(staged[1], hosts[1]) and same(s4, hosts[4])
+    tr.train_step(s4, read_logs=True)
+    s5 = tr.stage(hosts[0])                                      # slot 2: unconsumed as well
+    tr.train_step(s5, read_logs=True)
+    again = tr.stage(hosts[1])                                   # slot 0 again: consumed -> reused
+    p0 = tr._stage_ring['bufs'][0].data_ptr()
+    tr.train_step(again, read_logs=True)
+    tr.stage(hosts[2]); tr.stage(hosts[3])
+    tr.train_step(tr.stage(hosts[0]), read_logs=True)
+    assert tr._stage_ring['bufs'][0].data_ptr() == p0
+    # same first step from device-resident inputs
+    tr2 = make_trainer()
+    h = hosts[3]
+    res = dict(img=h['img'].cuda(), img_metas=metas, gt_bboxes=[b.cuda() for b in h['gt_bboxes']],
+               gt_labels=[l.cuda() for l in h['gt_labels']],
+               gt_masks=[BitmapMasks(m._t.cuda(), 256, 256) for m in h['gt_masks']],
+               gt_offsets=[o.cuda() for o in h['gt_offsets']])
+    logs_b = tr2.train_step(res, read_logs=True)
+    for k in ('loss_rpn_cls', 'loss_rpn_bbox'):
+        assert abs(logs_a[k] - logs_b[k]) <= 1e-6 * max(1.0, abs(logs_b[k])), k
