@@ -416,13 +416,17 @@ def main():
     for _ in range(args.warmup):
         trainer.train_step(batches[it % N_ROTATE], prefetch=batches[(it + 1) % N_ROTATE])
         it += 1
-    sync_all()
+    # everything that takes host time (NVML initialisation is 10-50 ms) happens BEFORE the barrier:
+    # a rank that leaves the barrier and starts its timed region late makes every other rank wait
+    # in the first gradient exchange, and the reported time is the maximum over ranks
     how = os.environ.get('LOFT_CLOCKS', 'nvml')
-    clocks = ClockSampler(local) if how == 'smi' else NvmlClockSampler(local)
+    clocks = None
     if rank == 0 and how != 'off':
+        clocks = ClockSampler(local) if how == 'smi' else NvmlClockSampler(local)
         clocks.start()
-    L.LAUNCHES[0] = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    L.LAUNCHES[0] = 0
     e0.record()
     marks, n_pos_sum = [], 0
     for _ in range(args.steps):
@@ -451,7 +455,7 @@ def main():
         ts = [a.elapsed_time(b) for a, b in trainer._comm_events[-args.steps:]]
         print(f'[rank {rank}] exposed grad exchange ms/step: mean {sum(ts) / len(ts):.3f} min '
               f'{min(ts):.3f} max {max(ts):.3f}; step {ms / args.steps:.3f}', file=sys.stderr)
-    clk = clocks.stop() if (rank == 0 and how != 'off') else None
+    clk = clocks.stop() if clocks is not None else None
     logs = trainer.read_logs()
     n_pos = n_pos_sum / args.steps                      # positives per step (both tiles)
     t = torch.tensor([ms], device=device, dtype=torch.float64)
@@ -477,10 +481,9 @@ def main():
         trainer.train_step(cur, read_logs='async', prefetch=nxt)
         cur = nxt
     trainer.flush_logs()
-    sync_all()
     h2d_total = 0                               # `cur` (staged above) feeds the first timed step;
-    torch.cuda.synchronize()                    # every timed step stages exactly one batch
-    ms0 = torch.cuda.memory_stats(device)
+    ms0 = torch.cuda.memory_stats(device)       # every timed step stages exactly one batch
+    sync_all()
     e0.record()
     e2e_marks, host_t, stage_t = [], [], []
     for j in range(args.steps):
