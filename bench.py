@@ -474,10 +474,11 @@ def main():
     # a prefetching loader feeds it) and the loss vector read back every step
     host_batches = [to_model_inputs(make_batch(seed=rank * 100 + i, pinned=True, num_gt=gts[i]))
                     for i in range(N_ROTATE)]
-    cur = trainer.stage(host_batches[0])
+    mw = os.environ.get('LOFT_STAGE_MASK_WINDOWS', '1') != '0'
+    cur = trainer.stage(host_batches[0], mask_windows=mw)
     e2e_warm = max(args.warmup, N_ROTATE + 1)   # first use of the staging path (ring buffers, events,
     for j in range(e2e_warm):                   # log buffers) and one full rotation of the batches
-        nxt = trainer.stage(host_batches[(j + 1) % N_ROTATE])
+        nxt = trainer.stage(host_batches[(j + 1) % N_ROTATE], mask_windows=mw)
         trainer.train_step(cur, read_logs='async', prefetch=nxt)
         cur = nxt
     trainer.flush_logs()
@@ -488,7 +489,7 @@ def main():
     e2e_marks, host_t, stage_t = [], [], []
     for j in range(args.steps):
         host_t.append(time.perf_counter())
-        nxt = trainer.stage(host_batches[(e2e_warm + j + 1) % N_ROTATE])   # overlaps this step
+        nxt = trainer.stage(host_batches[(e2e_warm + j + 1) % N_ROTATE], mask_windows=mw)
         stage_t.append(time.perf_counter() - host_t[-1])
         h2d_total += trainer.staged_bytes
         trainer.train_step(cur, read_logs='async', prefetch=nxt)   # D2H of every step's loss
@@ -572,6 +573,16 @@ def main():
                             'host_p50': round(e2e_host[len(e2e_host) // 2], 3),
                             'host_max': round(e2e_host[-1], 3)},
                 'warmup': e2e_warm, 'allocator': e2e_diag,
+                'mask_transfer': ('gt-box windows of the host bitmaps (Trainer.stage(mask_windows='
+                                  'True): a footprint bitmap is zero outside its box; the device '
+                                  'tensors are the full [G,1024,1024] stacks)' if mw else
+                                  'full [G,1024,1024] uint8 bitmaps'),
+                'host_input_bytes_per_step': int(sum(
+                    sum(t.numel() * t.element_size() for t in (v if isinstance(v, list) else [v])
+                        if isinstance(t, torch.Tensor)) +
+                    sum(m._t.numel() for m in (v if isinstance(v, list) else [])
+                        if hasattr(m, '_t') and m._t is not None)
+                    for k, v in host_batches[0].items() if k != 'img_metas')),
                 'note': 'inputs staged from pinned host memory on a copy stream (prefetch of the '
                         'next batch overlaps the step); every step\'s loss vector is copied to '
                         'pinned host memory asynchronously and read one step later, the last one '

@@ -29,6 +29,13 @@ int loft_abi_version(void);
  * all-reduce run beside the trunk backward (mmdet/apis/train.py:75-79, DDP overlap).  Returns the
  * previous setting.  Grid sizes are baked into captured CUDA graphs at capture time. */
 int loft_reserve_sms(int n);
+/* host -> device transfer of the gt-box windows (box grown by `pad` pixels, clipped) of a pinned
+ * uint8 bitmap stack [G, H, W] into the same positions of a zeroed dense device stack; boxes_dev is
+ * the device copy of the [G, 4] gt boxes.  The input transfer of BitmapMasks
+ * (mmdet/core/mask/structures.py:20-60) for masks that vanish outside their boxes */
+int loft_h2d_mask_windows(const unsigned char* src_host, const float* boxes_dev,
+                          unsigned char* dst_dev, int G, int H, int W, int pad,
+                          cudaStream_t stream);
 
 /* Fused epilogue of the dense kernels.  For pixel p, channel c:
  *   acc = sum_k ...;  if (raw_out) raw_out[p,c] = acc;           (pre-BN conv output)

@@ -472,3 +472,37 @@ def test_stage_ring_keeps_unconsumed_batches_and_matches_resident_inputs():
     logs_b = tr2.train_step(res, read_logs=True)
     for k in ('loss_rpn_cls', 'loss_rpn_bbox'):
         assert abs(logs_a[k] - logs_b[k]) <= 1e-6 * max(1.0, abs(logs_b[k])), k
+
+
+def test_stage_mask_windows_gives_the_full_bitmaps():
+    """Trainer.stage(mask_windows=True) moves only the gt-box windows of the host bitmaps; the
+    device stacks equal the full host stacks (masks vanish outside their boxes), also for boxes
+    touching the tile border and for an image without GT."""
+    from bonai_b200 import Config
+    from bonai_b200.apis import Trainer
+    from bonai_b200.core import BitmapMasks
+    from bonai_b200.models import build_detector
+    from oracle import loft_cpu as O
+    cfg = Config.fromfile(os.path.join(ROOT, 'configs', 'loft', 'loft_foa_r50_fpn_2x_b200.py'))
+    torch.manual_seed(0)
+    model = build_detector(cfg.model, train_cfg=cfg.train_cfg, test_cfg=cfg.test_cfg)
+    model.train()
+    tr = Trainer(model, cfg, torch.device('cuda:0'))
+    from bonai_b200.datasets import make_inputs
+    img, gb, gl, gm, go = make_inputs(3, 2, 320, (40, 0))
+    assert int(gm[0].sum()) > 0
+    pin = lambda t: t.contiguous().pin_memory()
+    metas = [dict(img_shape=(320, 320, 3), pad_shape=(320, 320, 3), scale_factor=1.0, flip=False)] * 2
+    host = dict(img=pin(img), img_metas=metas, gt_bboxes=[pin(b) for b in gb],
+                gt_labels=[pin(l) for l in gl], gt_masks=[BitmapMasks(pin(m), 320, 320) for m in gm],
+                gt_offsets=[pin(o) for o in go])
+    for _ in range(4):                                   # every ring slot, reused once
+        st = tr.stage(host, mask_windows=True)
+        torch.cuda.synchronize()
+        for a, b in zip(st['gt_masks'], gm):
+            assert torch.equal(a._t.cpu(), b)
+        assert tr.staged_bytes < 0.5 * sum(m.numel() for m in gm) + img.numel() * 4 + 4096
+        tr.train_step(st)
+    full = tr.stage(host)
+    torch.cuda.synchronize()
+    assert all(torch.equal(a._t.cpu(), b) for a, b in zip(full['gt_masks'], gm))
