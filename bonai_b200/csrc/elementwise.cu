@@ -808,6 +808,38 @@ __global__ void rot90_kernel(const float* __restrict__ x, float* __restrict__ y,
   }
 }
 
+// out = round?(a + b) over [rows, C] and colsum[c] += sum over rows of out[., c] in the same pass
+// (the FPN output convs' bias gradients are the per-channel sums of the gradient maps the trunk
+// assembles with this add: a separate read-only pass over 178 MB otherwise).  256 % (C/4) == 0, so
+// a thread's float4 column is fixed across its grid-stride loop.
+__global__ void __launch_bounds__(256)
+add_colsum_kernel(const float4* __restrict__ a, const float4* __restrict__ b,
+                  float4* __restrict__ out, long long n4, int C4, float* __restrict__ colsum,
+                  int round) {
+  __shared__ float s_sum[256 * 4];
+  for (int i = threadIdx.x; i < C4 * 4; i += 256) s_sum[i] = 0.f;
+  __syncthreads();
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const long long stride = (long long)gridDim.x * 256;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n4; i += stride) {
+    const float4 x = a[i], y = b[i];
+    float4 v = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
+    if (round) {
+      v.x = tf32_rna(v.x); v.y = tf32_rna(v.y); v.z = tf32_rna(v.z); v.w = tf32_rna(v.w);
+    }
+    out[i] = v;
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  const int c = (threadIdx.x % C4) * 4;
+  atomicAdd(&s_sum[c + 0], acc.x);
+  atomicAdd(&s_sum[c + 1], acc.y);
+  atomicAdd(&s_sum[c + 2], acc.z);
+  atomicAdd(&s_sum[c + 3], acc.w);
+  __syncthreads();
+  for (int i = threadIdx.x; i < C4 * 4; i += 256)
+    if (s_sum[i] != 0.f) atomicAdd(&colsum[i], s_sum[i]);
+}
+
 __global__ void add_kernel(const float* __restrict__ a, const float* __restrict__ b,
                            float* __restrict__ out, long long n, int round) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
@@ -1185,6 +1217,20 @@ int loft_add(const float* a, const float* b, float* out, long long n, int round_
   if (n == 0) return LOFT_OK;
   add_kernel<<<grid_for(n), kT, 0, stream>>>(a, b, out, n, round_tf32);
   LOFT_CUDA_LAUNCH_CHECK("add");
+  return LOFT_OK;
+}
+
+int loft_add_colsum(const float* a, const float* b, float* out, long long rows, int C,
+                    float* colsum, int round_tf32, cudaStream_t stream) {
+  LOFT_CHECK_ARG(a && b && out && colsum, "add_colsum: null pointer");
+  LOFT_CHECK_SHAPE(C % 4 == 0 && C >= 4 && C <= 1024 && 256 % (C / 4) == 0,
+                   "add_colsum: C=%d (C/4 must divide 256)", C);
+  if (rows == 0) return LOFT_OK;
+  const long long n4 = rows * (C / 4);
+  add_colsum_kernel<<<grid_for(n4, kT, 148 * 8), 256, 0, stream>>>(
+      reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b),
+      reinterpret_cast<float4*>(out), n4, C / 4, colsum, round_tf32);
+  LOFT_CUDA_LAUNCH_CHECK("add_colsum");
   return LOFT_OK;
 }
 

@@ -343,18 +343,36 @@ class _Program:
         n = len(self.lat)
         with self.bwd:
             gtot = self.B
+            # The bias gradient of FPN output conv l is the per-channel sum of gtot[l]: it rides on
+            # the LAST add that completes gtot[l] (add_colsum) instead of a read-only pass of its own.
+            last_fold = {l - 1 for l in range(nlev - 1, n - 1, -1)}      # levels an extra level folds into
+
+            def add_into(l, other, final):
+                Nf, Hf, Wf, Cf = self.P[l].shape
+                bg = neck._out[l].bias_grad if l < n else None
+                if final and bg is not None and Cf % 4 == 0 and 256 % (Cf // 4) == 0:
+                    L.call('add_colsum', L.ptr(gtot[l]), L.ptr(other), L.ptr(gtot[l]),
+                           L.ll(Nf * Hf * Wf), i32(Cf), L.ptr(bg), i32(1), L.stream())
+                    return True
+                L.call('add', L.ptr(gtot[l]), L.ptr(other), L.ptr(gtot[l]), L.ll(gtot[l].numel()),
+                       i32(1), L.stream())
+                return False
+
+            summed = set()
             for l in range(len(self.S)):       # what the RoI heads sent (RoIAlign backward sinks)
-                L.call('add', L.ptr(gtot[l]), L.ptr(self.S[l]), L.ptr(gtot[l]),
-                       L.ll(gtot[l].numel()), i32(1), L.stream())
+                if add_into(l, self.S[l], final=l not in last_fold):
+                    summed.add(l)
             # extra levels (P6 = P5-out subsampled): fold their gradient into the level below
             for l in range(nlev - 1, n - 1, -1):
                 Nf, Hf, Wf, Cf = self.P[l - 1].shape
                 u = self.buf(Nf, Hf, Wf, Cf)
                 L.call('subsample2_bwd', L.ptr(gtot[l]), L.ptr(u), None, i32(Nf), i32(Hf), i32(Wf),
                        i32(Cf), L.stream())
-                L.call('add', L.ptr(gtot[l - 1]), L.ptr(u), L.ptr(gtot[l - 1]),
-                       L.ll(u.numel()), i32(1), L.stream())
+                if add_into(l - 1, u, final=True):      # a level is folded into once, after its sink
+                    summed.add(l - 1)
             for l in range(n):
+                if l in summed:
+                    continue
                 Nf, Hf, Wf, Cf = self.P[l].shape
                 self.colsum(gtot[l], Nf * Hf * Wf, Cf, neck._out[l].bias_grad)
             # FPN 3x3 output convs, fine -> coarse (the top-down path's gradient flows that way)

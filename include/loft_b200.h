@@ -197,6 +197,9 @@ int loft_sum2x2_add(const float* fine, const float* base, float* out, int N, int
 int loft_rot90(const float* x, float* y, long long K, int S, int C, int k, cudaStream_t stream);
 int loft_add(const float* a, const float* b, float* out, long long n, int round_tf32,
              cudaStream_t stream);
+/* out = a + b over [rows, C] with colsum[c] += sum_rows out[., c] in the same pass (C/4 | 256) */
+int loft_add_colsum(const float* a, const float* b, float* out, long long rows, int C,
+                    float* colsum, int round_tf32, cudaStream_t stream);
 int loft_grad_sqnorm(const float* g, long long n, double* out, cudaStream_t stream);
 int loft_sgd_clip_step(float* p, const float* g, float* m, float* p_tf32, long long n, float lr,
                        float momentum, float weight_decay, float max_norm, float grad_scale,
