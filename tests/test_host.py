@@ -321,3 +321,68 @@ def test_synthetic_inputs_equal_the_oracles_recipe():
     assert torch.equal(a[0], b[0])
     for x, y in zip(a[1:], b[1:]):
         assert all(torch.equal(u, v) for u, v in zip(x, y))
+
+
+def test_batched_copies_collects_copy2d_into_one_call(monkeypatch):
+    """_lib.batched_copies: every call('copy2d') inside the block becomes one job of a single
+    loft_copy2d_multi launch at its end; other entry points run immediately; a recording launch
+    program (trunk.Tape) and nesting pass straight through."""
+    from bonai_b200 import _lib as L
+    calls = []
+
+    class Fake:
+        def __getattr__(self, name):
+            def fn(*a):
+                calls.append((name, a))
+                return 0
+            return fn
+    monkeypatch.setattr(L, 'lib', lambda: Fake())
+    i32, ll, vp = ctypes.c_int, ctypes.c_longlong, ctypes.c_void_p
+    st = vp(7)
+
+    def cp(src, dst, rows, cols, acc):
+        L.call('copy2d', vp(src), ll(cols), vp(dst), ll(cols), ll(rows), i32(cols), i32(acc), i32(0), st)
+
+    with L.batched_copies():
+        cp(0x1000, 0x2000, 3, 256, 0)
+        L.call('fill', vp(0x3000), ll(16), ctypes.c_float(0.0), st)       # not a copy: runs now
+        with L.batched_copies():                                          # nested: same batch
+            cp(0x1100, 0x2100, 1, 12, 1)
+        assert [c[0] for c in calls] == ['loft_fill']
+    assert [c[0] for c in calls] == ['loft_fill', 'loft_copy2d_multi']
+    arr, n, stream = calls[-1][1]
+    assert n.value == 2 and stream.value == 7
+    assert (arr[0].src, arr[0].dst, arr[0].rows, arr[0].cols, arr[0].accumulate) == \
+        (0x1000, 0x2000, 3, 256, 0)
+    assert (arr[1].src, arr[1].dst, arr[1].lds, arr[1].ldd, arr[1].accumulate) == \
+        (0x1100, 0x2100, 12, 12, 1)
+    calls.clear()
+    with L.batched_copies():                                              # nothing collected
+        pass
+    assert calls == []
+    rec = []
+    monkeypatch.setattr(L, 'RECORD', rec)
+    with L.batched_copies():                                              # recording: not deferred
+        cp(0x1000, 0x2000, 3, 256, 0)
+        assert [c[0] for c in calls] == ['loft_copy2d'] and rec[0][0] == 'copy2d'
+
+
+def test_offset_branch_shares_the_bbox_roi_features(model):
+    """The LOFT config's offset extractor is the bbox extractor (same RoIAlign, strides, scale):
+    LoftRoIHead feeds the offset head from the bbox features' rows; a different extractor or the
+    LOFT_SHARE_OFFSET_ROI=0 switch keeps the separate RoIAlign."""
+    rh = model.roi_head
+    assert rh._shares_bbox_rois()
+    os.environ['LOFT_SHARE_OFFSET_ROI'] = '0'
+    try:
+        assert not rh._shares_bbox_rois()
+    finally:
+        del os.environ['LOFT_SHARE_OFFSET_ROI']
+    saved = rh.offset_roi_extractor.featmap_strides
+    rh.offset_roi_extractor.featmap_strides = [4, 8, 16]
+    try:
+        assert not rh._shares_bbox_rois()
+    finally:
+        rh.offset_roi_extractor.featmap_strides = saved
+    assert not rh.mask_roi_extractor.roi_layers[0].output_size == \
+        rh.bbox_roi_extractor.roi_layers[0].output_size
