@@ -247,6 +247,18 @@ def roofline_probe(model, device, pk, n_pos, ms_per_step):
                              'profiles/r02_ncu_kernels.txt',
                 algorithmic_bytes=2 * G * P * S * S * C * 4 + G * 9 * C * C * 4,
                 peak_source=f"{pk['source']} bf16 dense burst; TF32 operands run at half that rate")
+    # Operand bytes the SMs must receive from L2 for this launch with the kernel's tiling (pair
+    # tile = 256 channels x 2 x 2 whole 7x7 maps; per k-block each CTA stages 16 KB of weights and
+    # its 98 pixel rows): equals ncu's l1tex__m_xbar2l1tex_read_bytes (883 MB at P=210,
+    # profiles/r02_ncu_kernels.txt).  The chip-wide L2 delivery cap is ~6300 B/cycle
+    # (B300_MICROARCH) = 12.4 TB/s at 1965 MHz: THAT is what bounds the wide TF32 tiles.
+    cap = 6300 * 1.965e9 / 1e12
+    deliv = G * ((P + 3) // 4) * 72 * 2 * (16384 + 98 * 128)
+    roof['l2_to_sm'] = dict(bytes=deliv, achieved_TBps=round(deliv / (tf * 1e-3) / 1e12, 2),
+                            cap_TBps=round(cap, 2),
+                            frac=round(deliv / (tf * 1e-3) / 1e12 / cap, 4),
+                            note='operand bytes delivered L2 -> SM per launch / launch time, against '
+                                 'the measured chip-wide L2 delivery cap (DESIGN 3.1, finding 4)')
     # largest single launch
     N, H, W = BATCH, IMG // 4, IMG // 4
     x2 = torch.randn(N, H, W, C, device=device)
@@ -267,6 +279,10 @@ def roofline_probe(model, device, pk, n_pos, ms_per_step):
                   traffic_note='dram__bytes_read.sum + dram__bytes_write.sum per launch (136.78 + '
                                '88.42 MB), ncu --set full, profiles/r02_ncu_kernels.txt',
                   algorithmic_bytes=2 * N * H * W * C * 4 + 9 * C * C * 4)
+    deliv2 = (N * H * W // 256) * 72 * 2 * (16384 + 128 * 128)    # pair tiles of 256 ch x 256 px
+    second['l2_to_sm'] = dict(bytes=deliv2, achieved_TBps=round(deliv2 / (t2 * 1e-3) / 1e12, 2),
+                              cap_TBps=round(cap, 2),
+                              frac=round(deliv2 / (t2 * 1e-3) / 1e12 / cap, 4))
     return roof, second
 
 
